@@ -1,0 +1,66 @@
+"""Loader for the sequential CPU model of the GPU deflate (tests/model/deflate_model.c). Test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "model", "deflate_model.c")
+SO = os.path.join(HERE, "model", "libdeflate_model.so")
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("bpp", "hash_bits", "ways", "lane_cap", "too_far", "lazy", "cont_min",
+                                         "prime_bytes", "capped_wins", "inwin", "cont_maxd", "sub_bytes", "hash2_bytes",
+                                         "hash2_bits", "noisy_thresh", "noisy_minlen", "noisy_neard", "cost_maxlen",
+                                         "cost_margin", "cost_warm", "hash2_ways")] + [("block_bytes", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("tokens", C.c_int64), ("blocks", C.c_int64), ("stored_blocks", C.c_int64)]
+
+
+# the configuration csrc/deflate_lz.cu + deflate_huff.cu implement
+KERNEL_PARAMS = dict(bpp=3, hash_bits=11, ways=2, lane_cap=64, too_far=32768, lazy=16, cont_min=258, prime_bytes=32768,
+                     capped_wins=1, inwin=0, cont_maxd=1, noisy_thresh=0, noisy_minlen=6, noisy_neard=0, cost_maxlen=8,
+                     cost_margin=0, cost_warm=64, hash2_ways=2, hash2_bytes=6, hash2_bits=10, sub_bytes=32768,
+                     block_bytes=512 * 1024)
+
+
+def load():
+    if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", SO, SRC], check=True)
+    lib = C.CDLL(SO)
+    lib.dm_deflate_page.restype = C.c_int64
+    lib.dm_deflate_page.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Params), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+    lib.dm_lz_subchunk.restype = C.c_int64
+    lib.dm_lz_subchunk.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Params), C.c_void_p, C.c_void_p]
+    return lib
+
+
+def deflate(lib, stream: bytes, **kw):
+    p = dict(KERNEL_PARAMS); p.update(kw)
+    P = Params(**p)
+    src = np.concatenate([np.frombuffer(stream, np.uint8), np.zeros(512, np.uint8)])
+    out = np.zeros(len(stream) + len(stream) // 8 + 4096, np.uint8)
+    st = Stats()
+    n = lib.dm_deflate_page(src.ctypes.data, len(stream), C.byref(P), out.ctypes.data, None, C.byref(st))
+    return out[:n].tobytes(), st
+
+
+def lz_tokens(lib, stream: bytes, **kw):
+    """Per sub-chunk token lists as the kernel lays them out: list of (tokens uint32 array, hist[316])."""
+    p = dict(KERNEL_PARAMS); p.update(kw)
+    P = Params(**p)
+    F = len(stream)
+    src = np.concatenate([np.frombuffer(stream, np.uint8), np.zeros(512, np.uint8)])
+    res = []
+    for bs in range(0, F, p["block_bytes"]):
+        be = min(F, bs + p["block_bytes"])
+        for s in range(bs, be, p["sub_bytes"]):
+            e = min(be, s + p["sub_bytes"])
+            tok = np.zeros(e - s + 64, np.uint32); hist = np.zeros(316, np.uint32)
+            n = lib.dm_lz_subchunk(src.ctypes.data, F, s, e, C.byref(P), tok.ctypes.data, hist.ctypes.data)
+            res.append((tok[:n].copy(), hist))
+    return res

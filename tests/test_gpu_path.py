@@ -1,0 +1,180 @@
+"""GPU: the whole path through the public function (prepare_page / prepare_pages -> vcp_prepare_batch)
+against the reference's CPU path (Pillow): pixels bit-exact, filter bytes equal, base64 exact, size <= 1.05 x."""
+import base64
+import io
+import threading
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import pillow_path as PP
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def V():
+    import vision_compression_project_b200 as v
+    return v
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from vision_compression_project_b200 import synth as s
+    return s
+
+
+def test_c1_reference_page(V, ref_page, fixtures):
+    """BASELINE configs[0]: output/page_1.png through save + base64."""
+    r = V.prepare_page(ref_page)
+    ours, ref = U.check_png_against(r.png, ref_page)
+    U.check_b64(r.png, r.b64)
+    fx = fixtures["fixtures"]["page_1.png"]
+    assert f"{r.adler32:08x}" == fx["adler32"] and r.size == tuple(fx["size"]) and r.mode == "RGB"
+    assert ours <= 1.05 * fx["pillow_png_bytes"] and ours <= 1.05 * fx["bytes"]       # vs local Pillow and vs the recorded file
+    print(f"C1: ours {ours} B, Pillow {ref} B, recorded {fx['bytes']} B")
+
+
+def test_c2_batch_letter_200(V, synth):
+    pages = synth.make_pages(8, "letter", 200, photo_every=4)
+    res = V.prepare_pages(pages)
+    tot_o = tot_r = 0
+    for im, r in zip(pages, res):
+        assert r.error is None
+        o, rf = U.check_png_against(r.png, im)
+        U.check_b64(r.png, r.b64)
+        tot_o += o; tot_r += rf
+    print(f"C2 (8 pages): ours {tot_o} B vs Pillow {tot_r} B = {tot_o / tot_r:.3f}")
+
+
+def test_c3_resize_lanczos_1568(V, synth):
+    pages = synth.make_pages(4, "letter", 300, photo_every=2)
+    res = V.prepare_pages(pages, max_side=1568)
+    for im, r in zip(pages, res):
+        _, _, exp = PP.prepare_page_cpu(im, max_side=1568)
+        assert r.size == (1212, 1568) == exp.size
+        U.check_png_against(r.png, exp)
+        U.check_b64(r.png, r.b64)
+
+
+def test_c5_mixed_sizes_modes(V, synth):
+    types = synth.mixed_page_types()
+    picks = [t for t in types if t[1] in (150, 200)][:6] + [t for t in types if t[1] == 300][:2] + [t for t in types if t[1] == 600][:2]
+    pages = [synth.make_page(i, p, d, m, c) for i, (p, d, m, c) in enumerate(picks)]
+    res = V.prepare_pages(pages, max_side=1568, reducing_gap=2.0, mode=None)
+    for im, r, t in zip(pages, res, picks):
+        assert r.error is None, (t, r.error)
+        _, _, exp = PP.prepare_page_cpu(im, max_side=1568, reducing_gap=2.0, mode=im.mode)
+        assert r.mode == im.mode and r.size == exp.size, t
+        U.check_png_against(r.png, exp)
+        U.check_b64(r.png, r.b64)
+
+
+def test_convert_modes_and_options(V):
+    rng = np.random.default_rng(21)
+    px = rng.integers(0, 256, (120, 90, 4), dtype=np.uint8)
+    px[:, :, :3] //= 8
+    rgba = Image.fromarray(px, "RGBA")
+    for src in (rgba, rgba.convert("L"), rgba.convert("LA"), rgba.convert("RGB")):
+        for mode in ("RGB", "L"):
+            r = V.prepare_page(src, mode=mode)
+            U.check_png_against(r.png, src if src.mode == mode else src.convert(mode))
+    r = V.prepare_page(rgba, mode=None)                                   # keep RGBA: colour type 6
+    U.check_png_against(r.png, rgba)
+    r = V.prepare_page(rgba.convert("RGB"), optimize=True)
+    U.check_png_against(r.png, rgba.convert("RGB"), pillow_kw={"optimize": True}, size_tol=1.10)
+    r = V.prepare_page(rgba.convert("RGB"), compress_level=0, want_base64=False)
+    assert r.b64 is None
+    U.check_png_against(r.png, rgba.convert("RGB"), pillow_kw={"compress_level": 0})
+    r = V.prepare_page(rgba.convert("RGB"), size=(200, 50), resample=V.BICUBIC)
+    U.check_png_against(r.png, rgba.convert("RGB").resize((200, 50), Image.Resampling.BICUBIC))
+
+
+def test_edge_sizes(V):
+    rng = np.random.default_rng(22)
+    for (w, h) in [(1, 1), (1, 7), (7, 1), (2, 2), (3, 1), (1365, 1), (1, 3000), (5, 5), (21846, 2), (17, 333)]:
+        for c, mode in ((1, "L"), (3, "RGB")):
+            px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+            im = Image.fromarray(px[:, :, 0] if c == 1 else px, mode)
+            r = V.prepare_page(im, mode=None)
+            U.check_png_against(r.png, im, size_tol=1.10)
+            U.check_b64(r.png, r.b64)
+    noise = Image.fromarray(rng.integers(0, 256, (700, 900, 3), dtype=np.uint8), "RGB")       # incompressible -> stored blocks
+    r = V.prepare_page(noise)
+    U.check_png_against(r.png, noise)
+    flat = Image.new("RGB", (1700, 2200), (255, 255, 255))                                     # blank page
+    r = V.prepare_page(flat)
+    U.check_png_against(r.png, flat, size_tol=1.5)
+    assert len(r.png) < 20000
+
+
+def test_input_kinds_agree(V, synth):
+    import torch
+    im = synth.make_page(5, size=(611, 407))
+    base = V.prepare_page(im).png
+    a = np.asarray(im)
+    assert V.prepare_page(a).png == base
+    assert V.prepare_page(torch.from_numpy(a.copy())).png == base
+    assert V.prepare_page(torch.from_numpy(a.copy()).cuda()).png == base
+    ppm = b"P6\n611 407\n255\n" + a.tobytes()
+    assert V.prepare_page(ppm).png == base
+    assert V.prepare_page(a.tobytes(), raw_shape=(407, 611, 3)).png == base
+    wide = np.zeros((407, 700, 3), np.uint8); wide[:, :611] = a
+    assert V.prepare_page(wide[:, :611]).png == base                      # strided rows
+    g = im.convert("L")
+    pgm = b"P5\n611 407\n255\n" + g.tobytes()
+    assert V.prepare_page(pgm, mode="L").png == V.prepare_page(g, mode="L").png
+
+
+def test_errors_and_partial_batch(V, synth):
+    good = synth.make_page(1, size=(300, 200))
+    with pytest.raises(ValueError):
+        V.prepare_page(Image.new("CMYK", (4, 4)))
+    with pytest.raises(ValueError):
+        V.prepare_page(good, mode="HSV")
+    with pytest.raises(ValueError):
+        V.prepare_page(b"not an image")
+    with pytest.raises(ValueError):
+        V.prepare_page(Image.new("RGBA", (40, 40)), mode=None, size=(20, 20))      # alpha resize is off the path
+    res = V.prepare_pages([good, Image.new("P", (4, 4)), good, b"junk"])
+    assert res[0].error is None and res[2].error is None and res[1].error and res[3].error
+    assert res[0].png == res[2].png and res[1].png is None
+    U.check_png_against(res[0].png, good)
+    assert V.prepare_pages([]) == []
+
+
+def test_five_threads_like_the_reference_pool(V, synth):
+    """pdf_extract.py:313-333 runs the per-page body on 5 worker threads."""
+    pages = [synth.make_page(i, size=(500 + 10 * i, 400)) for i in range(10)]
+    expect = [U.pillow_png(p) for p in pages]
+    out = [None] * 10
+    errs = []
+
+    def work(k):
+        try:
+            for i in range(k, 10, 5):
+                out[i] = V.prepare_page(pages[i])
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(5)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    for p, r in zip(pages, out):
+        U.check_png_against(r.png, p)
+
+
+def test_full_size_properties_c2(V, synth):
+    """Full BASELINE size (1700x2200) through size-independent properties: round trip, determinism, idempotence."""
+    pages = synth.make_pages(3, "letter", 200, photo_every=3)
+    r1 = V.prepare_pages(pages)
+    r2 = V.prepare_pages(pages)
+    for im, a, b in zip(pages, r1, r2):
+        assert a.png == b.png and a.b64 == b.b64                           # deterministic
+        dec = Image.open(io.BytesIO(base64.b64decode(a.b64))); dec.load()
+        assert dec.tobytes() == im.tobytes()                               # encode -> decode round trip
+        again = V.prepare_page(dec)
+        assert again.png == a.png                                          # idempotent on its own output
+    single = [V.prepare_page(p).png for p in pages]
+    assert single == [r.png for r in r1]                                   # batch == one at a time

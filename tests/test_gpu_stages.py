@@ -1,0 +1,190 @@
+"""GPU: every stage of libvcprep against the oracle / golden vectors, through the C ABI (stage-level symbols)."""
+import base64
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from oracle import restate as R
+from tests import model_util as M
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+FLT = {"lanczos": 1, "bilinear": 2, "bicubic": 3, "box": 4, "hamming": 5}
+
+
+@pytest.fixture(scope="module")
+def S():
+    from vision_compression_project_b200 import stages
+    return stages
+
+
+def test_convert_golden_and_modes(S, crops):
+    for ci in range(3):
+        px = crops[f"c{ci}_px"]
+        assert np.array_equal(S.convert(px, 1).cpu().numpy()[:, :, 0], crops[f"c{ci}_L"])
+    rng = np.random.default_rng(0)
+    for mode in ("L", "LA", "RGB", "RGBA"):
+        c = R.BPP[mode]
+        px = rng.integers(0, 256, (37, 53, c), dtype=np.uint8)
+        im = Image.fromarray(px[:, :, 0] if c == 1 else px, mode)
+        for dst, dc in (("RGB", 3), ("L", 1)):
+            if dst == mode:
+                continue
+            ref = np.asarray(im.convert(dst)).reshape(37, 53, dc)
+            assert np.array_equal(S.convert(px, dc).cpu().numpy(), ref), (mode, dst)
+
+
+def test_resample_golden(S, crops):
+    for ci in range(3):
+        px = crops[f"c{ci}_px"]
+        for fname, flt in FLT.items():
+            for size in [(61, 47), (131, 117)]:
+                got = S.resample(px, size, flt).cpu().numpy()
+                assert np.array_equal(got, crops[f"c{ci}_{fname}_{size[0]}x{size[1]}"]), (ci, fname, size)
+
+
+def test_resample_vs_pillow_shapes(S):
+    rng = np.random.default_rng(11)
+    cases = [((333, 517), (200, 100)), ((120, 90), (91, 121)), ((640, 480), (640, 200)), ((640, 480), (300, 480)),
+             ((50, 70), (50, 70)), ((9, 9), (1, 1)), ((1, 40), (7, 3)), ((900, 1200), (7, 5)), ((17, 3), (200, 2))]
+    for t, ((w, h), (ow, oh)) in enumerate(cases):
+        for c in (1, 3):
+            px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+            im = Image.fromarray(px[:, :, 0] if c == 1 else px, "L" if c == 1 else "RGB")
+            flt = 1 + (t + c) % 5
+            ref = np.asarray(im.resize((ow, oh), flt)).reshape(oh, ow, c)
+            got = S.resample(px, (ow, oh), flt).cpu().numpy()
+            assert np.array_equal(got, ref), ((w, h), (ow, oh), c, flt, int(np.abs(got.astype(int) - ref).max()))
+
+
+def test_resample_full_page_c3_shape(S):
+    """BASELINE config C3 geometry: 2550x3300 RGB -> 1212x1568 LANCZOS, bit-exact with Pillow."""
+    from vision_compression_project_b200 import synth
+    im = synth.make_page(3, "letter", 300, photo=True)
+    ref = np.asarray(im.resize((1212, 1568), Image.Resampling.LANCZOS))
+    got = S.resample(np.asarray(im), (1212, 1568), 1).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_reduce_golden_and_edges(S, crops):
+    for ci in range(3):
+        px = crops[f"c{ci}_px"]
+        assert np.array_equal(S.reduce(px, 2, 2).cpu().numpy(), crops[f"c{ci}_reduce2"])
+        assert np.array_equal(S.reduce(px, 3, 2).cpu().numpy(), crops[f"c{ci}_reduce3x2"])
+    rng = np.random.default_rng(2)
+    px = rng.integers(0, 256, (101, 67, 3), dtype=np.uint8)
+    im = Image.fromarray(px, "RGB")
+    for f in [(2, 2), (3, 7), (5, 1), (1, 4), (16, 16)]:
+        assert np.array_equal(S.reduce(px, f[0], f[1]).cpu().numpy(), np.asarray(im.reduce(f))), f
+
+
+def test_filter_golden_crops(S, crops):
+    for ci in range(3):
+        px = crops[f"c{ci}_px"]
+        f, ad = S.png_filter(px)
+        assert np.array_equal(f.cpu().numpy(), crops[f"c{ci}_filtered"])
+        assert ad == zlib.adler32(crops[f"c{ci}_filtered"].tobytes())
+        f, ad = S.png_filter(px, optimize=True)
+        assert np.array_equal(f.cpu().numpy(), crops[f"c{ci}_filtered_opt"])
+        f, ad = S.png_filter(crops[f"c{ci}_L"])
+        assert np.array_equal(f.cpu().numpy(), crops[f"c{ci}_L_filtered"])
+
+
+def test_filter_reference_page_recorded_decisions(S, ref_page, fixtures):
+    """All 2339 filter decisions + residuals of the reference's recorded output/page_1.png, and its Adler-32."""
+    fx = fixtures["fixtures"]["page_1.png"]
+    f, ad = S.png_filter(np.asarray(ref_page))
+    got = f.cpu().numpy()
+    assert U.sha(got.tobytes()) == fx["sha_filtered"]
+    assert f"{ad:08x}" == fx["adler32"]
+    hist = np.bincount(got.reshape(ref_page.height, -1)[:, 0], minlength=5).tolist()
+    assert hist == fx["filter_hist_NSUAP"]
+
+
+def test_filter_vs_pillow_odd_sizes(S):
+    rng = np.random.default_rng(4)
+    for t in range(60):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        mode = ["L", "RGB", "RGBA", "LA"][t % 4]
+        c = R.BPP[mode]
+        kind = t % 3
+        if kind == 0:
+            px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        elif kind == 1:
+            px = np.full((h, w, c), int(rng.integers(0, 256)), np.uint8)
+        else:
+            px = (np.add.outer(np.arange(h) * 3, np.arange(w) * 5)[:, :, None] + np.arange(c) * 17).astype(np.uint8)
+        im = Image.fromarray(px[:, :, 0] if c == 1 else px, mode)
+        for opt in (False, True):
+            ref = U.png_filtered(U.pillow_png(im, optimize=opt))
+            f, ad = S.png_filter(px, optimize=opt)
+            assert f.cpu().numpy().tobytes() == ref, (t, mode, (w, h), opt)
+            assert ad == zlib.adler32(ref)
+
+
+def test_checksums_and_base64_lengths(S):
+    rng = np.random.default_rng(9)
+    for n in [1, 2, 3, 4, 5, 11, 12, 13, 47, 48, 49, 255, 256, 257, 4095, 4096, 4097, 65535, 65536, 100003, 1 << 20, 3000001]:
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert S.adler32(d) == zlib.adler32(d), n
+        assert S.crc32(d) == zlib.crc32(d), n
+        assert S.base64(d) == base64.b64encode(d), n
+    assert S.adler32(b"\xff" * 700000) == zlib.adler32(b"\xff" * 700000)
+    assert S.crc32(bytes(5000)) == zlib.crc32(bytes(5000))
+
+
+def _streams(ref_page):
+    rng = np.random.default_rng(5)
+    filt = R.png_filter(np.asarray(ref_page.crop((0, 300, 1654, 700)))).tobytes()       # ~2 MB of real page rows
+    return {
+        "one": bytes([7]), "two": bytes(2), "three": bytes(3), "abc": b"abc" * 1000, "zeros70k": bytes(70000),
+        "noise40k": rng.integers(0, 256, 40000, dtype=np.uint8).tobytes(),
+        "lowent600k": (rng.integers(0, 4, 600000, dtype=np.uint8) * 60).tobytes(),
+        "z32768": bytes(32768), "z32769": bytes(32769), "z524288": bytes(524288), "z524289": bytes(524289),
+        "noise600k": rng.integers(0, 256, 600000, dtype=np.uint8).tobytes(),
+        "page_rows": filt,
+    }
+
+
+def test_deflate_valid_and_size(S, ref_page):
+    for name, d in _streams(ref_page).items():
+        z = S.deflate(d, bpp=3)
+        assert z[:2] == b"\x78\x9c", name
+        assert zlib.decompress(z) == d, name
+        ref = zlib.compressobj(6, zlib.DEFLATED, 15, 9, zlib.Z_FILTERED)
+        zr = ref.compress(d) + ref.flush()
+        assert len(z) <= 1.05 * len(zr) + 64, (name, len(z), len(zr))
+    z0 = S.deflate(bytes(100000), bpp=3, level=0)                                       # compress_level=0: stored
+    assert zlib.decompress(z0) == bytes(100000) and len(z0) == 2 + 100000 + 5 * 2 + 4
+
+
+def test_lz_tokens_match_sequential_model(S, ref_page):
+    """Token-for-token equality with tests/model/deflate_model.c (the sequential statement of the kernel)."""
+    lib = M.load()
+    for name, d in _streams(ref_page).items():
+        tok, ntok, hist = S.lz_tokens(d, bpp=3)
+        ref = M.lz_tokens(lib, d)
+        assert len(ref) == len(ntok), name
+        # sub-chunk j of block b starts at b*512Ki + k*32Ki
+        starts = []
+        for bs in range(0, len(d), 524288):
+            for s in range(bs, min(len(d), bs + 524288), 32768):
+                starts.append(s)
+        for j, (rt, rh) in enumerate(ref):
+            assert ntok[j] == len(rt), (name, j, int(ntok[j]), len(rt))
+            got = tok[starts[j]:starts[j] + len(rt)]
+            if not np.array_equal(got, rt):
+                k = int(np.argmax(got != rt))
+                raise AssertionError((name, j, k, hex(int(got[k])), hex(int(rt[k]))))
+            assert np.array_equal(hist[j], rh), (name, j)
+
+
+def test_deflate_bytes_match_sequential_model(S, ref_page):
+    lib = M.load()
+    for name, d in _streams(ref_page).items():
+        z = S.deflate(d, bpp=3)
+        zm, st = M.deflate(lib, d)
+        assert z == zm, (name, len(z), len(zm))

@@ -1,0 +1,11 @@
+"""vcprep — B200-native page-image preparation (convert -> resize -> PNG -> base64).
+
+The compute lives in libvcprep.so (csrc/, hand-written sm_100a CUDA behind the C ABI of include/vcprep.h);
+this package is the Python host mirror of the reference's call sites.  Importing it never touches a GPU;
+calling `prepare_page(s)` without the built library or without a B200 raises.
+"""
+from .api import (BICUBIC, BILINEAR, BOX, HAMMING, LANCZOS, PagePrep, PreparedPage, parse_pnm, prepare_page,
+                  prepare_pages, thumbnail_size)
+
+__all__ = ["prepare_page", "prepare_pages", "PagePrep", "PreparedPage", "thumbnail_size", "parse_pnm",
+           "LANCZOS", "BILINEAR", "BICUBIC", "BOX", "HAMMING"]

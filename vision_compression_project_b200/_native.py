@@ -1,0 +1,96 @@
+"""ctypes binding of libvcprep.so — mirrors include/vcprep.h one to one.  No compute happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvcprep.so")
+
+VCP_OK, VCP_EINVAL, VCP_ECUDA, VCP_ENOMEM, VCP_ESIZE = 0, -1, -2, -3, -4
+
+
+class PageDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+                ("row_stride", C.c_int64), ("dst_width", C.c_int32), ("dst_height", C.c_int32),
+                ("reduce_x", C.c_int32), ("reduce_y", C.c_int32)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("out_channels", C.c_int32), ("resample", C.c_int32), ("compress_level", C.c_int32),
+                ("optimize", C.c_int32), ("want_b64", C.c_int32), ("src_device", C.c_int32),
+                ("dst_device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PageResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+                ("png_off", C.c_uint64), ("png_len", C.c_uint64), ("b64_off", C.c_uint64), ("b64_len", C.c_uint64),
+                ("adler32", C.c_uint32), ("n_idat", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_convert", "ms_resample", "ms_filter", "ms_lz", "ms_huff",
+                                         "ms_assemble", "ms_b64", "ms_d2h", "ms_total")] + \
+               [(n, C.c_uint64) for n in ("kernel_launches", "in_bytes", "filtered_bytes", "png_bytes", "b64_bytes",
+                                          "arena_bytes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/vcprep.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "vcp_version": (C.c_int, []),
+    "vcp_last_error": (C.c_char_p, []),
+    "vcp_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vcp_destroy": (None, [C.c_void_p]),
+    "vcp_output_bound": (C.c_int, [C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vcp_prepare_batch": (C.c_int, [C.c_void_p, C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.c_void_p, C.c_uint64,
+                                    C.c_void_p, C.c_uint64, C.POINTER(PageResult)]),
+    "vcp_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "vcp_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int]),
+    "vcp_resample_coeffs": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "vcp_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "vcp_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "vcp_png_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "vcp_deflate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "vcp_lz_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vcp_adler32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]),
+    "vcp_crc32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]),
+    "vcp_base64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libvcprep.so.  Raises (never falls back) when the CUDA library is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA library is the only implementation of this path "
+                "(no CPU fallback). Build it with `python -m vision_compression_project_b200.build`.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return (load().vcp_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Map a VCP_E* code to the exception the reference's per-page try/except expects (pdf_extract.py:133-136)."""
+    if rc == VCP_OK:
+        return
+    msg = last_error()
+    if rc in (VCP_EINVAL, VCP_ESIZE):
+        raise ValueError(msg)
+    if rc == VCP_ENOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)

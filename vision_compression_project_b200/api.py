@@ -1,0 +1,334 @@
+"""Drop-in page-image preparation: PIL / bytes in -> PNG / base64 bytes out, computed on a B200.
+
+Stands where the reference does, per rasterised page (backend/app/pipeline/pdf_extract.py:129-130, :55;
+scripts/extract_pdf_with_gemini.py:151-152, :84; scripts/extract_page_with_gemini.py:119-127):
+
+    page_image.save(page_image_path)                 ->  open(path, "wb").write(prepare_page(page_image).png)
+    model.generate_content([prompt, page_image])     ->  generate_content([prompt, {"mime_type": "image/png",
+                                                                                    "data": prepared.png}])   # or .b64
+
+Keyword names and meaning follow Pillow (`Image.convert`, `Image.thumbnail` size rule, `Image.resize`,
+`Image.save(format="PNG", compress_level=, optimize=)`), so the oracle for any call is literally the Pillow
+composition in oracle/pillow_path.py.  All pixel and byte work runs in libvcprep.so (hand-written sm_100a
+kernels); Python only plans and moves pointers.  There is no CPU fallback: without the library or a GPU the
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from dataclasses import dataclass, field
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+try:  # PIL is only needed when the caller passes PIL images
+    from PIL import Image as _PILImage
+except Exception:  # pragma: no cover
+    _PILImage = None
+
+LANCZOS, BILINEAR, BICUBIC, BOX, HAMMING = 1, 2, 3, 4, 5
+_MODE_CH = {"L": 1, "LA": 2, "RGB": 3, "RGBA": 4}
+_CH_MODE = {1: "L", 2: "LA", 3: "RGB", 4: "RGBA"}
+
+
+@dataclass
+class PreparedPage:
+    png: Optional[bytes]
+    b64: Optional[bytes]
+    size: Tuple[int, int]
+    mode: str
+    adler32: int = 0
+    n_idat: int = 0
+    error: Optional[str] = None
+    stats: dict = field(default_factory=dict)
+
+
+def thumbnail_size(src: Tuple[int, int], box: Tuple[int, int]) -> Tuple[int, int]:
+    """Aspect-preserving target size of Image.thumbnail (PIL/Image.py:2876-2898): never enlarges."""
+    w, h = src
+    x, y = box
+    if x >= w and y >= h:
+        return (w, h)
+
+    def round_aspect(number, key):
+        return max(min(math.floor(number), math.ceil(number), key=key), 1)
+
+    aspect = w / h
+    if x / y >= aspect:
+        x = round_aspect(y * aspect, key=lambda n: abs(aspect - n / y))
+    else:
+        y = round_aspect(x / aspect, key=lambda n: 0 if n == 0 else abs(aspect - x / n))
+    return (x, y)
+
+
+def parse_pnm(data) -> Tuple[int, int, int, int]:
+    """Header of a binary PPM/PGM as `pdftoppm` writes it (P6/P5, maxval 255). Returns (w, h, channels, payload offset)."""
+    mv = memoryview(data)
+    if len(mv) < 7 or bytes(mv[:2]) not in (b"P6", b"P5"):
+        raise ValueError("bytes input must be a binary PPM/PGM (P6/P5) or come with raw_shape=(H, W, C)")
+    ch = 3 if bytes(mv[:2]) == b"P6" else 1
+    pos, vals = 2, []
+    n = len(mv)
+    while len(vals) < 3:
+        while pos < n and mv[pos] in b" \t\r\n":
+            pos += 1
+        if pos < n and mv[pos] == 0x23:                      # comment line
+            while pos < n and mv[pos] != 0x0A:
+                pos += 1
+            continue
+        start = pos
+        while pos < n and mv[pos] not in b" \t\r\n":
+            pos += 1
+        if start == pos:
+            raise ValueError("truncated PNM header")
+        vals.append(int(bytes(mv[start:pos])))
+    pos += 1                                                 # single whitespace after maxval
+    w, h, maxval = vals
+    if maxval != 255:
+        raise ValueError(f"PNM maxval {maxval} not supported (8-bit pages only)")
+    if len(mv) - pos < w * h * ch:
+        raise ValueError("truncated PNM payload")
+    return w, h, ch, pos
+
+
+class _Source:
+    __slots__ = ("keep", "ptr", "w", "h", "c", "stride", "device")
+
+    def __init__(self, keep, ptr, w, h, c, stride, device):
+        self.keep, self.ptr, self.w, self.h, self.c, self.stride, self.device = keep, ptr, w, h, c, stride, device
+
+
+def _as_source(image: Any, raw_shape) -> _Source:
+    if _PILImage is not None and isinstance(image, _PILImage.Image):
+        if image.mode not in _MODE_CH:
+            raise ValueError(f"unsupported image mode {image.mode!r} (supported: L, LA, RGB, RGBA)")
+        arr = np.asarray(image)                              # packs Pillow's RGBX storage to interleaved bytes
+        if not arr.flags.c_contiguous:
+            arr = np.ascontiguousarray(arr)
+        c = _MODE_CH[image.mode]
+        return _Source(arr, arr.ctypes.data, image.width, image.height, c, image.width * c, False)
+    try:
+        import torch
+        if isinstance(image, torch.Tensor):
+            t = image
+            if t.dtype != torch.uint8 or t.dim() not in (2, 3):
+                raise ValueError("tensor input must be uint8 (H, W) or (H, W, C)")
+            h, w = int(t.shape[0]), int(t.shape[1])
+            c = 1 if t.dim() == 2 else int(t.shape[2])
+            if t.dim() == 3 and (t.stride(2) != 1 or t.stride(1) != c):
+                t = t.contiguous()
+            if t.dim() == 2 and t.stride(1) != 1:
+                t = t.contiguous()
+            return _Source(t, t.data_ptr(), w, h, c, int(t.stride(0)), t.is_cuda)
+    except ImportError:  # pragma: no cover
+        pass
+    if isinstance(image, np.ndarray):
+        a = image
+        if a.dtype != np.uint8 or a.ndim not in (2, 3):
+            raise ValueError("array input must be uint8 (H, W) or (H, W, C)")
+        c = 1 if a.ndim == 2 else a.shape[2]
+        ok = a.strides[-1] == 1 and (a.ndim == 2 or a.strides[1] == c)
+        if not ok or a.strides[0] < a.shape[1] * c:
+            a = np.ascontiguousarray(a)
+        return _Source(a, a.ctypes.data, a.shape[1], a.shape[0], c, a.strides[0], False)
+    if isinstance(image, (bytes, bytearray, memoryview)):
+        mv = memoryview(image)
+        if raw_shape is not None:
+            h, w, c = raw_shape
+            if len(mv) < h * w * c:
+                raise ValueError("raw bytes shorter than raw_shape")
+            off = 0
+        else:
+            w, h, c, off = parse_pnm(mv)
+        arr = np.frombuffer(mv, np.uint8, count=w * h * c, offset=off)
+        return _Source((image, arr), arr.ctypes.data, w, h, c, w * c, False)
+    raise ValueError(f"unsupported input type {type(image).__name__}")
+
+
+class PagePrep:
+    """One device context: a libvcprep handle (stream + arena) and pinned output buffers.  Not shared across
+    threads concurrently (calls serialise on the handle); `prepare_page(s)` at module level keep one per thread,
+    matching the reference's 5-worker pool (pdf_extract.py:313-333)."""
+
+    def __init__(self, device: int = 0):
+        import torch
+        self._torch = torch
+        self.lib = N.load()
+        self.device = device
+        hp = C.c_void_p()
+        N.check(self.lib.vcp_init(device, C.byref(hp)))
+        self.handle = hp
+        self._out_png = None
+        self._out_b64 = None
+        self.max_batch_bytes = 1 << 30
+        self.launches_total = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vcp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ low level
+    def stats(self) -> dict:
+        s = N.Stats()
+        N.check(self.lib.vcp_get_stats(self.handle, C.byref(s)))
+        return s.as_dict()
+
+    def output_bound(self, descs, n, opts) -> Tuple[int, int]:
+        p, b = C.c_uint64(), C.c_uint64()
+        N.check(self.lib.vcp_output_bound(descs, n, C.byref(opts), C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def run(self, descs, n, opts, out_png_ptr, png_cap, out_b64_ptr, b64_cap):
+        """vcp_prepare_batch; returns the ctypes result array."""
+        res = (N.PageResult * n)()
+        N.check(self.lib.vcp_prepare_batch(self.handle, descs, n, C.byref(opts), out_png_ptr, png_cap,
+                                           out_b64_ptr, b64_cap, res))
+        self.launches_total += self.stats()["kernel_launches"]
+        return res
+
+    def _pinned(self, which: str, nbytes: int):
+        cur = getattr(self, which)
+        if cur is None or cur.numel() < nbytes:
+            cur = self._torch.empty(int(nbytes * 1.25) + 4096, dtype=self._torch.uint8, pin_memory=True)
+            setattr(self, which, cur)
+        return cur
+
+    # ------------------------------------------------------------------ planning
+    @staticmethod
+    def _plan(src: _Source, size, max_side, mode, resample, reducing_gap) -> N.PageDesc:
+        d = N.PageDesc()
+        d.src, d.width, d.height, d.channels, d.row_stride = src.ptr, src.w, src.h, src.c, src.stride
+        target = None
+        if size is not None:
+            target = (int(size[0]), int(size[1]))
+            if target[0] <= 0 or target[1] <= 0:
+                raise ValueError("height and width must be > 0")
+        elif max_side is not None:
+            target = thumbnail_size((src.w, src.h), (int(max_side), int(max_side)))
+        if target is not None and target != (src.w, src.h):
+            d.dst_width, d.dst_height = target
+            if reducing_gap is not None:
+                if reducing_gap < 1.0:
+                    raise ValueError("reducing_gap must be 1.0 or greater")
+                d.reduce_x = int(src.w / target[0] / reducing_gap) or 1     # PIL/Image.py:2413-2416
+                d.reduce_y = int(src.h / target[1] / reducing_gap) or 1
+        return d
+
+    def prepare_pages(self, images: Sequence[Any], *, size=None, max_side=None, mode: Optional[str] = "RGB",
+                      resample: int = LANCZOS, reducing_gap: Optional[float] = None, compress_level: int = 6,
+                      optimize: bool = False, want_base64: bool = True, raw_shape=None) -> List[PreparedPage]:
+        if mode not in ("RGB", "L", None):
+            raise ValueError(f"unsupported output mode {mode!r} (RGB, L or None = keep)")
+        if compress_level == -1:
+            compress_level = 6
+        if not 0 <= compress_level <= 9:
+            raise ValueError("compress_level must be -1 or 0..9")
+        n = len(images)
+        out: List[Optional[PreparedPage]] = [None] * n
+        srcs: List[Optional[_Source]] = [None] * n
+        for i, im in enumerate(images):
+            try:
+                srcs[i] = _as_source(im, raw_shape)
+            except (ValueError, TypeError) as e:               # a bad page never fails the batch
+                out[i] = PreparedPage(None, None, (0, 0), "", error=f"{type(e).__name__}: {e}")
+        # consecutive runs of the same residency (host / device), bounded in bytes
+        i = 0
+        while i < n:
+            if srcs[i] is None:
+                i += 1
+                continue
+            j, nbytes, dev = i, 0, srcs[i].device
+            idx = []
+            while j < n and (srcs[j] is None or srcs[j].device == dev):
+                if srcs[j] is not None:
+                    sz = srcs[j].w * srcs[j].h * srcs[j].c
+                    if idx and nbytes + sz > self.max_batch_bytes:
+                        break
+                    idx.append(j)
+                    nbytes += sz
+                j += 1
+            self._run_chunk(idx, srcs, out, dev, size, max_side, mode, resample, reducing_gap, compress_level,
+                            optimize, want_base64)
+            i = j
+        return out  # type: ignore[return-value]
+
+    def _run_chunk(self, idx, srcs, out, dev, size, max_side, mode, resample, reducing_gap, level, optimize, want_b64):
+        good, descs_l = [], []
+        for k in idx:
+            try:
+                descs_l.append(self._plan(srcs[k], size, max_side, mode, resample, reducing_gap))
+                good.append(k)
+            except ValueError as e:
+                out[k] = PreparedPage(None, None, (0, 0), "", error=f"ValueError: {e}")
+        m = len(good)
+        if m == 0:
+            return
+        descs = (N.PageDesc * m)(*descs_l)
+        opts = N.Opts()
+        opts.out_channels = {"RGB": 3, "L": 1, None: 0}[mode]
+        opts.resample, opts.compress_level, opts.optimize = int(resample), int(level), int(bool(optimize))
+        opts.want_b64, opts.src_device, opts.dst_device = int(bool(want_b64)), int(bool(dev)), 0
+        bound_png, bound_b64 = self.output_bound(descs, m, opts)
+        for attempt in (0, 1):
+            cap_png = bound_png if attempt else min(bound_png, max(32 << 20, bound_png // 4))
+            cap_b64 = bound_b64 if attempt else min(bound_b64, max(44 << 20, bound_b64 // 4))
+            bp = self._pinned("_out_png", cap_png)
+            bb = self._pinned("_out_b64", cap_b64) if want_b64 else None
+            try:
+                res = self.run(descs, m, opts, bp.data_ptr(), bp.numel(), bb.data_ptr() if bb is not None else None,
+                               bb.numel() if bb is not None else 0)
+                break
+            except ValueError as e:
+                if attempt or "too small" not in str(e):
+                    raise
+        st = self.stats()
+        png_np = bp.numpy()
+        b64_np = bb.numpy() if bb is not None else None
+        for r, k in zip(res, good):
+            if r.status != 0:
+                out[k] = PreparedPage(None, None, (0, 0), "", error=f"page rejected by libvcprep (status {r.status})")
+                continue
+            png = png_np[r.png_off:r.png_off + r.png_len].tobytes()
+            b64 = b64_np[r.b64_off:r.b64_off + r.b64_len].tobytes() if b64_np is not None else None
+            out[k] = PreparedPage(png, b64, (r.width, r.height), _CH_MODE[r.channels], r.adler32, r.n_idat, None, st)
+
+
+_tls = threading.local()
+
+
+def _engine(device: int) -> PagePrep:
+    engines = getattr(_tls, "engines", None)
+    if engines is None:
+        engines = _tls.engines = {}
+    e = engines.get(device)
+    if e is None:
+        e = engines[device] = PagePrep(device)
+    return e
+
+
+def prepare_pages(images: Sequence[Any], *, device: int = 0, **kw) -> List[PreparedPage]:
+    """Batched fast path: one launch set for all pages.  A page that cannot be processed gets `.error` set and
+    `.png is None`; the others are unaffected (the reference collects failed pages the same way,
+    pdf_extract.py:342-350)."""
+    return _engine(device).prepare_pages(images, **kw)
+
+
+def prepare_page(image: Any, *, device: int = 0, **kw) -> PreparedPage:
+    """Single page; raises (ValueError / MemoryError / RuntimeError) like the Pillow calls it replaces, so the
+    reference's per-page try/except (pdf_extract.py:133-136) keeps working."""
+    r = _engine(device).prepare_pages([image], **kw)[0]
+    if r.error is not None:
+        kind, _, msg = r.error.partition(": ")
+        raise {"ValueError": ValueError, "TypeError": TypeError}.get(kind, RuntimeError)(msg or r.error)
+    return r

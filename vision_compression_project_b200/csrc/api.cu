@@ -1,0 +1,731 @@
+// api.cu — the C ABI of libvcprep.so (include/vcprep.h): handle, planning, arena, launch sequence.
+//
+// This is the boundary the reference's per-page body binds to (SURVEY.md §8 b): it stands where
+//     page_image.save(page_image_path)         backend/app/pipeline/pdf_extract.py:130
+//     generate_content([prompt, page_image])   backend/app/pipeline/pdf_extract.py:55  (image -> PNG blob -> base64)
+// run Pillow / zlib / binascii natively.  A batch of pages goes through ONE launch set (not one per page):
+//   H2D -> convert -> reduce -> resample H -> resample V -> PNG filter (+Adler partials) -> Adler combine
+//       -> LZ77 -> Huffman build -> layout -> payload init -> Huffman emit -> CRC/framing -> base64 -> D2H.
+// Host work is planning only: geometry, Pillow's coefficient tables (double math, cached), arena carving.
+#include "../../include/vcprep.h"
+#include "vcp_internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+using namespace vcp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? VCP_ENOMEM : VCP_ECUDA, \
+    "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Coeffs { int ksize; std::vector<int32_t> bounds; std::vector<int32_t> kt; };   // kt transposed: [k][out]
+typedef std::tuple<int, int, int, float, float> CoeffKey;
+
+enum { EV_START, EV_H2D, EV_PIXEL, EV_FILTER, EV_LZ, EV_HUFF, EV_ASSEMBLE, EV_B64, EV_D2H, EV_COUNT };
+
+}  // namespace
+
+struct vcp_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    uint8_t* arena = nullptr; size_t arena_cap = 0;
+    uint8_t* meta = nullptr; size_t meta_cap = 0;          // pinned host staging: descriptors up, results down
+    std::map<CoeffKey, Coeffs> coeff_cache;
+    cudaEvent_t ev[EV_COUNT] = {};
+    vcp_stats stats = {};
+    size_t group_bytes = (size_t)2 << 30;                  // max filtered bytes per launch set
+};
+
+namespace {
+
+int ensure_arena(vcp_handle* h, size_t need) {
+    if (need <= h->arena_cap) return 0;
+    if (h->arena) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->arena)); h->arena = nullptr; h->arena_cap = 0; }
+    const size_t cap = align_up(need + need / 8, (size_t)1 << 20);
+    CU(cudaMalloc(&h->arena, cap));
+    h->arena_cap = cap;
+    return 0;
+}
+
+int ensure_meta(vcp_handle* h, size_t need) {
+    if (need <= h->meta_cap) return 0;
+    if (h->meta) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFreeHost(h->meta)); h->meta = nullptr; h->meta_cap = 0; }
+    const size_t cap = align_up(need * 2, (size_t)1 << 16);
+    CU(cudaMallocHost(&h->meta, cap));
+    h->meta_cap = cap;
+    return 0;
+}
+
+const Coeffs* get_coeffs(vcp_handle* h, int in_size, int out_size, int filter, float b0, float b1) {
+    CoeffKey key(in_size, out_size, filter, b0, b1);
+    auto it = h->coeff_cache.find(key);
+    if (it != h->coeff_cache.end()) return &it->second;
+    if (h->coeff_cache.size() > 256) h->coeff_cache.clear();
+    Coeffs c;
+    if (resample_coeffs_host(in_size, out_size, filter, b0, b1, nullptr, nullptr, &c.ksize) != 0) return nullptr;
+    std::vector<int32_t> kk((size_t)out_size * c.ksize);
+    c.bounds.resize((size_t)out_size * 2);
+    if (resample_coeffs_host(in_size, out_size, filter, b0, b1, c.bounds.data(), kk.data(), &c.ksize) != 0) return nullptr;
+    c.kt.resize(kk.size());
+    for (int x = 0; x < out_size; x++)
+        for (int k = 0; k < c.ksize; k++) c.kt[(size_t)k * out_size + x] = kk[(size_t)x * c.ksize + k];
+    return &(h->coeff_cache[key] = std::move(c));
+}
+
+struct Bump {
+    size_t off = 0;
+    size_t take(size_t n, size_t a = 256) { off = align_up(off, a); const size_t r = off; off += n; return r; }
+};
+
+constexpr size_t kNone = (size_t)-1;
+
+// Host-side plan of one page (offsets into the arena; kNone = stage skipped).
+struct PagePlan {
+    int status = 0;
+    const uint8_t* src = nullptr; int64_t src_stride = 0;
+    int sw = 0, sh = 0, sc = 0, c = 0, fx = 1, fy = 1, rw = 0, rh = 0, w = 0, h = 0;
+    bool need_conv = false, need_red = false, need_h = false, need_v = false;
+    float box[4] = {0, 0, 0, 0};
+    size_t o_raw = kNone, o_conv = kNone, o_red = kNone, o_tmp = kNone, o_vout = kNone, o_filt = kNone;
+    size_t o_hb = kNone, o_hk = kNone, o_vb = kNone, o_vk = kNone;
+    const Coeffs* ch = nullptr; const Coeffs* cv = nullptr;
+    int64_t filt_len = 0;
+    int nblk = 0, nsub = 0;
+    uint64_t png_bound = 0;
+};
+
+uint64_t png_bound_of(int64_t filt_len, int nblk) {
+    return align_up((size_t)(8 + 25 + 12 + (uint64_t)nblk * (12 + 6) + filt_len + 5 * (uint64_t)(filt_len / 65535 + nblk + 1)), 16);
+}
+uint64_t b64_bound_of(uint64_t png_bound) { return align_up((size_t)(4 * ((png_bound + 2) / 3)), 16); }
+
+int color_type_of(int c) { return c == 1 ? 0 : c == 2 ? 4 : c == 3 ? 2 : 6; }
+
+// geometry + validation of one page; no allocation
+int plan_geometry(const vcp_page_desc& d, const vcp_opts& o, PagePlan& P) {
+    if (!d.src) return fail(VCP_EINVAL, "page src is NULL");
+    if (d.width <= 0 || d.height <= 0) return fail(VCP_EINVAL, "bad page size %dx%d", d.width, d.height);
+    if (d.channels < 1 || d.channels > 4) return fail(VCP_EINVAL, "unsupported channel count %d (1=L 2=LA 3=RGB 4=RGBA)", d.channels);
+    if ((int64_t)d.width * d.channels > (1 << 20)) return fail(VCP_EINVAL, "page too wide (%d px)", d.width);
+    if (d.height > (1 << 20)) return fail(VCP_EINVAL, "page too tall (%d px)", d.height);
+    P.src = (const uint8_t*)d.src; P.sw = d.width; P.sh = d.height; P.sc = d.channels;
+    P.src_stride = d.row_stride ? d.row_stride : (int64_t)d.width * d.channels;
+    if (P.src_stride < (int64_t)d.width * d.channels) return fail(VCP_EINVAL, "row_stride %lld smaller than a row", (long long)d.row_stride);
+    P.c = o.out_channels ? o.out_channels : d.channels;
+    if (P.c != 1 && P.c != 3 && P.c != d.channels) return fail(VCP_EINVAL, "unsupported output channel count %d", P.c);
+    P.need_conv = P.c != P.sc;
+    P.fx = d.reduce_x > 1 ? d.reduce_x : 1; P.fy = d.reduce_y > 1 ? d.reduce_y : 1;
+    P.need_red = P.fx > 1 || P.fy > 1;
+    P.rw = (P.sw + P.fx - 1) / P.fx; P.rh = (P.sh + P.fy - 1) / P.fy;
+    const bool resize = d.dst_width > 0 && d.dst_height > 0;
+    if ((d.dst_width > 0) != (d.dst_height > 0)) return fail(VCP_EINVAL, "dst_width/dst_height must both be set or both be 0");
+    P.w = resize ? d.dst_width : P.rw; P.h = resize ? d.dst_height : P.rh;
+    if ((int64_t)P.w * P.c > 65536 || P.h > 65535 || P.sh > 65535) return fail(VCP_EINVAL, "page too large for the row kernels (%dx%d -> %dx%d)", P.sw, P.sh, P.w, P.h);
+    P.box[0] = 0.f; P.box[1] = 0.f;
+    P.box[2] = P.need_red ? (float)((double)P.sw / P.fx) : (float)P.rw;
+    P.box[3] = P.need_red ? (float)((double)P.sh / P.fy) : (float)P.rh;
+    P.need_h = P.w != P.rw || P.box[2] != (float)P.w;
+    P.need_v = P.h != P.rh || P.box[3] != (float)P.h;
+    if ((P.need_h || P.need_v) && (P.c == 2 || P.c == 4))
+        return fail(VCP_EINVAL, "resize of images with alpha is not on the path (Pillow premultiplies); convert to RGB or L");
+    if ((P.need_h || P.need_v) && (o.resample < VCP_LANCZOS || o.resample > VCP_HAMMING))
+        return fail(VCP_EINVAL, "unsupported resample filter %d", o.resample);
+    P.filt_len = (int64_t)P.h * (1 + (int64_t)P.w * P.c);
+    if (P.filt_len >= ((int64_t)1 << 31) - (1 << 20)) return fail(VCP_EINVAL, "page too large (%lld filtered bytes)", (long long)P.filt_len);
+    P.nblk = (int)((P.filt_len + kBlockBytes - 1) / kBlockBytes);
+    P.nsub = 0;
+    for (int b = 0; b < P.nblk; b++) {
+        const int64_t len = std::min<int64_t>(kBlockBytes, P.filt_len - (int64_t)b * kBlockBytes);
+        P.nsub += (int)((len + kSubBytes - 1) / kSubBytes);
+    }
+    P.png_bound = png_bound_of(P.filt_len, P.nblk);
+    return 0;
+}
+
+struct GroupOut {       // where the launch set of a group left its results (pinned host copies)
+    const uint64_t* png_off; const uint64_t* png_len; const uint64_t* b64_off; const uint64_t* b64_len;
+    const uint32_t* adler; const uint64_t* totals;
+    uint8_t* d_png; uint8_t* d_b64; uint8_t* d_filt0; uint32_t* d_tokens; uint32_t* d_sub_ntok; uint32_t* d_sub_hist;
+    int nsub; int nblocks;
+    std::vector<size_t> filt_off;     // per page: offset of its filtered stream from d_filt0's arena base
+};
+
+// Runs the whole launch set for pages[0..n) (all with status 0).  framed=0 + stream input: the pages' filtered
+// streams are given directly (stage-level vcp_deflate / vcp_lz_tokens): plans[i].src is the stream, filt_len set.
+enum RunMode { RUN_FULL = 0, RUN_STREAM = 1, RUN_FILTER_ONLY = 2, RUN_LZ_ONLY = 3 };
+
+int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, RunMode mode, GroupOut& out) {
+    const int n = (int)plans.size();
+    cudaStream_t st = h->stream;
+    const bool stream_in = (mode == RUN_STREAM || mode == RUN_LZ_ONLY);
+    // ---------------- carve the arena
+    Bump bump;
+    int nblocks = 0, nsub = 0, nrows = 0;
+    uint64_t png_cap = 0, b64_cap = 0;
+    std::vector<int32_t> coeff_blob;
+    auto put_coeff = [&](const std::vector<int32_t>& v) { const size_t o2 = coeff_blob.size(); coeff_blob.insert(coeff_blob.end(), v.begin(), v.end()); return o2; };
+    std::map<const Coeffs*, std::pair<size_t, size_t>> coeff_at;   // -> (bounds idx, kt idx) in coeff_blob
+    for (auto& P : plans) {
+        if (!stream_in) {
+            if (!o.src_device) P.o_raw = bump.take((size_t)P.sw * P.sc * P.sh + 16);
+            if (P.need_conv) P.o_conv = bump.take((size_t)P.sw * P.sh * P.c + 16);
+            if (P.need_red) P.o_red = bump.take((size_t)P.rw * P.rh * P.c + 16);
+            if (P.need_h) P.o_tmp = bump.take((size_t)P.w * P.rh * P.c + 16);
+            if (P.need_v) P.o_vout = bump.take((size_t)P.w * P.h * P.c + 16);
+            if (P.need_h) {
+                P.ch = get_coeffs(h, P.rw, P.w, o.resample, P.box[0], P.box[2]);
+                if (!P.ch) return fail(VCP_EINVAL, "bad resample parameters");
+                if (!coeff_at.count(P.ch)) { const size_t a = put_coeff(P.ch->bounds); const size_t b = put_coeff(P.ch->kt); coeff_at[P.ch] = {a, b}; }
+            }
+            if (P.need_v) {
+                P.cv = get_coeffs(h, P.rh, P.h, o.resample, P.box[1], P.box[3]);
+                if (!P.cv) return fail(VCP_EINVAL, "bad resample parameters");
+                if (!coeff_at.count(P.cv)) { const size_t a = put_coeff(P.cv->bounds); const size_t b = put_coeff(P.cv->kt); coeff_at[P.cv] = {a, b}; }
+            }
+        }
+        nblocks += P.nblk; nsub += P.nsub; nrows += P.h;
+        png_cap += P.png_bound; b64_cap += b64_bound_of(P.png_bound);
+    }
+    // filtered streams: one contiguous region so that token index = byte offset from its base
+    const size_t o_filt_region = bump.take(0);
+    for (auto& P : plans) { bump.take(kStreamPad); P.o_filt = bump.take((size_t)P.filt_len); }
+    bump.take(kStreamPad + 256);
+    const size_t filt_region_bytes = align_up(bump.off - o_filt_region, 256);
+    const bool need_lz = mode != RUN_FILTER_ONLY;
+    const bool need_huff = mode == RUN_FULL || mode == RUN_STREAM;
+    const size_t o_tokens = need_lz ? bump.take(filt_region_bytes * 4) : kNone;
+    const size_t o_sub_ntok = bump.take((size_t)nsub * 4 + 4);
+    const size_t o_sub_hist = bump.take((size_t)nsub * kHistSize * 4 + 4);
+    const size_t o_row_adler = bump.take((size_t)nrows * 4 + 4);
+    const size_t o_page_adler = bump.take((size_t)n * 4);
+    const size_t o_blk_code = bump.take((size_t)nblocks * kCodeStride * 2 + 4);
+    const size_t o_blk_clen = bump.take((size_t)nblocks * kCodeStride + 4);
+    const size_t o_blk_hdr = bump.take((size_t)nblocks * kHdrBytes + 4);
+    const size_t o_blk_hdr_bits = bump.take((size_t)nblocks * 4 + 4);
+    const size_t o_blk_eob = bump.take((size_t)nblocks * 8 + 8);
+    const size_t o_blk_bits = bump.take((size_t)nblocks * 8 + 8);
+    const size_t o_blk_stored = bump.take((size_t)nblocks * 4 + 4);
+    const size_t o_blk_len = bump.take((size_t)nblocks * 4 + 4);
+    const size_t o_sub_bitoff = bump.take((size_t)nsub * 8 + 8);
+    const size_t o_blk_dst = bump.take((size_t)nblocks * 8 + 8);
+    // results block (copied down in one piece): png_off[n] png_len[n] b64_off[n] b64_len[n] totals[2] adler[n] err[2]
+    const size_t res_bytes = (size_t)n * 8 * 4 + 16 + align_up((size_t)n * 4, 8) + 8;
+    const size_t o_res = bump.take(res_bytes);
+    const size_t o_png = need_huff ? bump.take((size_t)png_cap + 64) : kNone;
+    const size_t o_b64 = (need_huff && o.want_b64) ? bump.take((size_t)b64_cap + 64) : kNone;
+    const size_t o_coeff = bump.take(coeff_blob.size() * 4 + 4);
+    const size_t o_pages = bump.take((size_t)n * sizeof(PageD));
+    const size_t o_blocks = bump.take((size_t)nblocks * sizeof(BlockD) + 8);
+    const size_t o_sub2blk = bump.take((size_t)nsub * 4 + 4);
+    const size_t desc_bytes = bump.off - o_coeff;
+    int rc = ensure_arena(h, bump.off + 256);
+    if (rc) return rc;
+    rc = ensure_meta(h, desc_bytes + res_bytes + 256);
+    if (rc) return rc;
+    uint8_t* A = h->arena;
+    h->stats.arena_bytes = h->arena_cap;
+
+    // ---------------- descriptors (built in pinned memory, mirrored layout of [o_coeff, end))
+    uint8_t* M = h->meta;
+    memset(M, 0, desc_bytes);
+    if (!coeff_blob.empty()) memcpy(M, coeff_blob.data(), coeff_blob.size() * 4);
+    PageD* hp = reinterpret_cast<PageD*>(M + (o_pages - o_coeff));
+    BlockD* hb = reinterpret_cast<BlockD*>(M + (o_blocks - o_coeff));
+    uint32_t* hs2b = reinterpret_cast<uint32_t*>(M + (o_sub2blk - o_coeff));
+    const int32_t* d_coeff = reinterpret_cast<const int32_t*>(A + o_coeff);
+    int blk = 0, sub = 0, row = 0;
+    int max_sh = 0, max_sw = 0, max_rh = 0, max_rw = 0, max_w = 0, max_h = 0, max_wc = 0;
+    bool any_conv = false, any_red = false, any_h = false, any_v = false;
+    uint64_t in_bytes = 0, filt_bytes = 0;
+    out.filt_off.clear();
+    for (int i = 0; i < n; i++) {
+        PagePlan& P = plans[i];
+        PageD& D = hp[i];
+        D.sw = P.sw; D.sh = P.sh; D.sc = P.sc; D.c = P.c; D.fx = P.fx; D.fy = P.fy; D.rw = P.rw; D.rh = P.rh; D.w = P.w; D.h = P.h;
+        D.color_type = color_type_of(P.c);
+        const uint8_t* cur = nullptr; int64_t cur_stride = 0;
+        if (!stream_in) {
+            if (o.src_device) { cur = P.src; cur_stride = P.src_stride; }
+            else { cur = A + P.o_raw; cur_stride = (int64_t)P.sw * P.sc; }
+            D.src = cur; D.src_stride = cur_stride;
+            if (P.need_conv) { D.conv = A + P.o_conv; cur = D.conv; cur_stride = (int64_t)P.sw * P.c; any_conv = true; }
+            D.rdin = cur; D.rdin_stride = cur_stride;
+            if (P.need_red) { D.red = A + P.o_red; cur = D.red; cur_stride = (int64_t)P.rw * P.c; any_red = true; }
+            D.hin = cur; D.hin_stride = cur_stride;
+            if (P.need_h) {
+                D.tmp = A + P.o_tmp; cur = D.tmp; cur_stride = (int64_t)P.w * P.c; any_h = true;
+                D.hb = d_coeff + coeff_at[P.ch].first; D.hk = d_coeff + coeff_at[P.ch].second; D.hks = P.ch->ksize;
+            }
+            D.vin = cur; D.vin_stride = cur_stride;
+            if (P.need_v) {
+                D.vout = A + P.o_vout; cur = D.vout; cur_stride = (int64_t)P.w * P.c; any_v = true;
+                D.vb = d_coeff + coeff_at[P.cv].first; D.vk = d_coeff + coeff_at[P.cv].second; D.vks = P.cv->ksize;
+            }
+            D.pix = cur; D.pix_stride = cur_stride;
+            max_sh = std::max(max_sh, P.sh); max_sw = std::max(max_sw, P.sw);
+            if (P.need_red) { max_rh = std::max(max_rh, P.rh); max_rw = std::max(max_rw, P.rw); }
+            in_bytes += (uint64_t)P.sw * P.sh * P.sc;
+        }
+        max_h = std::max(max_h, P.h); max_w = std::max(max_w, P.w); max_wc = std::max(max_wc, P.w * P.c);
+        D.filt = A + P.o_filt; D.filt_len = P.filt_len;
+        out.filt_off.push_back(P.o_filt);
+        D.row0 = row; row += P.h;
+        D.blk0 = blk; D.nblk = P.nblk;
+        for (int b = 0; b < P.nblk; b++) {
+            BlockD& Bk = hb[blk];
+            Bk.page = i; Bk.first = b == 0; Bk.last = b == P.nblk - 1;
+            Bk.start = (int64_t)b * kBlockBytes; Bk.len = std::min<int64_t>(kBlockBytes, P.filt_len - Bk.start);
+            Bk.sub0 = sub; Bk.nsub = (int)((Bk.len + kSubBytes - 1) / kSubBytes);
+            for (int s = 0; s < Bk.nsub; s++) hs2b[sub++] = (uint32_t)blk;
+            blk++;
+        }
+        filt_bytes += (uint64_t)P.filt_len;
+    }
+    int max_resh_rows = 0;      // rows the horizontal pass walks = rh of pages that need it
+    for (auto& P : plans) if (P.need_h) max_resh_rows = std::max(max_resh_rows, P.rh);
+
+    BatchD B = {};
+    B.pages = reinterpret_cast<const PageD*>(A + o_pages); B.npages = n;
+    B.blocks = reinterpret_cast<const BlockD*>(A + o_blocks); B.nblocks = nblocks;
+    B.sub2blk = reinterpret_cast<const uint32_t*>(A + o_sub2blk); B.nsub = nsub;
+    B.filt_base = A + o_filt_region;
+    B.tokens = need_lz ? reinterpret_cast<uint32_t*>(A + o_tokens) : nullptr;
+    B.sub_ntok = reinterpret_cast<uint32_t*>(A + o_sub_ntok);
+    B.sub_hist = reinterpret_cast<uint32_t*>(A + o_sub_hist);
+    B.row_adler = reinterpret_cast<uint32_t*>(A + o_row_adler);
+    B.blk_code = reinterpret_cast<uint16_t*>(A + o_blk_code);
+    B.blk_clen = A + o_blk_clen;
+    B.blk_hdr = A + o_blk_hdr;
+    B.blk_hdr_bits = reinterpret_cast<uint32_t*>(A + o_blk_hdr_bits);
+    B.blk_eob_bit = reinterpret_cast<uint64_t*>(A + o_blk_eob);
+    B.blk_body_bits = reinterpret_cast<uint64_t*>(A + o_blk_bits);
+    B.blk_stored = reinterpret_cast<uint32_t*>(A + o_blk_stored);
+    B.blk_len = reinterpret_cast<uint32_t*>(A + o_blk_len);
+    B.sub_bitoff = reinterpret_cast<uint64_t*>(A + o_sub_bitoff);
+    B.blk_dst = reinterpret_cast<uint64_t*>(A + o_blk_dst);
+    uint8_t* R = A + o_res;
+    B.png_off = reinterpret_cast<uint64_t*>(R); B.png_len = B.png_off + n; B.b64_off = B.png_len + n; B.b64_len = B.b64_off + n;
+    B.totals = B.b64_len + n;
+    B.page_adler = reinterpret_cast<uint32_t*>(B.totals + 2);
+    B.err = reinterpret_cast<uint32_t*>(R + res_bytes - 8);
+    (void)o_page_adler;
+    B.png = need_huff ? A + o_png : nullptr; B.png_cap = png_cap;
+    B.b64 = (need_huff && o.want_b64) ? A + o_b64 : nullptr; B.b64_cap = b64_cap;
+    B.framed = mode == RUN_FULL; B.level = o.compress_level; B.want_b64 = (need_huff && o.want_b64) ? 1 : 0;
+
+    // ---------------- launch set
+    uint64_t launches = 0;
+    CU(cudaEventRecord(h->ev[EV_START], st));
+    CU(cudaMemcpyAsync(A + o_coeff, M, desc_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(R, 0, res_bytes, st));
+    if (!stream_in && !o.src_device) {
+        for (auto& P : plans)
+            CU(cudaMemcpy2DAsync(A + P.o_raw, (size_t)P.sw * P.sc, P.src, (size_t)P.src_stride, (size_t)P.sw * P.sc, (size_t)P.sh,
+                                 cudaMemcpyHostToDevice, st));
+    }
+    if (stream_in) {
+        for (auto& P : plans)
+            CU(cudaMemcpyAsync(A + P.o_filt, P.src, (size_t)P.filt_len, cudaMemcpyDeviceToDevice, st));
+    }
+    CU(cudaEventRecord(h->ev[EV_H2D], st));
+    if (!stream_in) {
+        if (any_conv) launches += launch_convert(B.pages, n, max_sh, max_sw, st);
+        if (any_red) launches += launch_reduce(B.pages, n, max_rh, max_rw, st);
+        if (any_h) launches += launch_resample_h(B.pages, n, max_resh_rows, max_w, st);
+        if (any_v) launches += launch_resample_v(B.pages, n, max_h, max_wc, st);
+    }
+    CU(cudaEventRecord(h->ev[EV_PIXEL], st));
+    if (!stream_in) {
+        launches += launch_png_filter(B.pages, n, max_h, max_wc, o.optimize, B.row_adler, st);
+        launches += launch_adler_combine(B.pages, n, B.row_adler, B.page_adler, st);
+    } else {
+        for (int i = 0; i < n; i++)     // stage-level: Adler-32 of a given stream (scratch: row_adler is unused here)
+            launches += launch_adler_flat(A + plans[i].o_filt, (uint64_t)plans[i].filt_len,
+                                          reinterpret_cast<uint32_t*>(A + o_tokens), B.page_adler + i, st);
+    }
+    CU(cudaEventRecord(h->ev[EV_FILTER], st));
+    if (need_lz) launches += launch_lz(B, st);
+    CU(cudaEventRecord(h->ev[EV_LZ], st));
+    if (need_huff) {
+        launches += launch_huff_build(B, st);
+        launches += launch_layout(B, st);
+        launches += launch_payload_init(B, st);
+        launches += launch_huff_emit(B, st);
+    }
+    CU(cudaEventRecord(h->ev[EV_HUFF], st));
+    if (need_huff) launches += launch_png_finish(B, st);
+    CU(cudaEventRecord(h->ev[EV_ASSEMBLE], st));
+    if (need_huff) launches += launch_base64_pages(B, st);
+    CU(cudaEventRecord(h->ev[EV_B64], st));
+    CU(cudaGetLastError());
+    // results block -> pinned host (after the descriptor mirror)
+    uint8_t* HR = M + align_up(desc_bytes, 64);
+    CU(cudaMemcpyAsync(HR, R, res_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out.png_off = reinterpret_cast<const uint64_t*>(HR); out.png_len = out.png_off + n; out.b64_off = out.png_len + n; out.b64_len = out.b64_off + n;
+    out.totals = out.b64_len + n;
+    out.adler = reinterpret_cast<const uint32_t*>(out.totals + 2);
+    const uint32_t err = *reinterpret_cast<const uint32_t*>(HR + res_bytes - 8);
+    if (err) return fail(VCP_ESIZE, "internal output bound exceeded (flags %u)", err);
+    out.d_png = B.png; out.d_b64 = B.b64; out.d_filt0 = A; out.d_tokens = B.tokens; out.d_sub_ntok = B.sub_ntok; out.d_sub_hist = B.sub_hist;
+    out.nsub = nsub; out.nblocks = nblocks;
+    h->stats.kernel_launches += launches;
+    h->stats.in_bytes += in_bytes; h->stats.filtered_bytes += filt_bytes;
+    float ms = 0;
+    auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms; };
+    h->stats.ms_h2d += el(EV_START, EV_H2D); h->stats.ms_convert += el(EV_H2D, EV_PIXEL); h->stats.ms_filter += el(EV_PIXEL, EV_FILTER);
+    h->stats.ms_lz += el(EV_FILTER, EV_LZ); h->stats.ms_huff += el(EV_LZ, EV_HUFF); h->stats.ms_assemble += el(EV_HUFF, EV_ASSEMBLE);
+    h->stats.ms_b64 += el(EV_ASSEMBLE, EV_B64);
+    return 0;
+}
+
+void reset_stats(vcp_handle* h) { const uint64_t a = h->stats.arena_bytes; memset(&h->stats, 0, sizeof h->stats); h->stats.arena_bytes = a; }
+
+}  // namespace
+
+// ================================================================================================= public C ABI
+extern "C" {
+
+int vcp_version(void) { return VCP_VERSION; }
+const char* vcp_last_error(void) { return g_err.c_str(); }
+
+int vcp_init(int device, vcp_handle** out) {
+    if (!out) return fail(VCP_EINVAL, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(VCP_EINVAL, "no CUDA device %d (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(VCP_ECUDA, "libvcprep is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    vcp_handle* h = new vcp_handle();
+    h->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(VCP_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    if (const char* g = getenv("VCP_GROUP_BYTES")) { const long long v = atoll(g); if (v >= (1 << 20)) h->group_bytes = (size_t)v; }
+    *out = h;
+    return 0;
+}
+
+void vcp_destroy(vcp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->arena) cudaFree(h->arena);
+    if (h->meta) cudaFreeHost(h->meta);
+    for (int i = 0; i < EV_COUNT; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int vcp_output_bound(const vcp_page_desc* pages, int n, const vcp_opts* opts, uint64_t* png_bytes, uint64_t* b64_bytes) {
+    if (n < 0 || (n > 0 && !pages) || !opts) return fail(VCP_EINVAL, "bad arguments");
+    uint64_t p = 0, b = 0;
+    for (int i = 0; i < n; i++) {
+        PagePlan P;
+        if (plan_geometry(pages[i], *opts, P) != 0) continue;      // a bad page produces no output
+        p += P.png_bound; b += b64_bound_of(P.png_bound);
+    }
+    if (png_bytes) *png_bytes = p + 64;
+    if (b64_bytes) *b64_bytes = opts->want_b64 ? b + 64 : 0;
+    return 0;
+}
+
+int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts,
+                      void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results) {
+    if (!h || n < 0 || (n > 0 && (!pages || !results)) || !opts) return fail(VCP_EINVAL, "bad arguments");
+    if (n > 0 && !out_png) return fail(VCP_EINVAL, "out_png is NULL");
+    if (opts->want_b64 && n > 0 && !out_b64) return fail(VCP_EINVAL, "want_b64 set but out_b64 is NULL");
+    if (opts->out_channels != 0 && opts->out_channels != 1 && opts->out_channels != 3) return fail(VCP_EINVAL, "out_channels must be 0, 1 or 3");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    reset_stats(h);
+    // per-page validation: a bad page gets its own status and is left out of the launch set
+    std::vector<PagePlan> all(n);
+    for (int i = 0; i < n; i++) {
+        memset(&results[i], 0, sizeof results[i]);
+        const int rc = plan_geometry(pages[i], *opts, all[i]);
+        all[i].status = rc;
+        results[i].status = rc;
+    }
+    uint64_t png_used = 0, b64_used = 0;
+    const cudaMemcpyKind kind = opts->dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    int i0 = 0;
+    while (i0 < n) {
+        // next group: consecutive good pages up to group_bytes of filtered stream
+        std::vector<PagePlan> g; std::vector<int> idx;
+        size_t bytes = 0;
+        int i = i0;
+        for (; i < n; i++) {
+            if (all[i].status) continue;
+            const size_t fb = (size_t)all[i].filt_len + (size_t)all[i].sw * all[i].sh * all[i].sc / 4;
+            if (!g.empty() && bytes + fb > h->group_bytes) break;
+            g.push_back(all[i]); idx.push_back(i); bytes += fb;
+        }
+        i0 = i;
+        if (g.empty()) break;
+        GroupOut go;
+        int rc = run_group(h, g, *opts, RUN_FULL, go);
+        if (rc) return rc;
+        const uint64_t gp = go.totals[0], gb = go.totals[1];
+        if (png_used + gp > png_cap) return fail(VCP_ESIZE, "out_png too small: need %llu more bytes at offset %llu (cap %llu); size it with vcp_output_bound",
+                                                 (unsigned long long)gp, (unsigned long long)png_used, (unsigned long long)png_cap);
+        if (opts->want_b64 && b64_used + gb > b64_cap) return fail(VCP_ESIZE, "out_b64 too small (cap %llu)", (unsigned long long)b64_cap);
+        cudaEvent_t e0 = h->ev[EV_B64], e1 = h->ev[EV_D2H];
+        CU(cudaEventRecord(e0, h->stream));
+        if (gp) CU(cudaMemcpyAsync((uint8_t*)out_png + png_used, go.d_png, gp, kind, h->stream));
+        if (opts->want_b64 && gb) CU(cudaMemcpyAsync((uint8_t*)out_b64 + b64_used, go.d_b64, gb, kind, h->stream));
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); h->stats.ms_d2h += ms;
+        for (size_t k = 0; k < idx.size(); k++) {
+            vcp_page_result& r = results[idx[k]];
+            r.width = g[k].w; r.height = g[k].h; r.channels = g[k].c;
+            r.png_off = png_used + go.png_off[k]; r.png_len = go.png_len[k];
+            if (opts->want_b64) { r.b64_off = b64_used + go.b64_off[k]; r.b64_len = go.b64_len[k]; }
+            r.adler32 = go.adler[k]; r.n_idat = (uint32_t)g[k].nblk;
+            h->stats.png_bytes += r.png_len; h->stats.b64_bytes += r.b64_len;
+        }
+        png_used += gp; b64_used += gb;
+    }
+    h->stats.ms_total = h->stats.ms_h2d + h->stats.ms_convert + h->stats.ms_filter + h->stats.ms_lz + h->stats.ms_huff +
+                        h->stats.ms_assemble + h->stats.ms_b64 + h->stats.ms_d2h;
+    return 0;
+}
+
+int vcp_get_stats(vcp_handle* h, vcp_stats* out) {
+    if (!h || !out) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    *out = h->stats;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stage-level entry points
+namespace {
+// upload one PageD built on the host and return its device address (uses the head of the arena's descriptor area)
+int stage_page(vcp_handle* h, const PageD& D, size_t extra_bytes, uint8_t** extra, const PageD** d_page) {
+    const size_t need = 1024 + align_up(extra_bytes, 256) + 512;
+    int rc = ensure_arena(h, need); if (rc) return rc;
+    rc = ensure_meta(h, 4096); if (rc) return rc;
+    memcpy(h->meta, &D, sizeof D);
+    CU(cudaMemcpyAsync(h->arena, h->meta, sizeof D, cudaMemcpyHostToDevice, h->stream));
+    *d_page = reinterpret_cast<const PageD*>(h->arena);
+    if (extra) *extra = h->arena + 1024;
+    return 0;
+}
+}  // namespace
+
+int vcp_convert(vcp_handle* h, const void* d_src, int width, int height, int src_channels, int64_t row_stride,
+                void* d_dst, int dst_channels) {
+    if (!h || !d_src || !d_dst || width <= 0 || height <= 0) return fail(VCP_EINVAL, "bad arguments");
+    if (src_channels < 1 || src_channels > 4 || (dst_channels != 1 && dst_channels != 3)) return fail(VCP_EINVAL, "unsupported conversion %d -> %d channels", src_channels, dst_channels);
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    PageD D = {};
+    D.src = (const uint8_t*)d_src; D.src_stride = row_stride ? row_stride : (int64_t)width * src_channels;
+    D.sw = width; D.sh = height; D.sc = src_channels; D.c = dst_channels; D.conv = (uint8_t*)d_dst;
+    const PageD* dp; int rc = stage_page(h, D, 0, nullptr, &dp); if (rc) return rc;
+    launch_convert(dp, 1, height, width, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vcp_resample_coeffs(int in_size, int out_size, int filter, float box0, float box1, int32_t* bounds, int32_t* kk, int* ksize) {
+    if (resample_coeffs_host(in_size, out_size, filter, box0, box1, bounds, kk, ksize) != 0) return fail(VCP_EINVAL, "bad resample parameters");
+    return 0;
+}
+
+int vcp_reduce(vcp_handle* h, const void* d_src, int width, int height, int channels, void* d_dst, int fx, int fy) {
+    if (!h || !d_src || !d_dst || width <= 0 || height <= 0 || channels < 1 || channels > 4 || fx < 1 || fy < 1) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    PageD D = {};
+    D.sw = width; D.sh = height; D.sc = channels; D.c = channels; D.fx = fx; D.fy = fy;
+    D.rw = (width + fx - 1) / fx; D.rh = (height + fy - 1) / fy;
+    D.rdin = (const uint8_t*)d_src; D.rdin_stride = (int64_t)width * channels; D.red = (uint8_t*)d_dst;
+    const PageD* dp; int rc = stage_page(h, D, 0, nullptr, &dp); if (rc) return rc;
+    launch_reduce(dp, 1, D.rh, D.rw, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int channels,
+                 void* d_dst, int out_width, int out_height, int filter) {
+    if (!h || !d_src || !d_dst || width <= 0 || height <= 0 || out_width <= 0 || out_height <= 0) return fail(VCP_EINVAL, "bad arguments");
+    if (channels != 1 && channels != 3) return fail(VCP_EINVAL, "resample supports L and RGB");
+    if (filter < VCP_LANCZOS || filter > VCP_HAMMING) return fail(VCP_EINVAL, "unsupported resample filter %d", filter);
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    const bool need_h = out_width != width, need_v = out_height != height;
+    if (!need_h && !need_v) {
+        CU(cudaMemcpyAsync(d_dst, d_src, (size_t)width * height * channels, cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    const Coeffs* ch = need_h ? get_coeffs(h, width, out_width, filter, 0.f, (float)width) : nullptr;
+    const Coeffs* cv = need_v ? get_coeffs(h, height, out_height, filter, 0.f, (float)height) : nullptr;
+    if ((need_h && !ch) || (need_v && !cv)) return fail(VCP_EINVAL, "bad resample parameters");
+    std::vector<int32_t> blob;
+    size_t ihb = 0, ihk = 0, ivb = 0, ivk = 0;
+    if (ch) { ihb = blob.size(); blob.insert(blob.end(), ch->bounds.begin(), ch->bounds.end()); ihk = blob.size(); blob.insert(blob.end(), ch->kt.begin(), ch->kt.end()); }
+    if (cv) { ivb = blob.size(); blob.insert(blob.end(), cv->bounds.begin(), cv->bounds.end()); ivk = blob.size(); blob.insert(blob.end(), cv->kt.begin(), cv->kt.end()); }
+    const size_t tmp_bytes = (need_h && need_v) ? (size_t)out_width * height * channels : 0;
+    const size_t extra = align_up(blob.size() * 4, 256) + tmp_bytes + 256;
+    int rc = ensure_arena(h, 1024 + extra + 512); if (rc) return rc;
+    int32_t* d_blob = reinterpret_cast<int32_t*>(h->arena + 1024);
+    uint8_t* d_tmp = h->arena + 1024 + align_up(blob.size() * 4, 256);
+    CU(cudaMemcpyAsync(d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));      // blob is pageable host memory
+    PageD D = {};
+    D.c = channels; D.rw = width; D.rh = height; D.w = out_width; D.h = out_height;
+    D.hin = (const uint8_t*)d_src; D.hin_stride = (int64_t)width * channels;
+    const uint8_t* cur = D.hin; int64_t cur_stride = D.hin_stride;
+    if (need_h) {
+        D.tmp = need_v ? d_tmp : (uint8_t*)d_dst; D.hb = d_blob + ihb; D.hk = d_blob + ihk; D.hks = ch->ksize;
+        cur = D.tmp; cur_stride = (int64_t)out_width * channels;
+    }
+    D.vin = cur; D.vin_stride = cur_stride;
+    if (need_v) { D.vout = (uint8_t*)d_dst; D.vb = d_blob + ivb; D.vk = d_blob + ivk; D.vks = cv->ksize; }
+    const PageD* dp; rc = stage_page(h, D, 0, nullptr, &dp); if (rc) return rc;
+    if (need_h) launch_resample_h(dp, 1, height, out_width, h->stream);
+    if (need_v) launch_resample_v(dp, 1, out_height, out_width * channels, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vcp_png_filter(vcp_handle* h, const void* d_pix, int width, int height, int channels, int optimize,
+                   void* d_dst, uint32_t* adler32_out) {
+    if (!h || !d_pix || !d_dst || width <= 0 || height <= 0 || channels < 1 || channels > 4) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    vcp_page_desc d = {}; d.src = d_pix; d.width = width; d.height = height; d.channels = channels;
+    vcp_opts o = {}; o.out_channels = 0; o.optimize = optimize; o.src_device = 1; o.compress_level = 6;
+    std::vector<PagePlan> g(1);
+    int rc = plan_geometry(d, o, g[0]); if (rc) return rc;
+    GroupOut go;
+    rc = run_group(h, g, o, RUN_FILTER_ONLY, go); if (rc) return rc;
+    CU(cudaMemcpyAsync(d_dst, h->arena + go.filt_off[0], (size_t)g[0].filt_len, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (adler32_out) *adler32_out = go.adler[0];
+    return 0;
+}
+
+static int stream_plan(const void* d_stream, uint64_t len, int bpp, PagePlan& P) {
+    if (!d_stream || len == 0 || len >= ((uint64_t)1 << 31) - (1 << 20)) return fail(VCP_EINVAL, "bad stream length %llu", (unsigned long long)len);
+    if (bpp < 1 || bpp > 4) return fail(VCP_EINVAL, "bpp must be 1..4");
+    P = PagePlan();
+    P.src = (const uint8_t*)d_stream; P.c = bpp; P.w = 1; P.h = 1; P.filt_len = (int64_t)len;
+    P.nblk = (int)((P.filt_len + kBlockBytes - 1) / kBlockBytes);
+    P.nsub = 0;
+    for (int b = 0; b < P.nblk; b++) {
+        const int64_t l = std::min<int64_t>(kBlockBytes, P.filt_len - (int64_t)b * kBlockBytes);
+        P.nsub += (int)((l + kSubBytes - 1) / kSubBytes);
+    }
+    P.png_bound = png_bound_of(P.filt_len, P.nblk);
+    return 0;
+}
+
+int vcp_deflate(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, int level, void* d_out, uint64_t cap, uint64_t* out_len) {
+    if (!h || !d_out || !out_len) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    std::vector<PagePlan> g(1);
+    int rc = stream_plan(d_stream, len, bpp, g[0]); if (rc) return rc;
+    vcp_opts o = {}; o.compress_level = level; o.src_device = 1;
+    GroupOut go;
+    rc = run_group(h, g, o, RUN_STREAM, go); if (rc) return rc;
+    if (go.png_len[0] > cap) return fail(VCP_ESIZE, "output buffer too small: need %llu", (unsigned long long)go.png_len[0]);
+    CU(cudaMemcpyAsync(d_out, go.d_png + go.png_off[0], go.png_len[0], cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out_len = go.png_len[0];
+    return 0;
+}
+
+int vcp_lz_tokens(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, uint32_t* d_tokens, uint32_t* sub_ntok_host, uint32_t* sub_hist_host) {
+    if (!h || !d_tokens || !sub_ntok_host) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    std::vector<PagePlan> g(1);
+    int rc = stream_plan(d_stream, len, bpp, g[0]); if (rc) return rc;
+    vcp_opts o = {}; o.compress_level = 6; o.src_device = 1;
+    GroupOut go;
+    rc = run_group(h, g, o, RUN_LZ_ONLY, go); if (rc) return rc;
+    // tokens are indexed by byte offset from the filtered region base; the stream sits kStreamPad after it
+    CU(cudaMemcpyAsync(d_tokens, go.d_tokens + kStreamPad, (size_t)len * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(sub_ntok_host, go.d_sub_ntok, (size_t)go.nsub * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (sub_hist_host) CU(cudaMemcpyAsync(sub_hist_host, go.d_sub_hist, (size_t)go.nsub * kHistSize * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vcp_adler32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) {
+    if (!h || !out || (len && !d_data)) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    const size_t nseg = (size_t)((len + 4095) / 4096);
+    int rc = ensure_arena(h, 1024 + nseg * 8 + 512); if (rc) return rc;
+    rc = ensure_meta(h, 4096); if (rc) return rc;
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(h->arena);
+    launch_adler_flat((const uint8_t*)d_data, len, reinterpret_cast<uint32_t*>(h->arena + 1024), d_out, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->meta, d_out, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = *reinterpret_cast<uint32_t*>(h->meta);
+    return 0;
+}
+
+int vcp_crc32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) {
+    if (!h || !out || (len && !d_data)) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_arena(h, 4096); if (rc) return rc;
+    rc = ensure_meta(h, 4096); if (rc) return rc;
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(h->arena);
+    launch_crc_flat((const uint8_t*)d_data, len, d_out, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->meta, d_out, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = *reinterpret_cast<uint32_t*>(h->meta);
+    return 0;
+}
+
+int vcp_base64(vcp_handle* h, const void* d_src, uint64_t len, void* d_dst) {
+    if (!h || (len && (!d_src || !d_dst))) return fail(VCP_EINVAL, "bad arguments");
+    if (((uintptr_t)d_src & 3) || ((uintptr_t)d_dst & 15)) return fail(VCP_EINVAL, "vcp_base64 needs a 4-byte aligned source and a 16-byte aligned destination");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    launch_base64_flat((const uint8_t*)d_src, len, (uint8_t*)d_dst, h->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     for (int i = lane; i < kHistSize; i += 32) hout[i] = M.hist[i];
 }
 
-int launch_lz(const BatchD& b, int, cudaStream_t st) {
+int launch_lz(const BatchD& b, cudaStream_t st) {
     if (b.nsub == 0) return 0;
     const size_t smem = sizeof(WarpMem) * kLzWarps;
     static bool configured = false;

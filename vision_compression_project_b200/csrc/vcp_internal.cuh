@@ -7,11 +7,14 @@
 namespace vcp {
 
 constexpr int kSubBytes   = 32768;        // LZ sub-chunk: one warp, one 64 Ki-position window of u16 table entries
+constexpr int kBlockBytes = 512 * 1024;   // deflate block = one IDAT chunk = 16 sub-chunks
 constexpr int kMaxDist    = 32768;
 constexpr int kMaxMatch   = 258;
 constexpr int kNumLL      = 286;
 constexpr int kNumD       = 30;
 constexpr int kHistSize   = kNumLL + kNumD;   // 316
+constexpr int kCodeStride = 320;          // per-block code table stride (u16 codes / u8 lengths)
+constexpr int kHdrBytes   = 768;          // per-block dynamic-header scratch (<= 17 + 57 + 316*14 bits)
 constexpr int kStreamPad  = 256;          // bytes of addressable slack before and after every page stream
 
 // One page of a batch (lives in device memory, built on the host per plan).
@@ -34,10 +37,11 @@ struct PageD {
     int64_t pix_stride;      // bytes between rows of pix
     const int32_t* hb; const int32_t* hk; int32_t hks;   // horizontal bounds (xmin,n)*w, coeffs [k][w] (transposed), ksize
     const int32_t* vb; const int32_t* vk; int32_t vks;   // vertical
-    uint8_t* filt;           // filtered stream: h * (1 + w*c) bytes
+    uint8_t* filt;           // filtered stream: h * (1 + w*c) bytes (256-byte aligned, kStreamPad slack either side)
     int64_t filt_len;
     int32_t row0;            // first entry of this page in the per-row Adler partial array
     int32_t blk0, nblk;      // deflate blocks of this page
+    int32_t color_type;      // PNG colour type of the output (0 L, 2 RGB, 4 LA, 6 RGBA)
     int32_t status;
 };
 
@@ -47,42 +51,56 @@ struct BlockD {
     int32_t first, last;     // first / last block of its page
     int64_t start, len;      // byte range inside the page's filtered stream
     int32_t sub0, nsub;      // LZ sub-chunks of this block (global numbering)
-    int64_t slot_off;        // offset of this block's output slot in the slot buffer
-    int64_t slot_cap;
 };
 
 struct BatchD {
     const PageD* pages; int32_t npages;
     const BlockD* blocks; int32_t nblocks;
     const uint32_t* sub2blk; int32_t nsub;
-    uint32_t* tokens;        // u32 per filtered byte position (token j of sub-chunk at stream offset o -> tokens[tok_base(o) + j])
+    const uint8_t* filt_base;    // base of the filtered buffer (token index = filt ptr - filt_base)
+    uint32_t* tokens;        // u32 per filtered byte position; tokens of a sub-chunk are compact from its first position
     uint32_t* sub_ntok;      // tokens per sub-chunk
     uint32_t* sub_hist;      // nsub * 316 histogram (without EOB)
-    uint32_t* row_adler;     // per row: (sum & 0xFFFF) | (weighted << 16) ... see png_filter.cu
+    uint32_t* row_adler;     // per row partials, see png_filter.cu
     uint32_t* page_adler;    // per page
-    uint8_t* slots;          // per-block compressed payloads
-    uint32_t* blk_len;       // payload bytes per block
-    uint32_t* blk_crc;       // CRC-32 of "IDAT"+payload per block
-    uint8_t* png;            // assembled PNGs
-    uint64_t* png_off; uint64_t* png_len;   // per page
-    uint8_t* b64;
+    // per deflate block, written by k_huff_build
+    uint16_t* blk_code;      // nblocks * kCodeStride: bit-reversed canonical codes, [0,286) lit/len, [286,316) dist
+    uint8_t*  blk_clen;      // nblocks * kCodeStride: code lengths
+    uint8_t*  blk_hdr;       // nblocks * kHdrBytes: BFINAL/BTYPE + dynamic header bits
+    uint32_t* blk_hdr_bits;
+    uint64_t* blk_eob_bit;   // bit offset of the EOB code inside the block body
+    uint64_t* blk_body_bits; // total bits of the body (incl. EOB and, if not last, the 3-bit empty stored header)
+    uint32_t* blk_stored;    // 1 = stored fallback
+    uint32_t* blk_len;       // payload bytes (zlib header + body + sync marker / Adler-32)
+    uint64_t* sub_bitoff;    // per sub-chunk: bit offset of its first token inside the block body
+    // layout (k_layout)
+    uint64_t* blk_dst;       // byte offset in png of the block's payload (after the 8-byte chunk header when framed)
+    uint8_t* png; uint64_t png_cap;
+    uint64_t* png_off; uint64_t* png_len;   // per page (offsets 16-byte aligned)
+    uint8_t* b64; uint64_t b64_cap;
     uint64_t* b64_off; uint64_t* b64_len;
-    int64_t tok_base_of_filt0;   // unused (tokens are indexed by filtered-buffer byte offset)
-    const uint8_t* filt_base;    // base of the filtered buffer (token index = filt ptr - filt_base)
+    uint64_t* totals;        // [0] = png bytes used, [1] = b64 bytes used
+    uint32_t* err;           // [0] != 0: capacity exceeded
+    int32_t framed;          // 1 = PNG container (sig/IHDR/IDAT/IEND); 0 = bare zlib stream (vcp_deflate)
+    int32_t level;           // 0 = stored only
+    int32_t want_b64;
 };
 
 // ---- launchers (each returns the number of kernels it launched) ----
-int launch_convert(const PageD* d_pages, int npages, int max_rows, int max_rowbytes, cudaStream_t st);
+int launch_convert(const PageD* d_pages, int npages, int max_rows, int max_w, cudaStream_t st);
 int launch_reduce(const PageD* d_pages, int npages, int max_rh, int max_rw, cudaStream_t st);
 int launch_resample_h(const PageD* d_pages, int npages, int max_rh, int max_w, cudaStream_t st);
 int launch_resample_v(const PageD* d_pages, int npages, int max_h, int max_wc, cudaStream_t st);
 int launch_png_filter(const PageD* d_pages, int npages, int max_h, int max_rowbytes, int optimize,
                       uint32_t* row_adler, cudaStream_t st);
 int launch_adler_combine(const PageD* d_pages, int npages, const uint32_t* row_adler, uint32_t* page_adler, cudaStream_t st);
-int launch_lz(const BatchD& b, int bpp_hint_unused, cudaStream_t st);
-int launch_huff(const BatchD& b, int level, cudaStream_t st);
-int launch_assemble(const BatchD& b, uint64_t png_cap, uint32_t* d_err, cudaStream_t st);
-int launch_base64(const BatchD& b, uint64_t b64_cap, uint32_t* d_err, cudaStream_t st);
+int launch_lz(const BatchD& b, cudaStream_t st);
+int launch_huff_build(const BatchD& b, cudaStream_t st);
+int launch_layout(const BatchD& b, cudaStream_t st);
+int launch_payload_init(const BatchD& b, cudaStream_t st);
+int launch_huff_emit(const BatchD& b, cudaStream_t st);
+int launch_png_finish(const BatchD& b, cudaStream_t st);
+int launch_base64_pages(const BatchD& b, cudaStream_t st);
 int launch_base64_flat(const uint8_t* src, uint64_t len, uint8_t* dst, cudaStream_t st);
 int launch_adler_flat(const uint8_t* data, uint64_t len, uint32_t* scratch, uint32_t* out, cudaStream_t st);
 int launch_crc_flat(const uint8_t* data, uint64_t len, uint32_t* out, cudaStream_t st);
