@@ -88,6 +88,10 @@ const char* vcp_last_error(void);
 int  vcp_init(int device, vcp_handle** out);
 void vcp_destroy(vcp_handle* h);
 
+/* Validate one page against the options without running anything: VCP_OK, or the VCP_E* that
+ * vcp_prepare_batch would put in its status (message in vcp_last_error). */
+int vcp_check_page(const vcp_page_desc* page, const vcp_opts* opts);
+
 /* Worst-case output sizes for a batch, so the caller can size out_png / out_b64. */
 int vcp_output_bound(const vcp_page_desc* pages, int n, const vcp_opts* opts,
                      uint64_t* png_bytes, uint64_t* b64_bytes);

@@ -218,17 +218,19 @@ int64_t dm_lz_subchunk(const uint8_t* S, int64_t F, int64_t s, int64_t e, const 
                 i += 1; next = q + 1;
             }
         }
-        /* ---- insert the window's positions (highest lane of a same-bucket group wins) */
+        /* ---- insert the window's positions (highest lane of a same-bucket group wins); with ins_limit only the
+           positions the parse has consumed (q < next) are inserted, so a position is never inserted twice */
+        const int64_t iend = (P->ins_limit && next < e) ? next : e;
         for (int k = 0; k < WIN; k++) {
-            int64_t q = p + k; if (q >= e) continue;
+            int64_t q = p + k; if (q >= iend) continue;
             if (q + 2 < F) {
                 uint32_t h = hash3(S + q, hb); int winner = 1;
-                for (int j = k + 1; j < WIN; j++) { int64_t q2 = p + j; if (q2 >= e || q2 + 2 >= F) continue; if (hash3(S + q2, hb) == h) { winner = 0; break; } }
+                for (int j = k + 1; j < WIN; j++) { int64_t q2 = p + j; if (q2 >= iend || q2 + 2 >= F) continue; if (hash3(S + q2, hb) == h) { winner = 0; break; } }
                 if (winner) INSERT(q);
             }
             if (nb2 && q + nb2 <= F) {
                 uint32_t h = hashN(S + q, nb2, hb2); int winner = 1;
-                for (int j = k + 1; j < WIN; j++) { int64_t q2 = p + j; if (q2 >= e || q2 + nb2 > F) continue; if (hashN(S + q2, nb2, hb2) == h) { winner = 0; break; } }
+                for (int j = k + 1; j < WIN; j++) { int64_t q2 = p + j; if (q2 >= iend || q2 + nb2 > F) continue; if (hashN(S + q2, nb2, hb2) == h) { winner = 0; break; } }
                 if (winner) INSERT2(q);
             }
         }

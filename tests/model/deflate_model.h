@@ -27,6 +27,7 @@ typedef struct {
     int32_t cost_margin;  /* quarter bits a match must save */
     int32_t cost_warm;    /* tokens needed in the sub-chunk before pricing starts */
     int32_t hash2_ways;
+    int32_t ins_limit;    /* 1: a window inserts only the positions its parse consumed (q < next) */
     int64_t block_bytes;  /* deflate block (multiple of sub_bytes) */
 } dm_params;
 typedef struct { int64_t tokens, blocks, stored_blocks; } dm_stats;

@@ -94,7 +94,7 @@ def test_convert_modes_and_options(V):
 
 def test_edge_sizes(V):
     rng = np.random.default_rng(22)
-    for (w, h) in [(1, 1), (1, 7), (7, 1), (2, 2), (3, 1), (1365, 1), (1, 3000), (5, 5), (21846, 2), (17, 333)]:
+    for (w, h) in [(1, 1), (1, 7), (7, 1), (2, 2), (3, 1), (1365, 1), (1, 3000), (5, 5), (21845, 2), (17, 333)]:
         for c, mode in ((1, "L"), (3, "RGB")):
             px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
             im = Image.fromarray(px[:, :, 0] if c == 1 else px, mode)
@@ -143,6 +143,8 @@ def test_errors_and_partial_batch(V, synth):
     assert res[0].png == res[2].png and res[1].png is None
     U.check_png_against(res[0].png, good)
     assert V.prepare_pages([]) == []
+    with pytest.raises(ValueError, match="too large"):
+        V.prepare_page(np.zeros((2, 21846, 3), np.uint8))                           # row longer than the row kernels stage
 
 
 def test_five_threads_like_the_reference_pool(V, synth):

@@ -44,6 +44,7 @@ SYMBOLS = {
     "vcp_last_error": (C.c_char_p, []),
     "vcp_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "vcp_destroy": (None, [C.c_void_p]),
+    "vcp_check_page": (C.c_int, [C.POINTER(PageDesc), C.POINTER(Opts)]),
     "vcp_output_bound": (C.c_int, [C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vcp_prepare_batch": (C.c_int, [C.c_void_p, C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.c_void_p, C.c_uint64,
                                     C.c_void_p, C.c_uint64, C.POINTER(PageResult)]),
@@ -84,13 +85,15 @@ def last_error() -> str:
     return (load().vcp_last_error() or b"").decode("utf-8", "replace")
 
 
+def error_for(rc: int, msg: str) -> Exception:
+    if rc in (VCP_EINVAL, VCP_ESIZE):
+        return ValueError(msg)
+    if rc == VCP_ENOMEM:
+        return MemoryError(msg)
+    return RuntimeError(msg)
+
+
 def check(rc: int) -> None:
     """Map a VCP_E* code to the exception the reference's per-page try/except expects (pdf_extract.py:133-136)."""
-    if rc == VCP_OK:
-        return
-    msg = last_error()
-    if rc in (VCP_EINVAL, VCP_ESIZE):
-        raise ValueError(msg)
-    if rc == VCP_ENOMEM:
-        raise MemoryError(msg)
-    raise RuntimeError(msg)
+    if rc != VCP_OK:
+        raise error_for(rc, last_error())

@@ -264,21 +264,23 @@ class PagePrep:
         return out  # type: ignore[return-value]
 
     def _run_chunk(self, idx, srcs, out, dev, size, max_side, mode, resample, reducing_gap, level, optimize, want_b64):
-        good, descs_l = [], []
-        for k in idx:
-            try:
-                descs_l.append(self._plan(srcs[k], size, max_side, mode, resample, reducing_gap))
-                good.append(k)
-            except ValueError as e:
-                out[k] = PreparedPage(None, None, (0, 0), "", error=f"ValueError: {e}")
-        m = len(good)
-        if m == 0:
-            return
-        descs = (N.PageDesc * m)(*descs_l)
         opts = N.Opts()
         opts.out_channels = {"RGB": 3, "L": 1, None: 0}[mode]
         opts.resample, opts.compress_level, opts.optimize = int(resample), int(level), int(bool(optimize))
         opts.want_b64, opts.src_device, opts.dst_device = int(bool(want_b64)), int(bool(dev)), 0
+        good, descs_l = [], []
+        for k in idx:
+            try:
+                d = self._plan(srcs[k], size, max_side, mode, resample, reducing_gap)
+                N.check(self.lib.vcp_check_page(C.byref(d), C.byref(opts)))      # per-page message, page stays out of the batch
+                descs_l.append(d)
+                good.append(k)
+            except (ValueError, MemoryError, RuntimeError) as e:
+                out[k] = PreparedPage(None, None, (0, 0), "", error=f"{type(e).__name__}: {e}")
+        m = len(good)
+        if m == 0:
+            return
+        descs = (N.PageDesc * m)(*descs_l)
         bound_png, bound_b64 = self.output_bound(descs, m, opts)
         for attempt in (0, 1):
             cap_png = bound_png if attempt else min(bound_png, max(32 << 20, bound_png // 4))
@@ -330,5 +332,5 @@ def prepare_page(image: Any, *, device: int = 0, **kw) -> PreparedPage:
     r = _engine(device).prepare_pages([image], **kw)[0]
     if r.error is not None:
         kind, _, msg = r.error.partition(": ")
-        raise {"ValueError": ValueError, "TypeError": TypeError}.get(kind, RuntimeError)(msg or r.error)
+        raise {"ValueError": ValueError, "TypeError": TypeError, "MemoryError": MemoryError}.get(kind, RuntimeError)(msg or r.error)
     return r

@@ -212,7 +212,7 @@ int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, Ru
     // filtered streams: one contiguous region so that token index = byte offset from its base
     const size_t o_filt_region = bump.take(0);
     for (auto& P : plans) { bump.take(kStreamPad); P.o_filt = bump.take((size_t)P.filt_len); }
-    bump.take(kStreamPad + 256);
+    bump.take(kStreamPad + 2048);                 // run_end() reads up to 1 KiB + a window past the last stream
     const size_t filt_region_bytes = align_up(bump.off - o_filt_region, 256);
     const bool need_lz = mode != RUN_FILTER_ONLY;
     const bool need_huff = mode == RUN_FULL || mode == RUN_STREAM;
@@ -441,6 +441,13 @@ void vcp_destroy(vcp_handle* h) {
     for (int i = 0; i < EV_COUNT; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+int vcp_check_page(const vcp_page_desc* page, const vcp_opts* opts) {
+    if (!page || !opts) return fail(VCP_EINVAL, "bad arguments");
+    if (opts->out_channels != 0 && opts->out_channels != 1 && opts->out_channels != 3) return fail(VCP_EINVAL, "out_channels must be 0, 1 or 3");
+    PagePlan P;
+    return plan_geometry(*page, *opts, P);
 }
 
 int vcp_output_bound(const vcp_page_desc* pages, int n, const vcp_opts* opts, uint64_t* png_bytes, uint64_t* b64_bytes) {

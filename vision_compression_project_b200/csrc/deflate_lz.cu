@@ -7,17 +7,19 @@
 // bit-for-bit with the sequential model in tests/model/deflate_model.c and inflate the result with zlib.
 //
 // Decomposition: the filtered stream of a page is cut into 32 KiB sub-chunks, one WARP each.  A warp
-// owns two small hash tables in shared memory (3-byte hash: 2^11 buckets x 2 ways, 6-byte hash: 2^10 x 2,
+// owns two small hash tables in shared memory (3-byte hash: 2^11 buckets x 2 ways, 4-byte hash: 2^10 x 2,
 // u16 positions relative to sub-chunk start - 32 KiB, so the previous 32 KiB of the page are addressable
 // history and are inserted before the sub-chunk starts).  It then walks its sub-chunk in windows of 32
 // positions, one per lane:
-//   1. one coalesced 128-byte load of the window, bytes handed to lanes with shuffles;
+//   1. the stream is pulled through three 128-byte register chunks per warp (current, next, prefetched), so a
+//      window's bytes come from shuffles and the global-load latency is hidden behind the previous windows;
 //   2. every lane proposes a match: distance-1 and distance-bpp runs from two 64-bit ballot masks,
-//      up to four hash candidates verified against global memory (exact up to 64 bytes);
+//      up to four hash candidates verified against global memory — all four are loaded at once, 16 bytes per
+//      round trip, in lock-step (exact up to 64 bytes);
 //      short matches are priced against literals with the running histogram (quarter-bit log2);
 //   3. one-step lazy rule between neighbouring lanes (a shuffle), greedy parse from lane 0 resolved by
-//      5 rounds of pointer jumping, last token extended cooperatively to <= 258, maximal distance-1
-//      runs continued without re-hashing;
+//      5 rounds of pointer jumping, last token extended cooperatively to <= 258; a maximal distance-1 run is
+//      measured 1 KiB per round trip and emitted as a burst of 258-tokens without re-hashing;
 //   4. tokens written compactly (rank = popc of the selection mask), histogram by shared atomics,
 //      window positions inserted with atomicMax (highest position wins -> deterministic).
 // Integer/latency bound, not HBM bound: the stream is read ~once from L2/HBM; see DESIGN.md §5.
@@ -28,12 +30,14 @@ namespace vcp {
 namespace {
 
 constexpr int HB3 = 11;               // 3-byte-hash table: 2^11 buckets, u32 = (newest<<16) | older
-constexpr int HB6 = 10;               // 6-byte-hash table: 2^10 buckets, same bucket format
-constexpr int kLzWarps = 4;           // warps (= sub-chunks) per CTA
+constexpr int HB6 = 10;               // 4-byte-hash table: 2^10 buckets, same bucket format
+constexpr int kH2Bytes = 4;           // bytes keyed by the second table
+constexpr int kLzWarps = 2;           // warps (= sub-chunks) per CTA
 constexpr int kLaneCap = 64;          // exact compare length of a hash candidate inside a lane
 constexpr int kLazyMax = 16;
 constexpr int kCostMaxLen = 8;
 constexpr int kCostWarm = 64;
+constexpr unsigned kFull = 0xffffffffu;
 
 struct __align__(16) WarpMem {
     uint32_t t3[1 << HB3];
@@ -66,23 +70,13 @@ __device__ __forceinline__ int dist_sym(int dist) {    // 1..32768 -> 0..29
     return 2 * n + ((v >> (n - 1)) & 1);
 }
 
-// exact match length of S[q..] vs S[c..], up to cap bytes (first 4 bytes of q given)
-__device__ __forceinline__ int lane_match(const uint32_t* __restrict__ S32, int q, int c, uint32_t cur4, int cap) {
-    int wc = c >> 2; const int shc = (c & 3) * 8;
-    uint32_t c0 = __ldg(S32 + wc), c1 = __ldg(S32 + wc + 1);
-    uint32_t x = cur4 ^ __funnelshift_r(c0, c1, shc);
-    if (x) return min(((__ffs(x) - 1) >> 3), cap);
-    int wq = (q >> 2) + 1; const int shq = (q & 3) * 8;
-    uint32_t q0 = __ldg(S32 + wq);
-    int n = 4;
-    while (n < cap) {
-        const uint32_t q1 = __ldg(S32 + wq + 1);
-        c0 = c1; c1 = __ldg(S32 + wc + 2);
-        x = __funnelshift_r(q0, q1, shq) ^ __funnelshift_r(c0, c1, shc);
-        if (x) { n += (__ffs(x) - 1) >> 3; break; }
-        q0 = q1; wq++; wc++; n += 4;
-    }
-    return min(n, cap);
+// number of equal leading bytes of two 16-byte strings given as four words each (16 = all equal)
+__device__ __forceinline__ int eq16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
+    if (x0) return (__ffs(x0) - 1) >> 3;
+    if (x1) return 4 + ((__ffs(x1) - 1) >> 3);
+    if (x2) return 8 + ((__ffs(x2) - 1) >> 3);
+    if (x3) return 12 + ((__ffs(x3) - 1) >> 3);
+    return 16;
 }
 
 // warp-cooperative: length of the common prefix of S[y..] and S[y-d..], up to maxn (128 bytes per step)
@@ -91,16 +85,53 @@ __device__ __forceinline__ int coop_match(const uint32_t* __restrict__ S32, int 
     while (n < maxn) {
         const int k = y + n + 4 * lane;
         const uint32_t x = ldu(S32, k) ^ ldu(S32, k - d);
-        const uint32_t mism = __ballot_sync(0xffffffffu, x != 0);
+        const uint32_t mism = __ballot_sync(kFull, x != 0);
         if (mism) {
             const int first = __ffs(mism) - 1;
-            const uint32_t xx = __shfl_sync(0xffffffffu, x, first);
+            const uint32_t xx = __shfl_sync(kFull, x, first);
             n += 4 * first + ((__ffs(xx) - 1) >> 3);
             break;
         }
         n += 128;
     }
     return min(n, maxn);
+}
+
+// 16-bit mask of the bytes of a uint4 that differ from the replicated byte v4
+__device__ __forceinline__ uint32_t ne_mask16(uint4 x, uint32_t v4) {
+    const uint32_t a = (__vcmpne4(x.x, v4) & 0x08040201u) * 0x01010101u >> 24;
+    const uint32_t b = (__vcmpne4(x.y, v4) & 0x08040201u) * 0x01010101u >> 24;
+    const uint32_t c = (__vcmpne4(x.z, v4) & 0x08040201u) * 0x01010101u >> 24;
+    const uint32_t d = (__vcmpne4(x.w, v4) & 0x08040201u) * 0x01010101u >> 24;
+    return a | (b << 4) | (c << 8) | (d << 12);
+}
+
+// warp-cooperative: first position >= from (and < e) whose byte differs from v; e if none.  1 KiB per round trip.
+__device__ __forceinline__ int run_end(const uint8_t* __restrict__ S, int from, int e, uint32_t v, int lane) {
+    const uint32_t v4 = v * 0x01010101u;
+    int a = from & ~15;
+    int skip = from - a;                                  // bytes of the first 16 that precede `from`
+    while (a < e) {
+        const uint4* g = reinterpret_cast<const uint4*>(S + a) + lane;
+        const uint4 x = __ldg(g), y = __ldg(g + 32);
+        uint32_t mx = ne_mask16(x, v4);
+        if (lane == 0) mx &= ~((1u << skip) - 1u);
+        const uint32_t my = ne_mask16(y, v4);
+        const uint32_t bx = __ballot_sync(kFull, mx != 0);
+        if (bx) {
+            const int f = __ffs(bx) - 1;
+            const uint32_t mm = __shfl_sync(kFull, mx, f);
+            return min(e, a + 16 * f + __ffs(mm) - 1);
+        }
+        const uint32_t by = __ballot_sync(kFull, my != 0);
+        if (by) {
+            const int f = __ffs(by) - 1;
+            const uint32_t mm = __shfl_sync(kFull, my, f);
+            return min(e, a + 512 + 16 * f + __ffs(mm) - 1);
+        }
+        a += 1024; skip = 0;
+    }
+    return e;
 }
 
 }  // namespace
@@ -130,38 +161,67 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     }
     __syncwarp();
 
-    // ---- prime with the previous 32 KiB of the page (window by window, same arithmetic as the main loop's insert)
-    for (int w0 = max(0, s - kMaxDist); w0 < s; w0 += 32) {
-        const int A = w0 & ~3;
-        const uint32_t wv = __ldg(S32 + (A >> 2) + lane);
-        const int o = (w0 - A) + lane, k = o >> 2, sh = (o & 3) * 8;
-        const uint32_t a0 = __shfl_sync(0xffffffffu, wv, k), a1 = __shfl_sync(0xffffffffu, wv, k + 1), a2 = __shfl_sync(0xffffffffu, wv, k + 2);
-        const uint32_t cur4 = __funnelshift_r(a0, a1, sh), nxt4 = __funnelshift_r(a1, a2, sh);
-        const int q = w0 + lane;
-        const bool ok3 = q < s && q + 2 < F, ok6 = q < s && q + 6 <= F;
-        const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
-        const uint32_t h6 = (cur4 * 0x9E3779B1u + (nxt4 & 0xFFFFu) * 0x85EBCA77u) >> (32 - HB6);
-        const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
-        __syncwarp();
-        const uint32_t pos = (uint32_t)(q - base);
-        if (ok3) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
-        if (ok6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
-        __syncwarp();
+    // ---- prime with the previous 32 KiB of the page: 128 bytes (4 windows) per load, next chunk prefetched.
+    //      Per window the arithmetic is the main loop's insert: the highest lane of a bucket group wins (atomicMax)
+    //      and shifts the bucket once.
+    {
+        const int h0 = max(0, s - kMaxDist);                                     // multiple of 128 (s is a multiple of 32 KiB)
+        uint32_t cw = h0 < s ? __ldg(S32 + (h0 >> 2) + lane) : 0u;
+        for (int w0 = h0; w0 < s; w0 += 128) {
+            const uint32_t cn = __ldg(S32 + ((w0 + 128) >> 2) + lane);           // <= 128 bytes past s: still inside the stream or its pad
+            const int sh = (lane & 3) * 8;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int i = 8 * t + (lane >> 2);
+                const uint32_t a0 = __shfl_sync(kFull, cw, i);
+                uint32_t a1 = __shfl_sync(kFull, cw, (i + 1) & 31);
+                if (t == 3) { const uint32_t b1 = __shfl_sync(kFull, cn, (i + 1) & 31); if (i + 1 >= 32) a1 = b1; }
+                const uint32_t cur4 = __funnelshift_r(a0, a1, sh);
+                const int q = w0 + 32 * t + lane;
+                const bool ok3 = q + 2 < F, ok6 = q + kH2Bytes <= F;
+                const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
+                const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
+                const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
+                __syncwarp();
+                const uint32_t pos = (uint32_t)(q - base);
+                if (ok3) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
+                if (ok6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
+                __syncwarp();
+            }
+            cw = cn;
+        }
     }
 
-    // ---- main loop
+    // ---- main loop.  Register window: three 128-byte chunks at A0, A0+128, A0+256 (A0 multiple of 128).
     int p = s;
     uint32_t ntok = 0;
+    int A0 = ((p - 4) >> 7) << 7;                                                // may be -128: the pad in front of the stream is addressable
+    uint32_t w0r = __ldg(S32 + (A0 >> 2) + lane), w1r = __ldg(S32 + (A0 >> 2) + 32 + lane), w2r = __ldg(S32 + (A0 >> 2) + 64 + lane);
     while (p < e) {
-        const int A = (p - 4) & ~3;                                              // >= -4: the pad in front of the stream is addressable
-        const uint32_t wv = __ldg(S32 + (A >> 2) + lane);
+        int ofs = p - 4 - A0;
+        if (ofs >= 384) {                                                        // long jump: refill
+            A0 = ((p - 4) >> 7) << 7; ofs = p - 4 - A0;
+            w0r = __ldg(S32 + (A0 >> 2) + lane); w1r = __ldg(S32 + (A0 >> 2) + 32 + lane); w2r = __ldg(S32 + (A0 >> 2) + 64 + lane);
+        } else {
+            while (ofs >= 128) {                                                 // slide: the prefetched chunk becomes "next"
+                w0r = w1r; w1r = w2r; A0 += 128; ofs -= 128;
+                w2r = (A0 + 256 < F + 128) ? __ldg(S32 + (A0 >> 2) + 64 + lane) : 0u;
+            }
+        }
         const int q = p + lane;
-        // bytes [q-4, q+8) for the first half, [q+28, q+33) for the second half
-        const int o = (p - 4 - A) + lane, k = o >> 2, sh = (o & 3) * 8;
-        const uint32_t a0 = __shfl_sync(0xffffffffu, wv, k), a1 = __shfl_sync(0xffffffffu, wv, k + 1);
-        const uint32_t a2 = __shfl_sync(0xffffffffu, wv, k + 2), a3 = __shfl_sync(0xffffffffu, wv, k + 3);
+        // V[l] = word (ofs>>2) + l of the register window: bytes [p-4-r, p-4-r+128), r = ofs & 3
+        uint32_t V;
+        {
+            const int kb = (ofs >> 2) + lane;
+            const uint32_t x = __shfl_sync(kFull, w0r, kb & 31), y = __shfl_sync(kFull, w1r, kb & 31);
+            V = (kb & 32) ? y : x;
+        }
+        const int o = (ofs & 3) + lane, k = o >> 2, sh = (o & 3) * 8;
+        const uint32_t a0 = __shfl_sync(kFull, V, k), a1 = __shfl_sync(kFull, V, k + 1), a2 = __shfl_sync(kFull, V, k + 2);
+        const uint32_t a3 = __shfl_sync(kFull, V, k + 3), a4 = __shfl_sync(kFull, V, k + 4), a5 = __shfl_sync(kFull, V, k + 5);
         const uint32_t lo = __funnelshift_r(a0, a1, sh), cur4 = __funnelshift_r(a1, a2, sh), nxt4 = __funnelshift_r(a2, a3, sh);
-        const uint32_t c0 = __shfl_sync(0xffffffffu, wv, k + 8), c1 = __shfl_sync(0xffffffffu, wv, k + 9);
+        const uint32_t q8 = __funnelshift_r(a3, a4, sh), q12 = __funnelshift_r(a4, a5, sh);   // bytes [q+8, q+16)
+        const uint32_t c0 = __shfl_sync(kFull, V, k + 8), c1 = __shfl_sync(kFull, V, k + 9);
         const uint32_t lo2 = __funnelshift_r(c0, c1, sh);                        // bytes [q+28, q+32)
         const uint32_t b2 = (c1 >> sh) & 0xFFu;                                  // byte q+32
         // equality bits for distance 1 and distance bpp at positions q and q+32
@@ -170,13 +230,13 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         const bool eba = (bq == ((lo >> (8 * (4 - bpp))) & 0xFFu)) && q >= bpp;
         const bool e1b = (b2 == (lo2 >> 24));
         const bool ebb = (b2 == ((lo2 >> (8 * (4 - bpp))) & 0xFFu));
-        const unsigned long long m1 = (unsigned long long)__ballot_sync(0xffffffffu, e1a) | ((unsigned long long)__ballot_sync(0xffffffffu, e1b) << 32);
-        const unsigned long long mb = (unsigned long long)__ballot_sync(0xffffffffu, eba) | ((unsigned long long)__ballot_sync(0xffffffffu, ebb) << 32);
+        const unsigned long long m1 = (unsigned long long)__ballot_sync(kFull, e1a) | ((unsigned long long)__ballot_sync(kFull, e1b) << 32);
+        const unsigned long long mb = (unsigned long long)__ballot_sync(kFull, eba) | ((unsigned long long)__ballot_sync(kFull, ebb) << 32);
 
         const int limit = min(kMaxMatch, e - q);                                 // <= 0 for lanes past the sub-chunk
         int bl = 0, bd = 0, be = 0; bool bcap = false;
         const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
-        const uint32_t h6 = (cur4 * 0x9E3779B1u + (nxt4 & 0xFFFFu) * 0x85EBCA77u) >> (32 - HB6);
+        const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
         const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
         if (limit >= 3) {
             const int runcap = min(64 - lane, limit);
@@ -197,16 +257,60 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 if (l >= 3 && eff > be) { be = eff; bl = l; bd = bpp; bcap = c; }
             }
             if (!bcap) {                                                          // a capped run outranks every hash candidate
+                // four candidates in lock-step: 16 bytes per round trip, all loads of a round issued together
                 const int hcap = min(kLaneCap, limit);
-                const bool ok6 = q + 6 <= F;
+                const bool ok6 = q + kH2Bytes <= F;
+                int cpos[4], clen[4]; bool live[4];
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
                     const uint32_t cnd = (w == 0) ? (b3 >> 16) : (w == 1) ? (b3 & 0xFFFFu) : (w == 2) ? (b6 >> 16) : (b6 & 0xFFFFu);
-                    if (cnd == 0 || (w >= 2 && !ok6)) continue;
                     const int cp = base + (int)cnd;
                     const int d = q - cp;
-                    if (d <= 0 || d > kMaxDist) continue;
-                    const int l = lane_match(S32, q, cp, cur4, hcap);
+                    live[w] = cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist;
+                    cpos[w] = live[w] ? cp : q;
+                    clen[w] = 0;
+                }
+                uint32_t x0[4], x1[4], x2[4], x3[4];
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const uint32_t* g = S32 + (cpos[w] >> 2);
+                    const int shc = (cpos[w] & 3) * 8;
+                    const uint32_t g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4);
+                    x0[w] = cur4 ^ __funnelshift_r(g0, g1, shc); x1[w] = nxt4 ^ __funnelshift_r(g1, g2, shc);
+                    x2[w] = q8 ^ __funnelshift_r(g2, g3, shc);   x3[w] = q12 ^ __funnelshift_r(g3, g4, shc);
+                }
+                bool any = false;
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int n = eq16(x0[w], x1[w], x2[w], x3[w]);
+                    clen[w] = live[w] ? min(n, hcap) : 0;
+                    live[w] = live[w] && n == 16 && hcap > 16;
+                    any |= live[w];
+                }
+                for (int n0 = 16; any; n0 += 16) {                                // rounds 2..4: only candidates still matching
+                    any = false;
+                    const uint32_t* gq = S32 + ((q + n0) >> 2);
+                    const int shq = ((q + n0) & 3) * 8;
+                    const uint32_t s0 = __ldg(gq), s1 = __ldg(gq + 1), s2 = __ldg(gq + 2), s3 = __ldg(gq + 3), s4 = __ldg(gq + 4);
+                    const uint32_t y0 = __funnelshift_r(s0, s1, shq), y1 = __funnelshift_r(s1, s2, shq);
+                    const uint32_t y2 = __funnelshift_r(s2, s3, shq), y3 = __funnelshift_r(s3, s4, shq);
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        if (live[w]) {
+                            const uint32_t* g = S32 + ((cpos[w] + n0) >> 2);
+                            const int shc = ((cpos[w] + n0) & 3) * 8;
+                            const uint32_t g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4);
+                            const int n = eq16(y0 ^ __funnelshift_r(g0, g1, shc), y1 ^ __funnelshift_r(g1, g2, shc),
+                                               y2 ^ __funnelshift_r(g2, g3, shc), y3 ^ __funnelshift_r(g3, g4, shc));
+                            clen[w] = min(n0 + n, hcap);
+                            live[w] = n == 16 && n0 + 16 < hcap;
+                            any |= live[w];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const int l = clen[w], d = q - cpos[w];
                     const bool c = (l == hcap) && (hcap < limit);
                     const int eff = c ? 1000 : l;
                     if (l >= 3 && (eff > be || (eff == be && d < bd))) { be = eff; bl = l; bd = d; bcap = c; }
@@ -231,7 +335,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         }
         // ---- one-step lazy rule between neighbouring lanes
         {
-            const int nxt = __shfl_down_sync(0xffffffffu, bl, 1);
+            const int nxt = __shfl_down_sync(kFull, bl, 1);
             if (lane < 31 && bl >= 3 && bl < kLazyMax && nxt > bl) { bl = 0; bd = 0; bcap = false; }
         }
         // ---- greedy parse from lane 0 by pointer jumping
@@ -241,16 +345,16 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         uint32_t Msel = 1u << lane;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
-            const uint32_t Mj = __shfl_sync(0xffffffffu, Msel, J & 31);
-            const int Jj = __shfl_sync(0xffffffffu, J, J & 31);
+            const uint32_t Mj = __shfl_sync(kFull, Msel, J & 31);
+            const int Jj = __shfl_sync(kFull, J, J & 31);
             if (J < 32) { Msel |= Mj; J = Jj; }
         }
-        const uint32_t sel = __shfl_sync(0xffffffffu, Msel, 0);
+        const uint32_t sel = __shfl_sync(kFull, Msel, 0);
         const int last = 31 - __clz(sel);
         // ---- the last token may be capped: extend it cooperatively
-        int Ll = __shfl_sync(0xffffffffu, bl, last);
-        const int dl = __shfl_sync(0xffffffffu, bd, last);
-        const bool capl = __shfl_sync(0xffffffffu, (int)bcap, last) != 0;
+        int Ll = __shfl_sync(kFull, bl, last);
+        const int dl = __shfl_sync(kFull, bd, last);
+        const bool capl = __shfl_sync(kFull, (int)bcap, last) != 0;
         const int ql = p + last;
         if (capl) {
             const int lim = min(kMaxMatch, e - ql);
@@ -272,26 +376,23 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         }
         ntok += __popc(sel);
         int next = ql + (Ll ? Ll : 1);
-        // ---- continuation of maximal distance-1 runs
-        if (Ll == kMaxMatch && dl <= 1) {
-            uint32_t extra = 0;
-            while (next < e) {
-                const int lim = min(kMaxMatch, e - next);
-                if (lim < kMaxMatch) break;
-                if (coop_match(S32, next, dl, kMaxMatch, lane) < kMaxMatch) break;
-                if (lane == 0) tok[ntok + extra] = 0x80000000u | ((uint32_t)(dl - 1) << 8) | (uint32_t)(kMaxMatch - 3);
-                extra++; next += kMaxMatch;
-            }
+        // ---- a maximal distance-1 run goes on: measure it 1 KiB per round trip, emit the full 258-tokens it holds
+        if (Ll == kMaxMatch && dl == 1 && e - next >= kMaxMatch) {
+            const uint32_t v = __ldg(S + next - 1);
+            const int rend = run_end(S, next, e, v, lane);
+            const uint32_t extra = (uint32_t)((rend - next) / kMaxMatch);
+            for (uint32_t i = lane; i < extra; i += 32) tok[ntok + i] = 0x80000000u | (uint32_t)(kMaxMatch - 3);
             if (extra) {
-                if (lane == 0) { atomicAdd(&M.hist[257 + 28], extra); atomicAdd(&M.hist[286 + dist_sym(dl)], extra); }
+                if (lane == 0) { atomicAdd(&M.hist[257 + 28], extra); atomicAdd(&M.hist[286], extra); }
                 ntok += extra;
+                next += (int)extra * kMaxMatch;
             }
         }
         // ---- insert this window's positions (atomicMax: the highest position of a bucket group wins)
         {
             const uint32_t pos = (uint32_t)(q - base);
             if (q < e && q + 2 < F) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
-            if (q < e && q + 6 <= F) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
+            if (q < e && q + kH2Bytes <= F) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
         }
         __syncwarp();
         p = next;
