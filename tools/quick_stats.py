@@ -11,7 +11,8 @@ from vision_compression_project_b200 import _native as N, synth
 from vision_compression_project_b200.api import PagePrep
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-uniq = [np.asarray(synth.make_page(i, "letter", 200, photo=(i % 4 == 3))) for i in range(min(n, 8))]
+photo_every = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+uniq = [np.asarray(synth.make_page(i, "letter", 200, photo=bool(photo_every) and (i % photo_every == photo_every - 1))) for i in range(min(n, 8))]
 dev = [torch.from_numpy(uniq[i % len(uniq)].copy()).cuda() for i in range(n)]
 e = PagePrep(0)
 descs = (N.PageDesc * n)()

@@ -72,11 +72,10 @@ __device__ __forceinline__ int dist_sym(int dist) {    // 1..32768 -> 0..29
 
 // number of equal leading bytes of two 16-byte strings given as four words each (16 = all equal)
 __device__ __forceinline__ int eq16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
-    if (x0) return (__ffs(x0) - 1) >> 3;
-    if (x1) return 4 + ((__ffs(x1) - 1) >> 3);
-    if (x2) return 8 + ((__ffs(x2) - 1) >> 3);
-    if (x3) return 12 + ((__ffs(x3) - 1) >> 3);
-    return 16;
+    const unsigned long long lo = ((unsigned long long)x1 << 32) | x0, hi = ((unsigned long long)x3 << 32) | x2;
+    const int nlo = lo ? (__ffsll((long long)lo) - 1) >> 3 : 8;
+    const int nhi = hi ? (__ffsll((long long)hi) - 1) >> 3 : 8;
+    return lo ? nlo : 8 + nhi;
 }
 
 // warp-cooperative: length of the common prefix of S[y..] and S[y-d..], up to maxn (128 bytes per step)
@@ -169,6 +168,20 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         uint32_t cw = h0 < s ? __ldg(S32 + (h0 >> 2) + lane) : 0u;
         for (int w0 = h0; w0 < s; w0 += 128) {
             const uint32_t cn = __ldg(S32 + ((w0 + 128) >> 2) + lane);           // <= 128 bytes past s: still inside the stream or its pad
+            // a chunk that is one repeated byte (white paper after filtering: most of a text page) hashes every position
+            // to the same two buckets: the four windows' inserts collapse to one store per table
+            const uint32_t c00 = __shfl_sync(kFull, cw, 0), cn0 = __shfl_sync(kFull, cn, 0);
+            if (__all_sync(kFull, cw == c00) && c00 == __funnelshift_l(c00, c00, 8) && cn0 == c00 && w0 + 132 <= F) {
+                if (lane == 0) {
+                    const uint32_t h3 = ((c00 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
+                    const uint32_t h6 = (c00 * 0x9E3779B1u) >> (32 - HB6);
+                    const uint32_t v = ((uint32_t)(w0 + 127 - base) << 16) | (uint32_t)(w0 + 95 - base);
+                    M.t3[h3] = v; M.t6[h6] = v;
+                }
+                __syncwarp();
+                cw = cn;
+                continue;
+            }
             const int sh = (lane & 3) * 8;
 #pragma unroll
             for (int t = 0; t < 4; t++) {
@@ -388,11 +401,20 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 next += (int)extra * kMaxMatch;
             }
         }
-        // ---- insert this window's positions (atomicMax: the highest position of a bucket group wins)
+        // ---- insert this window's positions (atomicMax: the highest position of a bucket group wins).
+        //      If bytes p .. p+34 are one repeated byte every lane has the same two buckets: only the highest valid lane writes.
         {
             const uint32_t pos = (uint32_t)(q - base);
-            if (q < e && q + 2 < F) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
-            if (q < e && q + kH2Bytes <= F) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
+            const bool i3 = q < e && q + 2 < F, i6 = q < e && q + kH2Bytes <= F;
+            const bool uniform = ((m1 >> 1) & 0x3FFFFFFFFull) == 0x3FFFFFFFFull;
+            if (uniform) {
+                const uint32_t m3 = __ballot_sync(kFull, i3), m6 = __ballot_sync(kFull, i6);
+                if (i3 && (m3 >> lane) == 1u) M.t3[h3] = (pos << 16) | (b3 >> 16);
+                if (i6 && (m6 >> lane) == 1u) M.t6[h6] = (pos << 16) | (b6 >> 16);
+            } else {
+                if (i3) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
+                if (i6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
+            }
         }
         __syncwarp();
         p = next;
