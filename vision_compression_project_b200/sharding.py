@@ -1,0 +1,60 @@
+"""Page-range sharding across the GPUs of one box (SURVEY.md §8 e): pages are independent, so every rank owns a
+contiguous range and there is no exchange step (no collective on the data path).
+
+The reference's analogue is the 5-thread page pool of `extract_pdf_to_page_jsons`
+(backend/app/pipeline/pdf_extract.py:313-350): results are collected in page order, failed pages are reported, not fatal.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+def page_range(n_pages: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) of rank `rank`; ranges tile [0, n_pages) and differ in size by at most one page."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_pages, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def balanced_ranges(weights: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Contiguous ranges with near-equal total weight (weight = W*H*C of a page) for mixed-size batches (config C5).
+    Greedy prefix cut at k/world of the total; every rank gets a (possibly empty) range, order is preserved."""
+    if world <= 0:
+        raise ValueError("bad world")
+    total = sum(weights)
+    out, lo, acc = [], 0, 0
+    n = len(weights)
+    for r in range(world):
+        target = total * (r + 1) / world
+        hi = lo
+        while hi < n and (acc + weights[hi] / 2 <= target or r == world - 1):
+            acc += weights[hi]
+            hi += 1
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def prepare_pages_sharded(images: Sequence, rank: int, world: int, device: int | None = None, **kw):
+    """This rank's share of `images` through the GPU path. Returns (lo, results) so the caller can place them in page order."""
+    from .api import prepare_pages
+    lo, hi = page_range(len(images), rank, world)
+    return lo, prepare_pages(images[lo:hi], device=rank if device is None else device, **kw)
+
+
+def gather_in_page_order(local: Sequence, lo: int, n_pages: int, group=None) -> list | None:
+    """Host-side concatenation of per-rank results in page order on rank 0 (variable-length byte strings; this is
+    control-plane traffic over the default process group, not a data-path collective)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((lo, list(local)), gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = [None] * n_pages
+    for l, items in gathered:
+        out[l:l + len(items)] = items
+    return out
