@@ -223,6 +223,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_v = world * n * Ke / float(te.item())
+    e2e_detail = dict(getattr(eng, "last_timing", {}))
+    e2e_detail.update({k_: v_ for k_, v_ in eng.stats().items() if k_.startswith("ms_")})
 
     if rank == 0:
         # correctness of what was timed (not timed): first page decodes to the input and base64 matches
@@ -252,7 +254,8 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "pages_per_gpu": n, "l2": "inputs (718 MB/step) larger than L2, no flush needed",
                        "png_bytes_per_page": png_bytes / n, "png_size_vs_pillow": ratio},
             "e2e": {"value": e2e_v, "unit": "pages/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": png_bytes + b64_bytes,
-                    "api": "prepare_pages(list of pinned uint8 arrays) -> PreparedPage(png bytes, b64 bytes)"},
+                    "api": "prepare_pages(list of pinned uint8 arrays) -> PreparedPage(png bytes, b64 bytes)",
+                    "last_step_ms": {k_: round(v_, 3) for k_, v_ in e2e_detail.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": {"ms_lz": "k_lz", "ms_filter": "k_png_filter", "ms_huff": "k_huff_build/k_layout/k_payload_init/k_huff_emit",

@@ -104,6 +104,10 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
 
 int vcp_get_stats(vcp_handle* h, vcp_stats* out);
 
+/* Host-side helper for language bindings: copy n byte ranges src_base+offs[i] .. +lens[i] into dsts[i] on `threads`
+ * host threads (the Python binding fills freshly allocated bytes objects with it while the GIL is released). */
+int vcp_host_scatter(const void* src_base, const uint64_t* offs, const uint64_t* lens, void* const* dsts, int n, int threads);
+
 /* ---- stage-level entry points (device pointers; used by the parity tests, one image at a time) ---- */
 
 /* Image.convert: Convert.c  (L/LA/RGB/RGBA -> RGB, RGB/RGBA/LA -> L). */

@@ -121,3 +121,13 @@ def test_input_normalisation_and_planning():
     assert (d.dst_width, d.dst_height) == (0, 0)
     with pytest.raises(ValueError):
         PagePrep._plan(src, (0, 5), None, "RGB", 1, None)
+
+
+def test_host_scatter_fills_fresh_bytes(lib):
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, 6_000_000, dtype=np.uint8)
+    ranges = [(0, 0), (5, 1), (100, 1_500_000), (2_000_000, 2_999_999), (7, 3), (5_999_999, 1)]
+    for threads in (1, 4, 64):
+        out = N.gather_bytes(src.ctypes.data, ranges, threads)
+        assert all(type(o) is bytes and o == src[a:a + n].tobytes() for o, (a, n) in zip(out, ranges))
+    assert N.gather_bytes(src.ctypes.data, [], 4) == []

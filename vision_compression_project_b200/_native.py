@@ -49,6 +49,7 @@ SYMBOLS = {
     "vcp_prepare_batch": (C.c_int, [C.c_void_p, C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.c_void_p, C.c_uint64,
                                     C.c_void_p, C.c_uint64, C.POINTER(PageResult)]),
     "vcp_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "vcp_host_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "vcp_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int]),
     "vcp_resample_coeffs": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "vcp_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
@@ -62,6 +63,25 @@ SYMBOLS = {
 }
 
 _lib = None
+
+# CPython C API: a bytes object created with PyBytes_FromStringAndSize(NULL, n) may be filled in place before it is shared
+_new_bytes = C.pythonapi.PyBytes_FromStringAndSize
+_new_bytes.restype = C.py_object
+_new_bytes.argtypes = [C.c_void_p, C.c_ssize_t]
+_bytes_ptr = C.pythonapi.PyBytes_AsString
+_bytes_ptr.restype = C.c_void_p
+_bytes_ptr.argtypes = [C.py_object]
+
+
+def gather_bytes(src_ptr: int, ranges, threads: int = 4):
+    """[(off, len), ...] inside the host buffer at src_ptr -> list of fresh bytes objects (filled by vcp_host_scatter)."""
+    n = len(ranges)
+    objs = [_new_bytes(None, ln) for _, ln in ranges]
+    offs = (C.c_uint64 * n)(*[o for o, _ in ranges])
+    lens = (C.c_uint64 * n)(*[ln for _, ln in ranges])
+    dsts = (C.c_void_p * n)(*[_bytes_ptr(o) for o in objs])
+    check(load().vcp_host_scatter(src_ptr, offs, lens, dsts, n, threads))
+    return objs
 
 
 def load() -> C.CDLL:

@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -47,35 +48,43 @@ enum { EV_START, EV_H2D, EV_PIXEL, EV_FILTER, EV_LZ, EV_HUFF, EV_ASSEMBLE, EV_B6
 
 }  // namespace
 
-struct vcp_handle {
-    int device = 0;
+// A lane = one CUDA stream with its own device arena and pinned staging block.  A handle has four, so that with host
+// inputs the H2D copies run back to back (up to three groups ahead) while earlier groups compute (vcp_prepare_batch).
+struct Lane {
     cudaStream_t stream = nullptr;
-    std::mutex mu;
     uint8_t* arena = nullptr; size_t arena_cap = 0;
     uint8_t* meta = nullptr; size_t meta_cap = 0;          // pinned host staging: descriptors up, results down
-    std::map<CoeffKey, Coeffs> coeff_cache;
     cudaEvent_t ev[EV_COUNT] = {};
+};
+constexpr int kLanes = 4;
+
+struct vcp_handle {
+    int device = 0;
+    std::mutex mu;
+    Lane lane[kLanes];
+    std::map<CoeffKey, Coeffs> coeff_cache;
     vcp_stats stats = {};
     size_t group_bytes = (size_t)2 << 30;                  // max filtered bytes per launch set
+    size_t pipe_bytes = (size_t)96 << 20;                  // host inputs: source bytes per pipelined group
 };
 
 namespace {
 
-int ensure_arena(vcp_handle* h, size_t need) {
-    if (need <= h->arena_cap) return 0;
-    if (h->arena) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->arena)); h->arena = nullptr; h->arena_cap = 0; }
+int ensure_arena(Lane& L, size_t need) {
+    if (need <= L.arena_cap) return 0;
+    if (L.arena) { CU(cudaStreamSynchronize(L.stream)); CU(cudaFree(L.arena)); L.arena = nullptr; L.arena_cap = 0; }
     const size_t cap = align_up(need + need / 8, (size_t)1 << 20);
-    CU(cudaMalloc(&h->arena, cap));
-    h->arena_cap = cap;
+    CU(cudaMalloc(&L.arena, cap));
+    L.arena_cap = cap;
     return 0;
 }
 
-int ensure_meta(vcp_handle* h, size_t need) {
-    if (need <= h->meta_cap) return 0;
-    if (h->meta) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFreeHost(h->meta)); h->meta = nullptr; h->meta_cap = 0; }
+int ensure_meta(Lane& L, size_t need) {
+    if (need <= L.meta_cap) return 0;
+    if (L.meta) { CU(cudaStreamSynchronize(L.stream)); CU(cudaFreeHost(L.meta)); L.meta = nullptr; L.meta_cap = 0; }
     const size_t cap = align_up(need * 2, (size_t)1 << 16);
-    CU(cudaMallocHost(&h->meta, cap));
-    h->meta_cap = cap;
+    CU(cudaMallocHost(&L.meta, cap));
+    L.meta_cap = cap;
     return 0;
 }
 
@@ -171,15 +180,19 @@ struct GroupOut {       // where the launch set of a group left its results (pin
     uint8_t* d_png; uint8_t* d_b64; uint8_t* d_filt0; uint32_t* d_tokens; uint32_t* d_sub_ntok; uint32_t* d_sub_hist;
     int nsub; int nblocks;
     std::vector<size_t> filt_off;     // per page: offset of its filtered stream from d_filt0's arena base
+    // issue -> finish state
+    Lane* lane = nullptr; int n = 0; size_t res_bytes = 0; uint8_t* host_res = nullptr;
+    uint64_t launches = 0, in_bytes = 0, filt_bytes = 0;
 };
 
 // Runs the whole launch set for pages[0..n) (all with status 0).  framed=0 + stream input: the pages' filtered
 // streams are given directly (stage-level vcp_deflate / vcp_lz_tokens): plans[i].src is the stream, filt_len set.
 enum RunMode { RUN_FULL = 0, RUN_STREAM = 1, RUN_FILTER_ONLY = 2, RUN_LZ_ONLY = 3 };
 
-int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, RunMode mode, GroupOut& out) {
+// Enqueues the whole launch set of a group on lane L (nothing here waits for the GPU).
+int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_opts& o, RunMode mode, GroupOut& out) {
     const int n = (int)plans.size();
-    cudaStream_t st = h->stream;
+    cudaStream_t st = L.stream;
     const bool stream_in = (mode == RUN_STREAM || mode == RUN_LZ_ONLY);
     // ---------------- carve the arena
     Bump bump;
@@ -234,6 +247,7 @@ int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, Ru
     // results block (copied down in one piece): png_off[n] png_len[n] b64_off[n] b64_len[n] totals[2] adler[n] err[2]
     const size_t res_bytes = (size_t)n * 8 * 4 + 16 + align_up((size_t)n * 4, 8) + 8;
     const size_t o_res = bump.take(res_bytes);
+    const size_t o_cnt = bump.take(256);
     const size_t o_png = need_huff ? bump.take((size_t)png_cap + 64) : kNone;
     const size_t o_b64 = (need_huff && o.want_b64) ? bump.take((size_t)b64_cap + 64) : kNone;
     const size_t o_coeff = bump.take(coeff_blob.size() * 4 + 4);
@@ -241,15 +255,15 @@ int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, Ru
     const size_t o_blocks = bump.take((size_t)nblocks * sizeof(BlockD) + 8);
     const size_t o_sub2blk = bump.take((size_t)nsub * 4 + 4);
     const size_t desc_bytes = bump.off - o_coeff;
-    int rc = ensure_arena(h, bump.off + 256);
+    int rc = ensure_arena(L, bump.off + 256);
     if (rc) return rc;
-    rc = ensure_meta(h, desc_bytes + res_bytes + 256);
+    rc = ensure_meta(L, desc_bytes + res_bytes + 256);
     if (rc) return rc;
-    uint8_t* A = h->arena;
-    h->stats.arena_bytes = h->arena_cap;
+    uint8_t* A = L.arena;
+    h->stats.arena_bytes = 0; for (const Lane& l : h->lane) h->stats.arena_bytes += l.arena_cap;
 
     // ---------------- descriptors (built in pinned memory, mirrored layout of [o_coeff, end))
-    uint8_t* M = h->meta;
+    uint8_t* M = L.meta;
     memset(M, 0, desc_bytes);
     if (!coeff_blob.empty()) memcpy(M, coeff_blob.data(), coeff_blob.size() * 4);
     PageD* hp = reinterpret_cast<PageD*>(M + (o_pages - o_coeff));
@@ -331,6 +345,7 @@ int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, Ru
     B.totals = B.b64_len + n;
     B.page_adler = reinterpret_cast<uint32_t*>(B.totals + 2);
     B.err = reinterpret_cast<uint32_t*>(R + res_bytes - 8);
+    B.counters = reinterpret_cast<uint32_t*>(A + o_cnt);
     (void)o_page_adler;
     B.png = need_huff ? A + o_png : nullptr; B.png_cap = png_cap;
     B.b64 = (need_huff && o.want_b64) ? A + o_b64 : nullptr; B.b64_cap = b64_cap;
@@ -338,26 +353,28 @@ int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, Ru
 
     // ---------------- launch set
     uint64_t launches = 0;
-    CU(cudaEventRecord(h->ev[EV_START], st));
+    CU(cudaEventRecord(L.ev[EV_START], st));
     CU(cudaMemcpyAsync(A + o_coeff, M, desc_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(R, 0, res_bytes, st));
+    CU(cudaMemsetAsync(R, 0, (o_cnt + 256) - o_res, st));
     if (!stream_in && !o.src_device) {
-        for (auto& P : plans)
-            CU(cudaMemcpy2DAsync(A + P.o_raw, (size_t)P.sw * P.sc, P.src, (size_t)P.src_stride, (size_t)P.sw * P.sc, (size_t)P.sh,
-                                 cudaMemcpyHostToDevice, st));
+        for (auto& P : plans) {
+            const size_t rowb = (size_t)P.sw * P.sc;
+            if ((size_t)P.src_stride == rowb) CU(cudaMemcpyAsync(A + P.o_raw, P.src, rowb * P.sh, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemcpy2DAsync(A + P.o_raw, rowb, P.src, (size_t)P.src_stride, rowb, (size_t)P.sh, cudaMemcpyHostToDevice, st));
+        }
     }
     if (stream_in) {
         for (auto& P : plans)
             CU(cudaMemcpyAsync(A + P.o_filt, P.src, (size_t)P.filt_len, cudaMemcpyDeviceToDevice, st));
     }
-    CU(cudaEventRecord(h->ev[EV_H2D], st));
+    CU(cudaEventRecord(L.ev[EV_H2D], st));
     if (!stream_in) {
         if (any_conv) launches += launch_convert(B.pages, n, max_sh, max_sw, st);
         if (any_red) launches += launch_reduce(B.pages, n, max_rh, max_rw, st);
         if (any_h) launches += launch_resample_h(B.pages, n, max_resh_rows, max_w, st);
         if (any_v) launches += launch_resample_v(B.pages, n, max_h, max_wc, st);
     }
-    CU(cudaEventRecord(h->ev[EV_PIXEL], st));
+    CU(cudaEventRecord(L.ev[EV_PIXEL], st));
     if (!stream_in) {
         launches += launch_png_filter(B.pages, n, max_h, max_wc, o.optimize, B.row_adler, st);
         launches += launch_adler_combine(B.pages, n, B.row_adler, B.page_adler, st);
@@ -366,40 +383,55 @@ int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, Ru
             launches += launch_adler_flat(A + plans[i].o_filt, (uint64_t)plans[i].filt_len,
                                           reinterpret_cast<uint32_t*>(A + o_tokens), B.page_adler + i, st);
     }
-    CU(cudaEventRecord(h->ev[EV_FILTER], st));
+    CU(cudaEventRecord(L.ev[EV_FILTER], st));
     if (need_lz) launches += launch_lz(B, st);
-    CU(cudaEventRecord(h->ev[EV_LZ], st));
+    CU(cudaEventRecord(L.ev[EV_LZ], st));
     if (need_huff) {
         launches += launch_huff_build(B, st);
         launches += launch_layout(B, st);
         launches += launch_payload_init(B, st);
         launches += launch_huff_emit(B, st);
     }
-    CU(cudaEventRecord(h->ev[EV_HUFF], st));
+    CU(cudaEventRecord(L.ev[EV_HUFF], st));
     if (need_huff) launches += launch_png_finish(B, st);
-    CU(cudaEventRecord(h->ev[EV_ASSEMBLE], st));
+    CU(cudaEventRecord(L.ev[EV_ASSEMBLE], st));
     if (need_huff) launches += launch_base64_pages(B, st);
-    CU(cudaEventRecord(h->ev[EV_B64], st));
+    CU(cudaEventRecord(L.ev[EV_B64], st));
     CU(cudaGetLastError());
     // results block -> pinned host (after the descriptor mirror)
     uint8_t* HR = M + align_up(desc_bytes, 64);
     CU(cudaMemcpyAsync(HR, R, res_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    out.lane = &L; out.n = n; out.res_bytes = res_bytes; out.host_res = HR;
+    out.launches = launches; out.in_bytes = in_bytes; out.filt_bytes = filt_bytes;
+    out.d_png = B.png; out.d_b64 = B.b64; out.d_filt0 = A; out.d_tokens = B.tokens; out.d_sub_ntok = B.sub_ntok; out.d_sub_hist = B.sub_hist;
+    out.nsub = nsub; out.nblocks = nblocks;
+    return 0;
+}
+
+// Waits for a group's launch set and exposes its results block.
+int finish_group(vcp_handle* h, GroupOut& out) {
+    Lane& L = *out.lane;
+    const int n = out.n;
+    CU(cudaStreamSynchronize(L.stream));
+    uint8_t* HR = out.host_res;
     out.png_off = reinterpret_cast<const uint64_t*>(HR); out.png_len = out.png_off + n; out.b64_off = out.png_len + n; out.b64_len = out.b64_off + n;
     out.totals = out.b64_len + n;
     out.adler = reinterpret_cast<const uint32_t*>(out.totals + 2);
-    const uint32_t err = *reinterpret_cast<const uint32_t*>(HR + res_bytes - 8);
+    const uint32_t err = *reinterpret_cast<const uint32_t*>(HR + out.res_bytes - 8);
     if (err) return fail(VCP_ESIZE, "internal output bound exceeded (flags %u)", err);
-    out.d_png = B.png; out.d_b64 = B.b64; out.d_filt0 = A; out.d_tokens = B.tokens; out.d_sub_ntok = B.sub_ntok; out.d_sub_hist = B.sub_hist;
-    out.nsub = nsub; out.nblocks = nblocks;
-    h->stats.kernel_launches += launches;
-    h->stats.in_bytes += in_bytes; h->stats.filtered_bytes += filt_bytes;
+    h->stats.kernel_launches += out.launches;
+    h->stats.in_bytes += out.in_bytes; h->stats.filtered_bytes += out.filt_bytes;
     float ms = 0;
-    auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms; };
+    auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, L.ev[a], L.ev[b]); return ms; };
     h->stats.ms_h2d += el(EV_START, EV_H2D); h->stats.ms_convert += el(EV_H2D, EV_PIXEL); h->stats.ms_filter += el(EV_PIXEL, EV_FILTER);
     h->stats.ms_lz += el(EV_FILTER, EV_LZ); h->stats.ms_huff += el(EV_LZ, EV_HUFF); h->stats.ms_assemble += el(EV_HUFF, EV_ASSEMBLE);
     h->stats.ms_b64 += el(EV_ASSEMBLE, EV_B64);
     return 0;
+}
+
+int run_group(vcp_handle* h, std::vector<PagePlan>& plans, const vcp_opts& o, RunMode mode, GroupOut& out) {
+    const int rc = issue_group(h, h->lane[0], plans, o, mode, out);
+    return rc ? rc : finish_group(h, out);
 }
 
 void reset_stats(vcp_handle* h) { const uint64_t a = h->stats.arena_bytes; memset(&h->stats, 0, sizeof h->stats); h->stats.arena_bytes = a; }
@@ -424,9 +456,12 @@ int vcp_init(int device, vcp_handle** out) {
     if (prop.major < 10) return fail(VCP_ECUDA, "libvcprep is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
     vcp_handle* h = new vcp_handle();
     h->device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete h; return fail(VCP_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&h->ev[i]);
+    for (Lane& L : h->lane) {
+        cudaError_t e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete h; return fail(VCP_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&L.ev[i]);
+    }
+    if (const char* g = getenv("VCP_PIPE_BYTES")) { const long long v = atoll(g); if (v >= (1 << 20)) h->pipe_bytes = (size_t)v; }
     if (const char* g = getenv("VCP_GROUP_BYTES")) { const long long v = atoll(g); if (v >= (1 << 20)) h->group_bytes = (size_t)v; }
     *out = h;
     return 0;
@@ -435,11 +470,13 @@ int vcp_init(int device, vcp_handle** out) {
 void vcp_destroy(vcp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->arena) cudaFree(h->arena);
-    if (h->meta) cudaFreeHost(h->meta);
-    for (int i = 0; i < EV_COUNT; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (Lane& L : h->lane) {
+        if (L.stream) cudaStreamSynchronize(L.stream);
+        if (L.arena) cudaFree(L.arena);
+        if (L.meta) cudaFreeHost(L.meta);
+        for (int i = 0; i < EV_COUNT; i++) if (L.ev[i]) cudaEventDestroy(L.ev[i]);
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
     delete h;
 }
 
@@ -471,6 +508,7 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
     if (opts->out_channels != 0 && opts->out_channels != 1 && opts->out_channels != 3) return fail(VCP_EINVAL, "out_channels must be 0, 1 or 3");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     reset_stats(h);
     // per-page validation: a bad page gets its own status and is left out of the launch set
     std::vector<PagePlan> all(n);
@@ -480,46 +518,73 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
         all[i].status = rc;
         results[i].status = rc;
     }
+    // ---- split into launch sets.  Device-resident sources: as large as group_bytes allows (fewer, fuller launches).
+    //      Host sources: groups of ~pipe_bytes so that the H2D copy of group g+1 (other lane, other stream) overlaps the
+    //      kernels of group g; results are collected in order.
+    const size_t limit = opts->src_device ? h->group_bytes : std::min(h->group_bytes, h->pipe_bytes);
+    std::vector<std::vector<int>> groups;
+    {
+        size_t bytes = 0;
+        for (int i = 0; i < n; i++) {
+            if (all[i].status) continue;
+            const size_t fb = opts->src_device ? (size_t)all[i].filt_len + (size_t)all[i].sw * all[i].sh * all[i].sc / 4
+                                               : (size_t)all[i].sw * all[i].sh * all[i].sc;
+            if (groups.empty() || (bytes + fb > limit && !groups.back().empty())) { groups.emplace_back(); bytes = 0; }
+            groups.back().push_back(i); bytes += fb;
+        }
+    }
+    const int G = (int)groups.size();
+    std::vector<GroupOut> ctx(G);
+    std::vector<std::vector<PagePlan>> gplans(G);
     uint64_t png_used = 0, b64_used = 0;
     const cudaMemcpyKind kind = opts->dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    int i0 = 0;
-    while (i0 < n) {
-        // next group: consecutive good pages up to group_bytes of filtered stream
-        std::vector<PagePlan> g; std::vector<int> idx;
-        size_t bytes = 0;
-        int i = i0;
-        for (; i < n; i++) {
-            if (all[i].status) continue;
-            const size_t fb = (size_t)all[i].filt_len + (size_t)all[i].sw * all[i].sh * all[i].sc / 4;
-            if (!g.empty() && bytes + fb > h->group_bytes) break;
-            g.push_back(all[i]); idx.push_back(i); bytes += fb;
-        }
-        i0 = i;
-        if (g.empty()) break;
-        GroupOut go;
-        int rc = run_group(h, g, *opts, RUN_FULL, go);
+    auto issue = [&](int g) -> int {
+        for (int i : groups[g]) gplans[g].push_back(all[i]);
+        return issue_group(h, h->lane[g % kLanes], gplans[g], *opts, RUN_FULL, ctx[g]);
+    };
+    auto collect = [&](int g) -> int {          // wait for group g, place its bytes in the caller's buffers (async on its lane)
+        GroupOut& go = ctx[g];
+        int rc = finish_group(h, go);
         if (rc) return rc;
+        Lane& L = *go.lane;
         const uint64_t gp = go.totals[0], gb = go.totals[1];
         if (png_used + gp > png_cap) return fail(VCP_ESIZE, "out_png too small: need %llu more bytes at offset %llu (cap %llu); size it with vcp_output_bound",
                                                  (unsigned long long)gp, (unsigned long long)png_used, (unsigned long long)png_cap);
         if (opts->want_b64 && b64_used + gb > b64_cap) return fail(VCP_ESIZE, "out_b64 too small (cap %llu)", (unsigned long long)b64_cap);
-        cudaEvent_t e0 = h->ev[EV_B64], e1 = h->ev[EV_D2H];
-        CU(cudaEventRecord(e0, h->stream));
-        if (gp) CU(cudaMemcpyAsync((uint8_t*)out_png + png_used, go.d_png, gp, kind, h->stream));
-        if (opts->want_b64 && gb) CU(cudaMemcpyAsync((uint8_t*)out_b64 + b64_used, go.d_b64, gb, kind, h->stream));
-        CU(cudaEventRecord(e1, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); h->stats.ms_d2h += ms;
-        for (size_t k = 0; k < idx.size(); k++) {
-            vcp_page_result& r = results[idx[k]];
-            r.width = g[k].w; r.height = g[k].h; r.channels = g[k].c;
+        CU(cudaEventRecord(L.ev[EV_B64], L.stream));
+        if (gp) CU(cudaMemcpyAsync((uint8_t*)out_png + png_used, go.d_png, gp, kind, L.stream));
+        if (opts->want_b64 && gb) CU(cudaMemcpyAsync((uint8_t*)out_b64 + b64_used, go.d_b64, gb, kind, L.stream));
+        CU(cudaEventRecord(L.ev[EV_D2H], L.stream));
+        for (size_t k = 0; k < groups[g].size(); k++) {
+            vcp_page_result& r = results[groups[g][k]];
+            const PagePlan& P = gplans[g][k];
+            r.width = P.w; r.height = P.h; r.channels = P.c;
             r.png_off = png_used + go.png_off[k]; r.png_len = go.png_len[k];
             if (opts->want_b64) { r.b64_off = b64_used + go.b64_off[k]; r.b64_len = go.b64_len[k]; }
-            r.adler32 = go.adler[k]; r.n_idat = (uint32_t)g[k].nblk;
+            r.adler32 = go.adler[k]; r.n_idat = (uint32_t)P.nblk;
             h->stats.png_bytes += r.png_len; h->stats.b64_bytes += r.b64_len;
         }
         png_used += gp; b64_used += gb;
+        return 0;
+    };
+    int rc = 0;
+    for (int g = 0; g < G && !rc; g++) {
+        // lane g % kLanes was last used by group g-kLanes: its payload copy must have left the arena before it is overwritten
+        if (g >= kLanes) {
+            Lane& L = h->lane[g % kLanes];
+            CU(cudaStreamSynchronize(L.stream));
+            float ms = 0; cudaEventElapsedTime(&ms, L.ev[EV_B64], L.ev[EV_D2H]); h->stats.ms_d2h += ms;
+        }
+        rc = issue(g);
+        if (!rc && g >= kLanes - 1) rc = collect(g - (kLanes - 1));
     }
+    for (int g = std::max(0, G - (kLanes - 1)); g < G && !rc; g++) rc = collect(g);
+    for (int l = 0; l < kLanes; l++) {             // drain both lanes even on error
+        Lane& L = h->lane[l];
+        cudaStreamSynchronize(L.stream);
+        if (!rc && l < G) { float ms = 0; if (cudaEventElapsedTime(&ms, L.ev[EV_B64], L.ev[EV_D2H]) == cudaSuccess) h->stats.ms_d2h += ms; }
+    }
+    if (rc) return rc;
     h->stats.ms_total = h->stats.ms_h2d + h->stats.ms_convert + h->stats.ms_filter + h->stats.ms_lz + h->stats.ms_huff +
                         h->stats.ms_assemble + h->stats.ms_b64 + h->stats.ms_d2h;
     return 0;
@@ -532,17 +597,44 @@ int vcp_get_stats(vcp_handle* h, vcp_stats* out) {
     return 0;
 }
 
+int vcp_host_scatter(const void* src_base, const uint64_t* offs, const uint64_t* lens, void* const* dsts, int n, int threads) {
+    if (n < 0 || (n > 0 && (!src_base || !offs || !lens || !dsts))) return fail(VCP_EINVAL, "bad arguments");
+    const uint8_t* base = (const uint8_t*)src_base;
+    uint64_t total = 0;
+    for (int i = 0; i < n; i++) total += lens[i];
+    const int T = std::max(1, std::min(threads, 16));
+    if (T == 1 || total < (1u << 20)) {
+        for (int i = 0; i < n; i++) if (lens[i]) memcpy(dsts[i], base + offs[i], (size_t)lens[i]);
+        return 0;
+    }
+    // split the total byte count evenly: thread t copies the byte interval [t*total/T, (t+1)*total/T) of the concatenation
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; t++) {
+        const uint64_t lo = total * t / T, hi = total * (t + 1) / T;
+        pool.emplace_back([=]() {
+            uint64_t pos = 0;
+            for (int i = 0; i < n && pos < hi; i++) {
+                const uint64_t a = std::max(lo, pos), b = std::min(hi, pos + lens[i]);
+                if (a < b) memcpy((uint8_t*)dsts[i] + (a - pos), base + offs[i] + (a - pos), (size_t)(b - a));
+                pos += lens[i];
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ stage-level entry points
 namespace {
 // upload one PageD built on the host and return its device address (uses the head of the arena's descriptor area)
-int stage_page(vcp_handle* h, const PageD& D, size_t extra_bytes, uint8_t** extra, const PageD** d_page) {
+int stage_page(Lane& L, const PageD& D, size_t extra_bytes, uint8_t** extra, const PageD** d_page) {
     const size_t need = 1024 + align_up(extra_bytes, 256) + 512;
-    int rc = ensure_arena(h, need); if (rc) return rc;
-    rc = ensure_meta(h, 4096); if (rc) return rc;
-    memcpy(h->meta, &D, sizeof D);
-    CU(cudaMemcpyAsync(h->arena, h->meta, sizeof D, cudaMemcpyHostToDevice, h->stream));
-    *d_page = reinterpret_cast<const PageD*>(h->arena);
-    if (extra) *extra = h->arena + 1024;
+    int rc = ensure_arena(L, need); if (rc) return rc;
+    rc = ensure_meta(L, 4096); if (rc) return rc;
+    memcpy(L.meta, &D, sizeof D);
+    CU(cudaMemcpyAsync(L.arena, L.meta, sizeof D, cudaMemcpyHostToDevice, L.stream));
+    *d_page = reinterpret_cast<const PageD*>(L.arena);
+    if (extra) *extra = L.arena + 1024;
     return 0;
 }
 }  // namespace
@@ -553,13 +645,14 @@ int vcp_convert(vcp_handle* h, const void* d_src, int width, int height, int src
     if (src_channels < 1 || src_channels > 4 || (dst_channels != 1 && dst_channels != 3)) return fail(VCP_EINVAL, "unsupported conversion %d -> %d channels", src_channels, dst_channels);
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     PageD D = {};
     D.src = (const uint8_t*)d_src; D.src_stride = row_stride ? row_stride : (int64_t)width * src_channels;
     D.sw = width; D.sh = height; D.sc = src_channels; D.c = dst_channels; D.conv = (uint8_t*)d_dst;
-    const PageD* dp; int rc = stage_page(h, D, 0, nullptr, &dp); if (rc) return rc;
-    launch_convert(dp, 1, height, width, h->stream);
+    const PageD* dp; int rc = stage_page(L, D, 0, nullptr, &dp); if (rc) return rc;
+    launch_convert(dp, 1, height, width, L.stream);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(L.stream));
     return 0;
 }
 
@@ -572,14 +665,15 @@ int vcp_reduce(vcp_handle* h, const void* d_src, int width, int height, int chan
     if (!h || !d_src || !d_dst || width <= 0 || height <= 0 || channels < 1 || channels > 4 || fx < 1 || fy < 1) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     PageD D = {};
     D.sw = width; D.sh = height; D.sc = channels; D.c = channels; D.fx = fx; D.fy = fy;
     D.rw = (width + fx - 1) / fx; D.rh = (height + fy - 1) / fy;
     D.rdin = (const uint8_t*)d_src; D.rdin_stride = (int64_t)width * channels; D.red = (uint8_t*)d_dst;
-    const PageD* dp; int rc = stage_page(h, D, 0, nullptr, &dp); if (rc) return rc;
-    launch_reduce(dp, 1, D.rh, D.rw, h->stream);
+    const PageD* dp; int rc = stage_page(L, D, 0, nullptr, &dp); if (rc) return rc;
+    launch_reduce(dp, 1, D.rh, D.rw, L.stream);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(L.stream));
     return 0;
 }
 
@@ -590,10 +684,11 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
     if (filter < VCP_LANCZOS || filter > VCP_HAMMING) return fail(VCP_EINVAL, "unsupported resample filter %d", filter);
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     const bool need_h = out_width != width, need_v = out_height != height;
     if (!need_h && !need_v) {
-        CU(cudaMemcpyAsync(d_dst, d_src, (size_t)width * height * channels, cudaMemcpyDeviceToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpyAsync(d_dst, d_src, (size_t)width * height * channels, cudaMemcpyDeviceToDevice, L.stream));
+        CU(cudaStreamSynchronize(L.stream));
         return 0;
     }
     const Coeffs* ch = need_h ? get_coeffs(h, width, out_width, filter, 0.f, (float)width) : nullptr;
@@ -605,11 +700,11 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
     if (cv) { ivb = blob.size(); blob.insert(blob.end(), cv->bounds.begin(), cv->bounds.end()); ivk = blob.size(); blob.insert(blob.end(), cv->kt.begin(), cv->kt.end()); }
     const size_t tmp_bytes = (need_h && need_v) ? (size_t)out_width * height * channels : 0;
     const size_t extra = align_up(blob.size() * 4, 256) + tmp_bytes + 256;
-    int rc = ensure_arena(h, 1024 + extra + 512); if (rc) return rc;
-    int32_t* d_blob = reinterpret_cast<int32_t*>(h->arena + 1024);
-    uint8_t* d_tmp = h->arena + 1024 + align_up(blob.size() * 4, 256);
-    CU(cudaMemcpyAsync(d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));      // blob is pageable host memory
+    int rc = ensure_arena(L, 1024 + extra + 512); if (rc) return rc;
+    int32_t* d_blob = reinterpret_cast<int32_t*>(L.arena + 1024);
+    uint8_t* d_tmp = L.arena + 1024 + align_up(blob.size() * 4, 256);
+    CU(cudaMemcpyAsync(d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, L.stream));
+    CU(cudaStreamSynchronize(L.stream));      // blob is pageable host memory
     PageD D = {};
     D.c = channels; D.rw = width; D.rh = height; D.w = out_width; D.h = out_height;
     D.hin = (const uint8_t*)d_src; D.hin_stride = (int64_t)width * channels;
@@ -620,11 +715,11 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
     }
     D.vin = cur; D.vin_stride = cur_stride;
     if (need_v) { D.vout = (uint8_t*)d_dst; D.vb = d_blob + ivb; D.vk = d_blob + ivk; D.vks = cv->ksize; }
-    const PageD* dp; rc = stage_page(h, D, 0, nullptr, &dp); if (rc) return rc;
-    if (need_h) launch_resample_h(dp, 1, height, out_width, h->stream);
-    if (need_v) launch_resample_v(dp, 1, out_height, out_width * channels, h->stream);
+    const PageD* dp; rc = stage_page(L, D, 0, nullptr, &dp); if (rc) return rc;
+    if (need_h) launch_resample_h(dp, 1, height, out_width, L.stream);
+    if (need_v) launch_resample_v(dp, 1, out_height, out_width * channels, L.stream);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(L.stream));
     return 0;
 }
 
@@ -633,14 +728,15 @@ int vcp_png_filter(vcp_handle* h, const void* d_pix, int width, int height, int 
     if (!h || !d_pix || !d_dst || width <= 0 || height <= 0 || channels < 1 || channels > 4) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     vcp_page_desc d = {}; d.src = d_pix; d.width = width; d.height = height; d.channels = channels;
     vcp_opts o = {}; o.out_channels = 0; o.optimize = optimize; o.src_device = 1; o.compress_level = 6;
     std::vector<PagePlan> g(1);
     int rc = plan_geometry(d, o, g[0]); if (rc) return rc;
     GroupOut go;
     rc = run_group(h, g, o, RUN_FILTER_ONLY, go); if (rc) return rc;
-    CU(cudaMemcpyAsync(d_dst, h->arena + go.filt_off[0], (size_t)g[0].filt_len, cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(d_dst, L.arena + go.filt_off[0], (size_t)g[0].filt_len, cudaMemcpyDeviceToDevice, L.stream));
+    CU(cudaStreamSynchronize(L.stream));
     if (adler32_out) *adler32_out = go.adler[0];
     return 0;
 }
@@ -664,14 +760,15 @@ int vcp_deflate(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, int 
     if (!h || !d_out || !out_len) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     std::vector<PagePlan> g(1);
     int rc = stream_plan(d_stream, len, bpp, g[0]); if (rc) return rc;
     vcp_opts o = {}; o.compress_level = level; o.src_device = 1;
     GroupOut go;
     rc = run_group(h, g, o, RUN_STREAM, go); if (rc) return rc;
     if (go.png_len[0] > cap) return fail(VCP_ESIZE, "output buffer too small: need %llu", (unsigned long long)go.png_len[0]);
-    CU(cudaMemcpyAsync(d_out, go.d_png + go.png_off[0], go.png_len[0], cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(d_out, go.d_png + go.png_off[0], go.png_len[0], cudaMemcpyDeviceToDevice, L.stream));
+    CU(cudaStreamSynchronize(L.stream));
     *out_len = go.png_len[0];
     return 0;
 }
@@ -680,16 +777,17 @@ int vcp_lz_tokens(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, ui
     if (!h || !d_tokens || !sub_ntok_host) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     std::vector<PagePlan> g(1);
     int rc = stream_plan(d_stream, len, bpp, g[0]); if (rc) return rc;
     vcp_opts o = {}; o.compress_level = 6; o.src_device = 1;
     GroupOut go;
     rc = run_group(h, g, o, RUN_LZ_ONLY, go); if (rc) return rc;
     // tokens are indexed by byte offset from the filtered region base; the stream sits kStreamPad after it
-    CU(cudaMemcpyAsync(d_tokens, go.d_tokens + kStreamPad, (size_t)len * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CU(cudaMemcpyAsync(sub_ntok_host, go.d_sub_ntok, (size_t)go.nsub * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (sub_hist_host) CU(cudaMemcpyAsync(sub_hist_host, go.d_sub_hist, (size_t)go.nsub * kHistSize * 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(d_tokens, go.d_tokens + kStreamPad, (size_t)len * 4, cudaMemcpyDeviceToDevice, L.stream));
+    CU(cudaMemcpyAsync(sub_ntok_host, go.d_sub_ntok, (size_t)go.nsub * 4, cudaMemcpyDeviceToHost, L.stream));
+    if (sub_hist_host) CU(cudaMemcpyAsync(sub_hist_host, go.d_sub_hist, (size_t)go.nsub * kHistSize * 4, cudaMemcpyDeviceToHost, L.stream));
+    CU(cudaStreamSynchronize(L.stream));
     return 0;
 }
 
@@ -697,15 +795,16 @@ int vcp_adler32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) 
     if (!h || !out || (len && !d_data)) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0]; (void)L;
     const size_t nseg = (size_t)((len + 4095) / 4096);
-    int rc = ensure_arena(h, 1024 + nseg * 8 + 512); if (rc) return rc;
-    rc = ensure_meta(h, 4096); if (rc) return rc;
-    uint32_t* d_out = reinterpret_cast<uint32_t*>(h->arena);
-    launch_adler_flat((const uint8_t*)d_data, len, reinterpret_cast<uint32_t*>(h->arena + 1024), d_out, h->stream);
+    int rc = ensure_arena(L, 1024 + nseg * 8 + 512); if (rc) return rc;
+    rc = ensure_meta(L, 4096); if (rc) return rc;
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(L.arena);
+    launch_adler_flat((const uint8_t*)d_data, len, reinterpret_cast<uint32_t*>(L.arena + 1024), d_out, L.stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h->meta, d_out, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    *out = *reinterpret_cast<uint32_t*>(h->meta);
+    CU(cudaMemcpyAsync(L.meta, d_out, 4, cudaMemcpyDeviceToHost, L.stream));
+    CU(cudaStreamSynchronize(L.stream));
+    *out = *reinterpret_cast<uint32_t*>(L.meta);
     return 0;
 }
 
@@ -713,14 +812,15 @@ int vcp_crc32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) {
     if (!h || !out || (len && !d_data)) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
-    int rc = ensure_arena(h, 4096); if (rc) return rc;
-    rc = ensure_meta(h, 4096); if (rc) return rc;
-    uint32_t* d_out = reinterpret_cast<uint32_t*>(h->arena);
-    launch_crc_flat((const uint8_t*)d_data, len, d_out, h->stream);
+    Lane& L = h->lane[0]; (void)L;
+    int rc = ensure_arena(L, 4096); if (rc) return rc;
+    rc = ensure_meta(L, 4096); if (rc) return rc;
+    uint32_t* d_out = reinterpret_cast<uint32_t*>(L.arena);
+    launch_crc_flat((const uint8_t*)d_data, len, d_out, L.stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h->meta, d_out, 4, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    *out = *reinterpret_cast<uint32_t*>(h->meta);
+    CU(cudaMemcpyAsync(L.meta, d_out, 4, cudaMemcpyDeviceToHost, L.stream));
+    CU(cudaStreamSynchronize(L.stream));
+    *out = *reinterpret_cast<uint32_t*>(L.meta);
     return 0;
 }
 
@@ -729,9 +829,10 @@ int vcp_base64(vcp_handle* h, const void* d_src, uint64_t len, void* d_dst) {
     if (((uintptr_t)d_src & 3) || ((uintptr_t)d_dst & 15)) return fail(VCP_EINVAL, "vcp_base64 needs a 4-byte aligned source and a 16-byte aligned destination");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
-    launch_base64_flat((const uint8_t*)d_src, len, (uint8_t*)d_dst, h->stream);
+    Lane& L = h->lane[0]; (void)L;
+    launch_base64_flat((const uint8_t*)d_src, len, (uint8_t*)d_dst, L.stream);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(L.stream));
     return 0;
 }
 

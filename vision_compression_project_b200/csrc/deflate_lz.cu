@@ -24,6 +24,7 @@
 //      window positions inserted with atomicMax (highest position wins -> deterministic).
 // Integer/latency bound, not HBM bound: the stream is read ~once from L2/HBM; see DESIGN.md §5.
 #include "vcp_internal.cuh"
+#include <algorithm>
 
 namespace vcp {
 
@@ -138,9 +139,13 @@ __device__ __forceinline__ int run_end(const uint8_t* __restrict__ S, int from, 
 __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     extern __shared__ __align__(16) unsigned char lz_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = blockIdx.x * kLzWarps + warp;
-    if (sub >= B.nsub) return;
     WarpMem& M = reinterpret_cast<WarpMem*>(lz_smem)[warp];
+  // persistent warps: sub-chunks are handed out in stream order from a work queue, so the grid never has a ragged last wave
+  for (;;) {
+    int sub = 0;
+    if (lane == 0) sub = (int)atomicAdd(&B.counters[0], 1u);
+    sub = __shfl_sync(kFull, sub, 0);
+    if (sub >= B.nsub) return;
     const BlockD& blk = B.blocks[B.sub2blk[sub]];
     const PageD& pg = B.pages[blk.page];
     const uint8_t* __restrict__ S = pg.filt;
@@ -423,6 +428,8 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     if (lane == 0) B.sub_ntok[sub] = ntok;
     uint32_t* hout = B.sub_hist + (size_t)sub * kHistSize;
     for (int i = lane; i < kHistSize; i += 32) hout[i] = M.hist[i];
+    __syncwarp();
+  }
 }
 
 int launch_lz(const BatchD& b, cudaStream_t st) {
@@ -433,7 +440,8 @@ int launch_lz(const BatchD& b, cudaStream_t st) {
         cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    k_lz<<<(b.nsub + kLzWarps - 1) / kLzWarps, kLzWarps * 32, smem, st>>>(b);
+    const int ctas = std::min((b.nsub + kLzWarps - 1) / kLzWarps, 148 * (16 / kLzWarps));   // 16 resident warps per SM (smem bound)
+    k_lz<<<ctas, kLzWarps * 32, smem, st>>>(b);
     return 1;
 }
 

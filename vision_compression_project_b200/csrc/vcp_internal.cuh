@@ -81,6 +81,7 @@ struct BatchD {
     uint64_t* b64_off; uint64_t* b64_len;
     uint64_t* totals;        // [0] = png bytes used, [1] = b64 bytes used
     uint32_t* err;           // [0] != 0: capacity exceeded
+    uint32_t* counters;      // zeroed per launch set: [0] = next LZ sub-chunk (work queue of k_lz)
     int32_t framed;          // 1 = PNG container (sig/IHDR/IDAT/IEND); 0 = bare zlib stream (vcp_deflate)
     int32_t level;           // 0 = stored only
     int32_t want_b64;
