@@ -51,10 +51,9 @@ __device__ __forceinline__ uint32_t ldu(const uint32_t* __restrict__ S32, int x)
     return __funnelshift_r(__ldg(S32 + w), __ldg(S32 + w + 1), (x & 3) * 8);
 }
 
-__device__ __forceinline__ int ilog2x4(uint32_t v) {   // quarter-bit log2, v >= 1
+__device__ __forceinline__ int ilog2x4(uint32_t v) {   // quarter-bit log2, 1 <= v < 2^30: 4*floor(log2 v) + next two mantissa bits
     const int n = 31 - __clz(v);
-    const uint32_t frac = n >= 2 ? (v >> (n - 2)) & 3u : (n == 1 ? (v & 1u) << 1 : 0u);
-    return 4 * n + (int)frac;
+    return 4 * n + (int)(((v << 2) >> n) & 3u);
 }
 
 __device__ __forceinline__ int len_sym(int len) {      // 3..258 -> 0..28
@@ -73,10 +72,12 @@ __device__ __forceinline__ int dist_sym(int dist) {    // 1..32768 -> 0..29
 
 // number of equal leading bytes of two 16-byte strings given as four words each (16 = all equal)
 __device__ __forceinline__ int eq16(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
-    const unsigned long long lo = ((unsigned long long)x1 << 32) | x0, hi = ((unsigned long long)x3 << 32) | x2;
-    const int nlo = lo ? (__ffsll((long long)lo) - 1) >> 3 : 8;
-    const int nhi = hi ? (__ffsll((long long)hi) - 1) >> 3 : 8;
-    return lo ? nlo : 8 + nhi;
+    const uint32_t w01 = x0 ? x0 : x1, w23 = x2 ? x2 : x3;
+    const int b01 = x0 ? 0 : 4, b23 = x2 ? 8 : 12;
+    const bool lo = (x0 | x1) != 0u;
+    const uint32_t w = lo ? w01 : w23;
+    const int b = lo ? b01 : b23;
+    return b + (w ? (__ffs(w) - 1) >> 3 : 4);
 }
 
 // warp-cooperative: length of the common prefix of S[y..] and S[y-d..], up to maxn (128 bytes per step)
@@ -170,9 +171,10 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     //      and shifts the bucket once.
     {
         const int h0 = max(0, s - kMaxDist);                                     // multiple of 128 (s is a multiple of 32 KiB)
-        uint32_t cw = h0 < s ? __ldg(S32 + (h0 >> 2) + lane) : 0u;
+        uint32_t cw = 0u, cn = 0u;                                               // current chunk, next chunk; a third is in flight
+        if (h0 < s) { cw = __ldg(S32 + (h0 >> 2) + lane); cn = __ldg(S32 + ((h0 + 128) >> 2) + lane); }
         for (int w0 = h0; w0 < s; w0 += 128) {
-            const uint32_t cn = __ldg(S32 + ((w0 + 128) >> 2) + lane);           // <= 128 bytes past s: still inside the stream or its pad
+            const uint32_t cf = __ldg(S32 + ((w0 + 256) >> 2) + lane);           // <= 256 bytes past s: inside the stream or its pad
             // a chunk that is one repeated byte (white paper after filtering: most of a text page) hashes every position
             // to the same two buckets: the four windows' inserts collapse to one store per table
             const uint32_t c00 = __shfl_sync(kFull, cw, 0), cn0 = __shfl_sync(kFull, cn, 0);
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     M.t3[h3] = v; M.t6[h6] = v;
                 }
                 __syncwarp();
-                cw = cn;
+                cw = cn; cn = cf;
                 continue;
             }
             const int sh = (lane & 3) * 8;
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 if (ok6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
                 __syncwarp();
             }
-            cw = cn;
+            cw = cn; cn = cf;
         }
     }
 
