@@ -71,19 +71,27 @@ static inline int ilog2x4(uint32_t v) {
 }
 
 /* ------------------------------------------------------------------ LZ: one sub-chunk (one warp) */
-int64_t dm_lz_subchunk(const uint8_t* S, int64_t F, int64_t s, int64_t e, const dm_params* P,
-                       uint32_t* tok, uint32_t* hist /* 286 + 30 */) {
+/* T / T2: caller-owned tables (T: ways << hash_bits, T2: hash2_ways << hash2_bits u16 entries).
+   cont = 0: tables are cleared and primed with the previous prime_bytes of the stream (independent sub-chunk);
+   cont = 1: tables hold the state left by the sub-chunk [s - sub_bytes, s) (entries relative to s - sub_bytes - 32 KiB);
+             they are rebased by sub_bytes (entries that fall out of the window become empty) and not primed. */
+int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, const dm_params* P,
+                          uint32_t* tok, uint32_t* hist /* 286 + 30 */, uint16_t* T, uint16_t* T2, int cont) {
     const int hb = P->hash_bits, ways = P->ways, bpp = P->bpp, lcap = P->lane_cap;
     const int64_t base = s - MAXD;                  /* table stores pos - base as u16 */
     const int tsize = (1 << hb) * ways;
-    uint16_t* T = (uint16_t*)malloc(sizeof(uint16_t) * tsize);
-    memset(T, 0, sizeof(uint16_t) * tsize);       /* 0 = empty (position base+0 is never a candidate) */
+    const int tsize2 = P->hash2_bytes ? ((P->hash2_ways > 0 ? P->hash2_ways : 1) << P->hash2_bits) : 0;
+    if (!cont) {
+        memset(T, 0, sizeof(uint16_t) * tsize);   /* 0 = empty (position base+0 is never a candidate) */
+        if (tsize2) memset(T2, 0, sizeof(uint16_t) * tsize2);
+    } else {
+        for (int i = 0; i < tsize; i++) T[i] = T[i] >= P->sub_bytes ? (uint16_t)(T[i] - P->sub_bytes) : 0;
+        for (int i = 0; i < tsize2; i++) T2[i] = T2[i] >= P->sub_bytes ? (uint16_t)(T2[i] - P->sub_bytes) : 0;
+    }
     int64_t ntok = 0;
     memset(hist, 0, sizeof(uint32_t) * 316);
     const int nb2 = P->hash2_bytes, hb2 = P->hash2_bits;
-    uint16_t* T2 = NULL;
     const int ways2 = P->hash2_ways > 0 ? P->hash2_ways : 1;
-    if (nb2) { T2 = (uint16_t*)calloc((size_t)ways2 << hb2, sizeof(uint16_t)); }
 
 #define INSERT(q) do { if ((q) >= 0 && (q) + 2 < F) { uint32_t h_ = hash3(S + (q), hb) * ways; \
         for (int w_ = ways - 1; w_ > 0; w_--) { T[h_ + w_] = T[h_ + w_ - 1]; } \
@@ -95,6 +103,7 @@ int64_t dm_lz_subchunk(const uint8_t* S, int64_t F, int64_t s, int64_t e, const 
     /* priming: positions [max(0, s - prime), s), window by window; within a window only the
        highest lane of each hash group writes, and for ways>1 it shifts the bucket ONCE. */
     int64_t hs = s - P->prime_bytes; if (hs < 0) hs = 0;
+    if (cont) hs = s;                               /* continuing: nothing to prime */
     for (int64_t w0 = hs; w0 < s; w0 += WIN) {
         for (int i = 0; i < WIN; i++) {
             int64_t q = w0 + i; if (q >= s) continue;
@@ -237,8 +246,16 @@ int64_t dm_lz_subchunk(const uint8_t* S, int64_t F, int64_t s, int64_t e, const 
         p = next;
         score = score - (score >> 3) + nlit;
     }
-    free(T); free(T2);
     return ntok;
+}
+
+/* independent sub-chunk (fresh tables) */
+int64_t dm_lz_subchunk(const uint8_t* S, int64_t F, int64_t s, int64_t e, const dm_params* P, uint32_t* tok, uint32_t* hist) {
+    uint16_t* T = (uint16_t*)malloc(sizeof(uint16_t) * ((size_t)P->ways << P->hash_bits));
+    uint16_t* T2 = (uint16_t*)malloc(sizeof(uint16_t) * (((size_t)(P->hash2_ways > 0 ? P->hash2_ways : 1) << P->hash2_bits) + 1));
+    int64_t n = dm_lz_subchunk_ex(S, F, s, e, P, tok, hist, T, T2, 0);
+    free(T); free(T2);
+    return n;
 }
 
 /* ------------------------------------------------------------------ Huffman */
@@ -411,6 +428,10 @@ int64_t dm_deflate_page(const uint8_t* S, int64_t F, const dm_params* P, uint8_t
     int64_t nblocks = (F + P->block_bytes - 1) / P->block_bytes; if (nblocks == 0) nblocks = 1;
     uint32_t adler = adler32_(S, F);
     uint32_t* tok = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(P->block_bytes + 64));
+    uint16_t* T = (uint16_t*)malloc(sizeof(uint16_t) * ((size_t)P->ways << P->hash_bits));
+    uint16_t* T2 = (uint16_t*)malloc(sizeof(uint16_t) * (((size_t)(P->hash2_ways > 0 ? P->hash2_ways : 1) << P->hash2_bits) + 1));
+    const int G = P->group_subs > 1 ? P->group_subs : 1;      /* consecutive sub-chunks of a page handled by one warp */
+    int64_t subidx = 0;
     int64_t o = 0;
     if (st) memset(st, 0, sizeof *st);
     for (int64_t b = 0; b < nblocks; b++) {
@@ -418,7 +439,8 @@ int64_t dm_deflate_page(const uint8_t* S, int64_t F, const dm_params* P, uint8_t
         uint32_t hist[316] = {0}, h1[316]; int64_t ntok = 0;
         for (int64_t s = bs; s < be; s += P->sub_bytes) {
             int64_t e = s + P->sub_bytes; if (e > be) e = be;
-            ntok += dm_lz_subchunk(S, F, s, e, P, tok + ntok, h1);
+            ntok += dm_lz_subchunk_ex(S, F, s, e, P, tok + ntok, h1, T, T2, (int)(subidx % G != 0));
+            subidx++;
             for (int i = 0; i < 316; i++) hist[i] += h1[i];
         }
         int stored = 0;
@@ -427,6 +449,6 @@ int64_t dm_deflate_page(const uint8_t* S, int64_t F, const dm_params* P, uint8_t
         if (st) { st->tokens += ntok; st->stored_blocks += stored; st->blocks++; }
         o += n;
     }
-    free(tok);
+    free(tok); free(T); free(T2);
     return o;
 }

@@ -28,12 +28,15 @@ typedef struct {
     int32_t cost_warm;    /* tokens needed in the sub-chunk before pricing starts */
     int32_t hash2_ways;
     int32_t ins_limit;    /* 1: a window inserts only the positions its parse consumed (q < next) */
+    int32_t group_subs;   /* consecutive sub-chunks of a page that share one pair of tables (first primed, rest continue) */
     int64_t block_bytes;  /* deflate block (multiple of sub_bytes) */
 } dm_params;
 typedef struct { int64_t tokens, blocks, stored_blocks; } dm_stats;
 int dm_len_sym(int len);
 int dm_dist_sym(int dist);
 int64_t dm_lz_subchunk(const uint8_t* S, int64_t F, int64_t s, int64_t e, const dm_params* P, uint32_t* tok, uint32_t* hist);
+int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, const dm_params* P, uint32_t* tok, uint32_t* hist,
+                          uint16_t* T, uint16_t* T2, int cont);
 void dm_huff_lengths(const uint32_t* freq, int n, int maxbits, uint8_t* lens);
 void dm_canonical(const uint8_t* lens, int n, int maxbits, uint16_t* codes);
 int64_t dm_huff_block(const uint32_t* tok, int64_t ntok, const uint32_t* hist, const uint8_t* raw, int64_t rawlen,

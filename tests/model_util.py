@@ -14,17 +14,17 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("bpp", "hash_bits", "ways", "lane_cap", "too_far", "lazy", "cont_min",
                                          "prime_bytes", "capped_wins", "inwin", "cont_maxd", "sub_bytes", "hash2_bytes",
                                          "hash2_bits", "noisy_thresh", "noisy_minlen", "noisy_neard", "cost_maxlen",
-                                         "cost_margin", "cost_warm", "hash2_ways", "ins_limit")] + [("block_bytes", C.c_int64)]
+                                         "cost_margin", "cost_warm", "hash2_ways", "ins_limit", "group_subs")] + [("block_bytes", C.c_int64)]
 
 
 class Stats(C.Structure):
     _fields_ = [("tokens", C.c_int64), ("blocks", C.c_int64), ("stored_blocks", C.c_int64)]
 
 
-# the configuration csrc/deflate_lz.cu + deflate_huff.cu implement
-KERNEL_PARAMS = dict(bpp=3, hash_bits=11, ways=2, lane_cap=64, too_far=32768, lazy=16, cont_min=258, prime_bytes=32768,
+# the configuration csrc/deflate_lz.cu + deflate_huff.cu implement (group_subs mirrors kGroupSubs in vcp_internal.cuh)
+KERNEL_PARAMS = dict(bpp=3, hash_bits=10, ways=2, lane_cap=64, too_far=32768, lazy=16, cont_min=258, prime_bytes=32768,
                      capped_wins=1, inwin=0, cont_maxd=1, noisy_thresh=0, noisy_minlen=6, noisy_neard=0, cost_maxlen=8,
-                     cost_margin=0, cost_warm=64, hash2_ways=2, ins_limit=0, hash2_bytes=4, hash2_bits=10, sub_bytes=32768,
+                     cost_margin=0, cost_warm=64, hash2_ways=2, ins_limit=0, group_subs=1, hash2_bytes=4, hash2_bits=10, sub_bytes=32768,
                      block_bytes=512 * 1024)
 
 
@@ -34,8 +34,9 @@ def load():
     lib = C.CDLL(SO)
     lib.dm_deflate_page.restype = C.c_int64
     lib.dm_deflate_page.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Params), C.c_void_p, C.c_void_p, C.POINTER(Stats)]
-    lib.dm_lz_subchunk.restype = C.c_int64
-    lib.dm_lz_subchunk.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Params), C.c_void_p, C.c_void_p]
+    lib.dm_lz_subchunk_ex.restype = C.c_int64
+    lib.dm_lz_subchunk_ex.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Params), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
@@ -56,11 +57,17 @@ def lz_tokens(lib, stream: bytes, **kw):
     F = len(stream)
     src = np.concatenate([np.frombuffer(stream, np.uint8), np.zeros(512, np.uint8)])
     res = []
+    T = np.zeros(p["ways"] << p["hash_bits"], np.uint16)
+    T2 = np.zeros((max(1, p["hash2_ways"]) << p["hash2_bits"]) + 1, np.uint16)
+    G = max(1, p["group_subs"])
+    idx = 0
     for bs in range(0, F, p["block_bytes"]):
         be = min(F, bs + p["block_bytes"])
         for s in range(bs, be, p["sub_bytes"]):
             e = min(be, s + p["sub_bytes"])
             tok = np.zeros(e - s + 64, np.uint32); hist = np.zeros(316, np.uint32)
-            n = lib.dm_lz_subchunk(src.ctypes.data, F, s, e, C.byref(P), tok.ctypes.data, hist.ctypes.data)
+            n = lib.dm_lz_subchunk_ex(src.ctypes.data, F, s, e, C.byref(P), tok.ctypes.data, hist.ctypes.data,
+                                      T.ctypes.data, T2.ctypes.data, int(idx % G != 0))
             res.append((tok[:n].copy(), hist))
+            idx += 1
     return res

@@ -254,6 +254,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     const size_t o_pages = bump.take((size_t)n * sizeof(PageD));
     const size_t o_blocks = bump.take((size_t)nblocks * sizeof(BlockD) + 8);
     const size_t o_sub2blk = bump.take((size_t)nsub * 4 + 4);
+    const size_t o_item2sub = bump.take((size_t)nsub * 4 + 4);
     const size_t desc_bytes = bump.off - o_coeff;
     int rc = ensure_arena(L, bump.off + 256);
     if (rc) return rc;
@@ -269,6 +270,8 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     PageD* hp = reinterpret_cast<PageD*>(M + (o_pages - o_coeff));
     BlockD* hb = reinterpret_cast<BlockD*>(M + (o_blocks - o_coeff));
     uint32_t* hs2b = reinterpret_cast<uint32_t*>(M + (o_sub2blk - o_coeff));
+    uint32_t* hi2s = reinterpret_cast<uint32_t*>(M + (o_item2sub - o_coeff));
+    int nitems = 0;
     const int32_t* d_coeff = reinterpret_cast<const int32_t*>(A + o_coeff);
     int blk = 0, sub = 0, row = 0;
     int max_sh = 0, max_sw = 0, max_rh = 0, max_rw = 0, max_w = 0, max_h = 0, max_wc = 0;
@@ -308,6 +311,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
         out.filt_off.push_back(P.o_filt);
         D.row0 = row; row += P.h;
         D.blk0 = blk; D.nblk = P.nblk;
+        for (int k = 0; k < P.nsub; k += kGroupSubs) hi2s[nitems++] = (uint32_t)(sub + k);   // groups restart at every page
         for (int b = 0; b < P.nblk; b++) {
             BlockD& Bk = hb[blk];
             Bk.page = i; Bk.first = b == 0; Bk.last = b == P.nblk - 1;
@@ -325,6 +329,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     B.pages = reinterpret_cast<const PageD*>(A + o_pages); B.npages = n;
     B.blocks = reinterpret_cast<const BlockD*>(A + o_blocks); B.nblocks = nblocks;
     B.sub2blk = reinterpret_cast<const uint32_t*>(A + o_sub2blk); B.nsub = nsub;
+    B.item2sub = reinterpret_cast<const uint32_t*>(A + o_item2sub); B.nitems = nitems;
     B.filt_base = A + o_filt_region;
     B.tokens = need_lz ? reinterpret_cast<uint32_t*>(A + o_tokens) : nullptr;
     B.sub_ntok = reinterpret_cast<uint32_t*>(A + o_sub_ntok);

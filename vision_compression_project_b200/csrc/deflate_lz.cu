@@ -30,7 +30,7 @@ namespace vcp {
 
 namespace {
 
-constexpr int HB3 = 11;               // 3-byte-hash table: 2^11 buckets, u32 = (newest<<16) | older
+constexpr int HB3 = 10;               // 3-byte-hash table: 2^10 buckets, u32 = (newest<<16) | older
 constexpr int HB6 = 10;               // 4-byte-hash table: 2^10 buckets, same bucket format
 constexpr int kH2Bytes = 4;           // bytes keyed by the second table
 constexpr int kLzWarps = 2;           // warps (= sub-chunks) per CTA
@@ -143,10 +143,14 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     WarpMem& M = reinterpret_cast<WarpMem*>(lz_smem)[warp];
   // persistent warps: sub-chunks are handed out in stream order from a work queue, so the grid never has a ragged last wave
   for (;;) {
-    int sub = 0;
-    if (lane == 0) sub = (int)atomicAdd(&B.counters[0], 1u);
-    sub = __shfl_sync(kFull, sub, 0);
-    if (sub >= B.nsub) return;
+    int item = 0;
+    if (lane == 0) item = (int)atomicAdd(&B.counters[0], 1u);
+    item = __shfl_sync(kFull, item, 0);
+    if (item >= B.nitems) return;
+    const int sub_first = (int)B.item2sub[item];
+    const int sub_count = (item + 1 < B.nitems ? (int)B.item2sub[item + 1] : B.nsub) - sub_first;
+   for (int si = 0; si < sub_count; si++) {
+    const int sub = sub_first + si;
     const BlockD& blk = B.blocks[B.sub2blk[sub]];
     const PageD& pg = B.pages[blk.page];
     const uint8_t* __restrict__ S = pg.filt;
@@ -158,18 +162,34 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     const int base = s - kMaxDist;                                               // table entries are pos - base (u16), 0 = empty
     uint32_t* __restrict__ tok = B.tokens + ((S - B.filt_base) + s);
 
-    // ---- clear tables + histogram
-    {
+    if (si == 0) {
+        // ---- first sub-chunk of the group: clear tables + histogram, then prime (below)
         uint4* z = reinterpret_cast<uint4*>(&M);
         const uint4 zero = make_uint4(0, 0, 0, 0);
         for (int i = lane; i < (int)(sizeof(WarpMem) / 16); i += 32) z[i] = zero;
+    } else {
+        // ---- next sub-chunk of the group: the tables already hold every position the parse of the previous sub-chunk
+        //      inserted; move them to the new base (s advanced by 32 KiB; what falls out of the window becomes empty)
+        uint4* z = reinterpret_cast<uint4*>(&M);
+        constexpr int kTableVec = (int)((sizeof(M.t3) + sizeof(M.t6)) / 16);
+        for (int i = lane; i < kTableVec; i += 32) {
+            uint4 v = z[i];
+            // per u16 half: h >= 0x8000 ? h - 0x8000 : 0   ==   (h & 0x7FFF) masked by the replicated top bit
+            #define VCP_REBASE(x) ((x) & 0x7FFF7FFFu & ((((x) >> 15) & 0x00010001u) * 0xFFFFu))
+            v.x = VCP_REBASE(v.x); v.y = VCP_REBASE(v.y); v.z = VCP_REBASE(v.z); v.w = VCP_REBASE(v.w);
+            #undef VCP_REBASE
+            z[i] = v;
+        }
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        uint4* hz = reinterpret_cast<uint4*>(M.hist);
+        for (int i = lane; i < (int)(sizeof(M.hist) / 16); i += 32) hz[i] = zero;
     }
     __syncwarp();
 
     // ---- prime with the previous 32 KiB of the page: 128 bytes (4 windows) per load, next chunk prefetched.
     //      Per window the arithmetic is the main loop's insert: the highest lane of a bucket group wins (atomicMax)
     //      and shifts the bucket once.
-    {
+    if (si == 0) {
         const int h0 = max(0, s - kMaxDist);                                     // multiple of 128 (s is a multiple of 32 KiB)
         uint32_t cw = 0u, cn = 0u;                                               // current chunk, next chunk; a third is in flight
         if (h0 < s) { cw = __ldg(S32 + (h0 >> 2) + lane); cn = __ldg(S32 + ((h0 + 128) >> 2) + lane); }
@@ -431,18 +451,23 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     uint32_t* hout = B.sub_hist + (size_t)sub * kHistSize;
     for (int i = lane; i < kHistSize; i += 32) hout[i] = M.hist[i];
     __syncwarp();
+   }
   }
 }
 
 int launch_lz(const BatchD& b, cudaStream_t st) {
-    if (b.nsub == 0) return 0;
+    if (b.nitems == 0) return 0;
     const size_t smem = sizeof(WarpMem) * kLzWarps;
-    static bool configured = false;
-    if (!configured) {
+    static int resident = 0;                                  // CTAs the device can hold at once (persistent grid)
+    if (!resident) {
         cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        int per_sm = 0, dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz, kLzWarps * 32, smem);
+        resident = std::max(1, per_sm) * sms;
     }
-    const int ctas = std::min((b.nsub + kLzWarps - 1) / kLzWarps, 148 * (16 / kLzWarps));   // 16 resident warps per SM (smem bound)
+    const int ctas = std::min((b.nitems + kLzWarps - 1) / kLzWarps, resident);
     k_lz<<<ctas, kLzWarps * 32, smem, st>>>(b);
     return 1;
 }

@@ -8,6 +8,8 @@ namespace vcp {
 
 constexpr int kSubBytes   = 32768;        // LZ sub-chunk: one warp, one 64 Ki-position window of u16 table entries
 constexpr int kBlockBytes = 512 * 1024;   // deflate block = one IDAT chunk = 16 sub-chunks
+constexpr int kGroupSubs  = 1;            // consecutive sub-chunks of a page one warp handles with one pair of hash tables
+                                          // (2 halves the priming work but measured slower on B200: fewer, longer work items -> ragged tail)
 constexpr int kMaxDist    = 32768;
 constexpr int kMaxMatch   = 258;
 constexpr int kNumLL      = 286;
@@ -57,6 +59,7 @@ struct BatchD {
     const PageD* pages; int32_t npages;
     const BlockD* blocks; int32_t nblocks;
     const uint32_t* sub2blk; int32_t nsub;
+    const uint32_t* item2sub; int32_t nitems;   // LZ work items: first sub-chunk of each group of <= kGroupSubs (never across pages)
     const uint8_t* filt_base;    // base of the filtered buffer (token index = filt ptr - filt_base)
     uint32_t* tokens;        // u32 per filtered byte position; tokens of a sub-chunk are compact from its first position
     uint32_t* sub_ntok;      // tokens per sub-chunk
