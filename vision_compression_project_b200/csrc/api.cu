@@ -206,8 +206,8 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
             if (!o.src_device) P.o_raw = bump.take((size_t)P.sw * P.sc * P.sh + 16);
             if (P.need_conv) P.o_conv = bump.take((size_t)P.sw * P.sh * P.c + 16);
             if (P.need_red) P.o_red = bump.take((size_t)P.rw * P.rh * P.c + 16);
-            if (P.need_h) P.o_tmp = bump.take((size_t)P.w * P.rh * P.c + 16);
-            if (P.need_v) P.o_vout = bump.take((size_t)P.w * P.h * P.c + 16);
+            if (P.need_h) P.o_tmp = bump.take(align_up((size_t)P.w * P.c, 16) * P.rh + 16);      // rows padded to 16 B: aligned word loads in the V pass
+            if (P.need_v) P.o_vout = bump.take(align_up((size_t)P.w * P.c, 16) * P.h + 16);
             if (P.need_h) {
                 P.ch = get_coeffs(h, P.rw, P.w, o.resample, P.box[0], P.box[2]);
                 if (!P.ch) return fail(VCP_EINVAL, "bad resample parameters");
@@ -293,12 +293,12 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
             if (P.need_red) { D.red = A + P.o_red; cur = D.red; cur_stride = (int64_t)P.rw * P.c; any_red = true; }
             D.hin = cur; D.hin_stride = cur_stride;
             if (P.need_h) {
-                D.tmp = A + P.o_tmp; cur = D.tmp; cur_stride = (int64_t)P.w * P.c; any_h = true;
+                D.tmp = A + P.o_tmp; D.tmp_stride = (int64_t)align_up((size_t)P.w * P.c, 16); cur = D.tmp; cur_stride = D.tmp_stride; any_h = true;
                 D.hb = d_coeff + coeff_at[P.ch].first; D.hk = d_coeff + coeff_at[P.ch].second; D.hks = P.ch->ksize;
             }
             D.vin = cur; D.vin_stride = cur_stride;
             if (P.need_v) {
-                D.vout = A + P.o_vout; cur = D.vout; cur_stride = (int64_t)P.w * P.c; any_v = true;
+                D.vout = A + P.o_vout; D.vout_stride = (int64_t)align_up((size_t)P.w * P.c, 16); cur = D.vout; cur_stride = D.vout_stride; any_v = true;
                 D.vb = d_coeff + coeff_at[P.cv].first; D.vk = d_coeff + coeff_at[P.cv].second; D.vks = P.cv->ksize;
             }
             D.pix = cur; D.pix_stride = cur_stride;
@@ -716,10 +716,11 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
     const uint8_t* cur = D.hin; int64_t cur_stride = D.hin_stride;
     if (need_h) {
         D.tmp = need_v ? d_tmp : (uint8_t*)d_dst; D.hb = d_blob + ihb; D.hk = d_blob + ihk; D.hks = ch->ksize;
-        cur = D.tmp; cur_stride = (int64_t)out_width * channels;
+        D.tmp_stride = (int64_t)out_width * channels;
+        cur = D.tmp; cur_stride = D.tmp_stride;
     }
     D.vin = cur; D.vin_stride = cur_stride;
-    if (need_v) { D.vout = (uint8_t*)d_dst; D.vb = d_blob + ivb; D.vk = d_blob + ivk; D.vks = cv->ksize; }
+    if (need_v) { D.vout = (uint8_t*)d_dst; D.vout_stride = (int64_t)out_width * channels; D.vb = d_blob + ivb; D.vk = d_blob + ivk; D.vks = cv->ksize; }
     const PageD* dp; rc = stage_page(L, D, 0, nullptr, &dp); if (rc) return rc;
     if (need_h) launch_resample_h(dp, 1, height, out_width, L.stream);
     if (need_v) launch_resample_v(dp, 1, out_height, out_width * channels, L.stream);

@@ -310,22 +310,40 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     cpos[w] = live[w] ? cp : q;
                     clen[w] = 0;
                 }
-                uint32_t x0[4], x1[4], x2[4], x3[4];
+                // stage A: the first 4 bytes only (two words per candidate, all eight loads issued before the first use) —
+                // in noisy rows almost every candidate dies here
+                uint32_t g0k[4], g1k[4];
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
-                    const uint32_t* g = S32 + (cpos[w] >> 2);
-                    const int shc = (cpos[w] & 3) * 8;
-                    const uint32_t g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4);
-                    x0[w] = cur4 ^ __funnelshift_r(g0, g1, shc); x1[w] = nxt4 ^ __funnelshift_r(g1, g2, shc);
-                    x2[w] = q8 ^ __funnelshift_r(g2, g3, shc);   x3[w] = q12 ^ __funnelshift_r(g3, g4, shc);
-                }
+                for (int w = 0; w < 4; w++) { const uint32_t* g = S32 + (cpos[w] >> 2); g0k[w] = __ldg(g); g1k[w] = __ldg(g + 1); }
                 bool any = false;
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
-                    const int n = eq16(x0[w], x1[w], x2[w], x3[w]);
+                    const uint32_t x0 = cur4 ^ __funnelshift_r(g0k[w], g1k[w], (cpos[w] & 3) * 8);
+                    const int n = x0 ? (__ffs(x0) - 1) >> 3 : 4;
                     clen[w] = live[w] ? min(n, hcap) : 0;
-                    live[w] = live[w] && n == 16 && hcap > 16;
+                    live[w] = live[w] && x0 == 0u && hcap > 4;
                     any |= live[w];
+                }
+                // stage B: bytes 4..15 of the survivors (loads first, then the compares)
+                if (any) {
+                    uint32_t g2k[4], g3k[4], g4k[4];
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        g2k[w] = g3k[w] = g4k[w] = 0u;
+                        if (live[w]) { const uint32_t* g = S32 + (cpos[w] >> 2); g2k[w] = __ldg(g + 2); g3k[w] = __ldg(g + 3); g4k[w] = __ldg(g + 4); }
+                    }
+                    any = false;
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        if (live[w]) {
+                            const int shc = (cpos[w] & 3) * 8;
+                            const int n = eq16(0u, nxt4 ^ __funnelshift_r(g1k[w], g2k[w], shc), q8 ^ __funnelshift_r(g2k[w], g3k[w], shc),
+                                               q12 ^ __funnelshift_r(g3k[w], g4k[w], shc));
+                            clen[w] = min(n, hcap);
+                            live[w] = n == 16 && hcap > 16;
+                            any |= live[w];
+                        }
+                    }
                 }
                 for (int n0 = 16; any; n0 += 16) {                                // rounds 2..4: only candidates still matching
                     any = false;

@@ -83,58 +83,134 @@ __device__ __forceinline__ uint8_t clip8(int v) {
     return (uint8_t)min(max(v, 0), 255);
 }
 
-// Horizontal pass: thread = one output pixel (all channels) of one row.
-__global__ void k_resample_h(const PageD* __restrict__ pages) {
+// Horizontal pass.  A CTA owns 128 output pixels x 8 input rows.  The input span those outputs read (bounds are
+// monotonic: [xmin of the first, xmin+n of the last)) is staged row by row into shared memory with coalesced word
+// loads; a thread keeps 8 rows x C accumulators in registers and walks the taps once, so every Q22 coefficient is
+// loaded once per 8 rows and every pixel byte comes from shared memory.  Spans too long for the tile (extreme
+// down-scales) take the direct path below.
+constexpr int kHPix = 128;           // output pixels per CTA
+constexpr int kHRows = 8;            // input rows per CTA
+constexpr int kHSpanMax = 4096;      // staged bytes per row (aligned span)
+
+template <int C>
+__device__ __forceinline__ void resample_h_direct(const PageD& P, int y, int xx) {
+    const int w = P.w;
+    const int xmin = __ldg(P.hb + 2 * xx), n = __ldg(P.hb + 2 * xx + 1);
+    const uint8_t* __restrict__ row = P.hin + (int64_t)y * P.hin_stride + (int64_t)xmin * C;
+    uint8_t* __restrict__ out = P.tmp + (int64_t)y * P.tmp_stride + (int64_t)xx * C;
+    int a[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) a[ch] = 1 << 21;
+    for (int k = 0; k < n; k++) {
+        const int kv = __ldg(P.hk + (int64_t)k * w + xx);
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) a[ch] += (int)__ldg(row + C * k + ch) * kv;
+    }
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) out[ch] = clip8(a[ch]);
+}
+
+template <int C>
+__device__ __forceinline__ void resample_h_tile(const PageD& P, uint32_t* sm) {
+    const int w = P.w;
+    const int xx0 = blockIdx.x * kHPix;
+    const int y0 = blockIdx.y * kHRows;
+    const int xx = xx0 + threadIdx.x;
+    const int xxl = min(w, xx0 + kHPix) - 1;                       // last output pixel of the tile
+    const int lo_px = __ldg(P.hb + 2 * xx0);
+    const int hi_px = __ldg(P.hb + 2 * xxl) + __ldg(P.hb + 2 * xxl + 1);
+    const int rows = min(kHRows, P.rh - y0);
+    // byte span of the tile inside an input row, widened to aligned words of the row's global address
+    const int64_t lo_b = (int64_t)lo_px * C, hi_b = (int64_t)hi_px * C;
+    const uint8_t* row0 = P.hin + (int64_t)y0 * P.hin_stride;
+    const bool rows_aligned = (P.hin_stride & 3) == 0;             // same (address & 3) for every row of the tile
+    const int mis = (int)(((uintptr_t)row0 + lo_b) & 3);
+    const int span_words = (int)((mis + (hi_b - lo_b) + 3) >> 2);
+    if (!rows_aligned || span_words * 4 > kHSpanMax) {              // direct path (block-uniform decision)
+        if (xx < w) for (int r = 0; r < rows; r++) resample_h_direct<C>(P, y0 + r, xx);
+        return;
+    }
+    for (int r = 0; r < rows; r++) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(row0 + (int64_t)r * P.hin_stride + lo_b - mis);
+        uint32_t* d = sm + r * (kHSpanMax / 4);
+        for (int j = threadIdx.x; j < span_words; j += kHPix) d[j] = __ldg(g + j);
+    }
+    __syncthreads();
+    if (xx >= w) return;
+    const int xmin = __ldg(P.hb + 2 * xx), n = __ldg(P.hb + 2 * xx + 1);
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(sm) + mis + (xmin - lo_px) * C;
+    int acc[kHRows][C];
+#pragma unroll
+    for (int r = 0; r < kHRows; r++)
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) acc[r][ch] = 1 << 21;
+    for (int k = 0; k < n; k++) {
+        const int kv = __ldg(P.hk + (int64_t)k * w + xx);
+        const uint8_t* pk = sb + C * k;
+#pragma unroll
+        for (int r = 0; r < kHRows; r++)
+#pragma unroll
+            for (int ch = 0; ch < C; ch++) acc[r][ch] += (int)pk[r * kHSpanMax + ch] * kv;     // rows past `rows` read stale smem, never stored
+    }
+    for (int r = 0; r < rows; r++) {
+        uint8_t* out = P.tmp + (int64_t)(y0 + r) * P.tmp_stride + (int64_t)xx * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) out[ch] = clip8(acc[r][ch]);
+    }
+}
+
+__global__ void __launch_bounds__(kHPix) k_resample_h(const PageD* __restrict__ pages) {
+    __shared__ __align__(16) uint32_t sm[kHRows * kHSpanMax / 4];
     const PageD& P = pages[blockIdx.z];
     if (!P.tmp) return;
-    const int y = blockIdx.y;
-    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= P.rh || xx >= P.w) return;
-    const int c = P.c, w = P.w;
-    const int xmin = __ldg(P.hb + 2 * xx), n = __ldg(P.hb + 2 * xx + 1);
-    const uint8_t* __restrict__ row = P.hin + (int64_t)y * P.hin_stride + (int64_t)xmin * c;
-    uint8_t* __restrict__ out = P.tmp + ((int64_t)y * w + xx) * c;
-    if (c == 3) {
-        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    if ((int)blockIdx.y * kHRows >= P.rh || (int)blockIdx.x * kHPix >= P.w) return;
+    if (P.c == 3) resample_h_tile<3>(P, sm); else resample_h_tile<1>(P, sm);
+}
+
+// Vertical pass: a thread owns 4 consecutive bytes of one output row (one aligned word per tap) when the rows are
+// word aligned (always inside the arena), otherwise one byte.  The tap weight is the same for the whole row.
+__global__ void __launch_bounds__(256) k_resample_v(const PageD* __restrict__ pages) {
+    const PageD& P = pages[blockIdx.z];
+    if (!P.vout) return;
+    const int yy = blockIdx.y;
+    if (yy >= P.h) return;
+    const int wc = P.w * P.c;
+    const int ymin = __ldg(P.vb + 2 * yy), n = __ldg(P.vb + 2 * yy + 1);
+    const bool aligned = ((((uintptr_t)P.vin) | (uintptr_t)P.vin_stride | ((uintptr_t)P.vout) | (uintptr_t)P.vout_stride) & 3) == 0;
+    const int i4 = blockIdx.x * blockDim.x + threadIdx.x;       // word index in the row
+    if (aligned) {
+        if (4 * i4 >= wc) return;
+        const uint32_t* __restrict__ col = reinterpret_cast<const uint32_t*>(P.vin + (int64_t)ymin * P.vin_stride) + i4;
+        const int64_t sw = P.vin_stride >> 2;
+        int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21, a3 = 1 << 21;
         for (int k = 0; k < n; k++) {
-            const int kv = __ldg(P.hk + (int64_t)k * w + xx);
-            a0 += (int)__ldg(row + 3 * k) * kv; a1 += (int)__ldg(row + 3 * k + 1) * kv; a2 += (int)__ldg(row + 3 * k + 2) * kv;
+            const uint32_t v = __ldg(col + (int64_t)k * sw);
+            const int kv = __ldg(P.vk + (int64_t)k * P.h + yy);
+            a0 += (int)(v & 0xFFu) * kv; a1 += (int)((v >> 8) & 0xFFu) * kv; a2 += (int)((v >> 16) & 0xFFu) * kv; a3 += (int)(v >> 24) * kv;
         }
-        out[0] = clip8(a0); out[1] = clip8(a1); out[2] = clip8(a2);
+        const uint32_t o = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
+        // padded rows: the bytes past wc inside the last word are row padding, writing them is harmless
+        reinterpret_cast<uint32_t*>(P.vout + (int64_t)yy * P.vout_stride)[i4] = o;
     } else {
-        for (int ch = 0; ch < c; ch++) {
+        for (int i = 4 * i4; i < min(wc, 4 * i4 + 4); i++) {
+            const uint8_t* __restrict__ col = P.vin + (int64_t)ymin * P.vin_stride + i;
             int a = 1 << 21;
-            for (int k = 0; k < n; k++) a += (int)__ldg(row + (int64_t)k * c + ch) * __ldg(P.hk + (int64_t)k * w + xx);
-            out[ch] = clip8(a);
+            for (int k = 0; k < n; k++) a += (int)__ldg(col + (int64_t)k * P.vin_stride) * __ldg(P.vk + (int64_t)k * P.h + yy);
+            P.vout[(int64_t)yy * P.vout_stride + i] = clip8(a);
         }
     }
 }
 
-// Vertical pass: thread = one output byte (x*c + ch) of one output row; reads are contiguous along the row.
-__global__ void k_resample_v(const PageD* __restrict__ pages) {
-    const PageD& P = pages[blockIdx.z];
-    if (!P.vout) return;
-    const int yy = blockIdx.y;
-    const int wc = P.w * P.c;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (yy >= P.h || i >= wc) return;
-    const int ymin = __ldg(P.vb + 2 * yy), n = __ldg(P.vb + 2 * yy + 1);
-    const uint8_t* __restrict__ col = P.vin + (int64_t)ymin * P.vin_stride + i;
-    int a = 1 << 21;
-    for (int k = 0; k < n; k++) a += (int)__ldg(col + (int64_t)k * P.vin_stride) * __ldg(P.vk + (int64_t)k * P.h + yy);
-    P.vout[(int64_t)yy * wc + i] = clip8(a);
-}
-
 int launch_resample_h(const PageD* d_pages, int npages, int max_rh, int max_w, cudaStream_t st) {
     if (npages == 0 || max_rh == 0) return 0;
-    dim3 grid((max_w + 127) / 128, max_rh, npages);
-    k_resample_h<<<grid, 128, 0, st>>>(d_pages);
+    dim3 grid((max_w + kHPix - 1) / kHPix, (max_rh + kHRows - 1) / kHRows, npages);
+    k_resample_h<<<grid, kHPix, 0, st>>>(d_pages);
     return 1;
 }
 
 int launch_resample_v(const PageD* d_pages, int npages, int max_h, int max_wc, cudaStream_t st) {
     if (npages == 0 || max_h == 0) return 0;
-    dim3 grid((max_wc + 255) / 256, max_h, npages);
+    dim3 grid(((max_wc + 3) / 4 + 255) / 256, max_h, npages);
     k_resample_v<<<grid, 256, 0, st>>>(d_pages);
     return 1;
 }

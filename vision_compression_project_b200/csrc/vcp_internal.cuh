@@ -33,8 +33,10 @@ struct PageD {
     uint8_t* red;            // rw*rh*c   reduce output (nullptr: stage skipped)
     const uint8_t* hin; int64_t hin_stride;     // horizontal-pass input (rw x rh)
     uint8_t* tmp;            // w*rh*c    horizontal-pass output (nullptr: stage skipped)
+    int64_t tmp_stride;      // bytes between rows of tmp (padded to 16 inside the arena)
     const uint8_t* vin; int64_t vin_stride;     // vertical-pass input (w x rh)
     uint8_t* vout;           // w*h*c     vertical-pass output (nullptr: stage skipped)
+    int64_t vout_stride;     // bytes between rows of vout (padded to 16 inside the arena)
     const uint8_t* pix;      // w*h*c     final pixels (aliases src/conv/red/tmp/vout)
     int64_t pix_stride;      // bytes between rows of pix
     const int32_t* hb; const int32_t* hk; int32_t hks;   // horizontal bounds (xmin,n)*w, coeffs [k][w] (transposed), ksize
