@@ -161,11 +161,13 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
                         if (q2 + 2 < F && hash3(S + q2, hb) == hv) { cands[nc++] = q2; break; }
                     }
                 }
-                for (int w = 0; w < ways && nc < ways; w++) {
+                /* in a noisy stretch (literal EMA high) only the newest entry of each table is verified when noisy_ways1 is set */
+                const int nw1 = (noisy && P->noisy_ways1) ? 1 : ways, nw2 = (noisy && P->noisy_ways1) ? 1 : ways2;
+                for (int w = 0; w < nw1 && nc < ways; w++) {
                     uint16_t cnd = T[h + w]; if (cnd == 0) continue;
                     cands[nc++] = base + cnd;
                 }
-                if (nb2 && q + nb2 <= F) { uint32_t h2 = hashN(S + q, nb2, hb2) * ways2; for (int w = 0; w < ways2; w++) { uint16_t cnd = T2[h2 + w]; if (cnd != 0) cands[nc++] = base + cnd; } }
+                if (nb2 && q + nb2 <= F) { uint32_t h2 = hashN(S + q, nb2, hb2) * ways2; for (int w = 0; w < nw2; w++) { uint16_t cnd = T2[h2 + w]; if (cnd != 0) cands[nc++] = base + cnd; } }
                 for (int w = 0; w < nc; w++) {
                     int64_t cp = cands[w];
                     if (cp >= q || q - cp > MAXD) continue;

@@ -38,6 +38,7 @@ constexpr int kLaneCap = 64;          // exact compare length of a hash candidat
 constexpr int kLazyMax = 16;
 constexpr int kCostMaxLen = 8;
 constexpr int kCostWarm = 64;
+constexpr int kNoisy = 160;            // literal EMA (8 x literals per window) at which only the newest way of each table is verified
 constexpr unsigned kFull = 0xffffffffu;
 
 struct __align__(16) WarpMem {
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     // ---- main loop.  Register window: three 128-byte chunks at A0, A0+128, A0+256 (A0 multiple of 128).
     int p = s;
     uint32_t ntok = 0;
+    int score = 0;                                                               // EMA of literal tokens per window, x8
     int A0 = ((p - 4) >> 7) << 7;                                                // may be -128: the pad in front of the stream is addressable
     uint32_t w0r = __ldg(S32 + (A0 >> 2) + lane), w1r = __ldg(S32 + (A0 >> 2) + 32 + lane), w2r = __ldg(S32 + (A0 >> 2) + 64 + lane);
     while (p < e) {
@@ -300,13 +302,14 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 // four candidates in lock-step: 16 bytes per round trip, all loads of a round issued together
                 const int hcap = min(kLaneCap, limit);
                 const bool ok6 = q + kH2Bytes <= F;
+                const bool noisy = score >= kNoisy;                               // literal-dense stretch: older ways rarely pay for their loads
                 int cpos[4], clen[4]; bool live[4];
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
                     const uint32_t cnd = (w == 0) ? (b3 >> 16) : (w == 1) ? (b3 & 0xFFFFu) : (w == 2) ? (b6 >> 16) : (b6 & 0xFFFFu);
                     const int cp = base + (int)cnd;
                     const int d = q - cp;
-                    live[w] = cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist;
+                    live[w] = cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist && !(noisy && (w & 1));
                     cpos[w] = live[w] ? cp : q;
                     clen[w] = 0;
                 }
@@ -433,6 +436,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             }
         }
         ntok += __popc(sel);
+        score = score - (score >> 3) + __popc(__ballot_sync(kFull, ((sel >> lane) & 1u) && bl == 0));
         int next = ql + (Ll ? Ll : 1);
         // ---- a maximal distance-1 run goes on: measure it 1 KiB per round trip, emit the full 258-tokens it holds
         if (Ll == kMaxMatch && dl == 1 && e - next >= kMaxMatch) {
