@@ -24,7 +24,7 @@ namespace vcp {
 
 namespace {
 
-constexpr int kBuildThreads = 320;     // >= 316 symbols
+constexpr int kBuildThreads = 160;     // 12 CTAs per SM: every block of a 64-page batch is resident at once
 constexpr int kEmitThreads = 256;
 
 __device__ __forceinline__ int len_sym(int len) {      // 3..258 -> 0..28
@@ -139,14 +139,58 @@ __constant__ uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ build
+namespace {
+
+// two-queue Huffman merge over m sorted leaves (one thread): fills parent[0 .. 2m-2); queue heads live in registers
+__device__ void merge_serial(const uint32_t* freq, const uint16_t* order, int m, uint32_t* w, uint16_t* parent) {
+    for (int i = 0; i < m; i++) w[i] = freq[order[i]];
+    constexpr uint32_t INF = 0xFFFFFFFFu;
+    int li = 0, ii = m, nn = m;
+    uint32_t wl = w[0], wi = INF;
+    while (nn < 2 * m - 1) {
+        int p0, p1; uint32_t v0, v1;
+        if (li < m && wl <= wi) { p0 = li++; v0 = wl; wl = li < m ? w[li] : INF; } else { p0 = ii++; v0 = wi; wi = ii < nn ? w[ii] : INF; }
+        if (li < m && wl <= wi) { p1 = li++; v1 = wl; wl = li < m ? w[li] : INF; } else { p1 = ii++; v1 = wi; wi = ii < nn ? w[ii] : INF; }
+        const uint32_t sum = v0 + v1;
+        w[nn] = sum; parent[p0] = (uint16_t)nn; parent[p1] = (uint16_t)nn;
+        if (ii == nn) wi = sum;                       // the internal queue was empty: the new node is its head
+        nn++;
+    }
+    parent[2 * m - 2] = (uint16_t)(2 * m - 2);        // root points at itself
+}
+
+// clamp the per-length leaf counts to maxbits (Kraft repair), as dm_huff_lengths does (one thread)
+__device__ void kraft_repair(int* cnt, int maxbits) {
+    long long K = 0;
+    for (int l = 1; l <= maxbits; l++) K += (long long)cnt[l] << (maxbits - l);
+    long long excess = K - (1ll << maxbits);
+    while (excess > 0) {
+        int l = maxbits - 1;
+        while (cnt[l] == 0) l--;
+        cnt[l]--; cnt[l + 1]++;
+        excess -= 1ll << (maxbits - l - 1);
+    }
+    while (excess < 0) {
+        bool done = false;
+        for (int l = maxbits; l >= 2; l--) {
+            const long long cost = 1ll << (maxbits - l);
+            if (cnt[l] > 0 && cost <= -excess) { cnt[l]--; cnt[l - 1]++; excess += cost; done = true; break; }
+        }
+        if (!done) break;
+    }
+}
+
+}  // namespace
+
 __global__ void __launch_bounds__(kBuildThreads) k_huff_build(BatchD B) {
     __shared__ uint32_t freq[kCodeStride];          // [0,286) lit/len, [286,316) dist (patched copies)
     __shared__ uint16_t order_ll[kNumLL], order_d[kNumD];
     __shared__ uint8_t lens[kCodeStride];
     __shared__ uint16_t codes[kCodeStride];
-    __shared__ uint32_t w_ll[2 * kNumLL]; __shared__ uint16_t par_ll[2 * kNumLL];
-    __shared__ uint32_t w_d[2 * kNumD];   __shared__ uint16_t par_d[2 * kNumD];
+    __shared__ uint32_t w_ll[2 * kNumLL]; __shared__ uint16_t par_ll[2 * kNumLL]; __shared__ uint16_t dep_ll[2 * kNumLL];
+    __shared__ uint32_t w_d[2 * kNumD];   __shared__ uint16_t par_d[2 * kNumD];   __shared__ uint16_t dep_d[2 * kNumD];
     __shared__ int m_ll, m_d;
+    __shared__ int cnt_ll[16], cnt_d[16];
     __shared__ uint32_t cost[kCodeStride];          // bits per occurrence of each symbol (code + extra)
     __shared__ unsigned long long sub_bits[kBlockBytes / kSubBytes];
     __shared__ uint32_t hdr_bits_s;
@@ -156,68 +200,112 @@ __global__ void __launch_bounds__(kBuildThreads) k_huff_build(BatchD B) {
     const BlockD blk = B.blocks[b];
 
     // ---- block histogram
-    if (tid < kHistSize) {
+    for (int t = tid; t < kCodeStride; t += kBuildThreads) {
         uint32_t s = 0;
-        for (int j = 0; j < blk.nsub; j++) s += B.sub_hist[(size_t)(blk.sub0 + j) * kHistSize + tid];
-        if (tid == 256) s += 1;                      // EOB
-        freq[tid] = s; lens[tid] = 0;
-    } else if (tid < kCodeStride) { freq[tid] = 0; lens[tid] = 0; codes[tid] = 0; cost[tid] = 0; }
+        if (t < kHistSize) {
+            for (int j = 0; j < blk.nsub; j++) s += B.sub_hist[(size_t)(blk.sub0 + j) * kHistSize + t];
+            if (t == 256) s += 1;                    // EOB
+        }
+        freq[t] = s; lens[t] = 0; codes[t] = 0; cost[t] = 0;
+    }
+    if (tid < 16) { cnt_ll[tid] = 0; cnt_d[tid] = 0; }
     __syncthreads();
-    // ---- at least two used symbols per alphabet (dm_huff_lengths)
+    // ---- at least two used symbols per alphabet (dm_huff_lengths); symbol counts
     if (tid == 0) {
         int used = 0; for (int i = 0; i < kNumLL; i++) used += freq[i] != 0;   // EOB makes used >= 1
-        if (used == 1) { if (freq[0]) freq[1] = 1; else freq[0] = 1; }
+        if (used == 1) { if (freq[0]) freq[1] = 1; else freq[0] = 1; used = 2; }
+        m_ll = used;
     } else if (tid == 32) {
         uint32_t* f = freq + kNumLL;
         int used = 0; for (int i = 0; i < kNumD; i++) used += f[i] != 0;
-        if (used == 0) { f[0] = 1; f[1] = 1; }
-        else if (used == 1) { if (f[0]) f[1] = 1; else f[0] = 1; }
+        if (used == 0) { f[0] = 1; f[1] = 1; used = 2; }
+        else if (used == 1) { if (f[0]) f[1] = 1; else f[0] = 1; used = 2; }
+        m_d = used;
     }
     __syncthreads();
     // ---- rank sort by (freq, symbol) among used symbols
-    if (tid < kNumLL) {
-        const uint32_t f = freq[tid];
+    for (int t = tid; t < kHistSize; t += kBuildThreads) {
+        const bool isd = t >= kNumLL;
+        const int lo = isd ? kNumLL : 0, hi = isd ? kHistSize : kNumLL;
+        const uint32_t f = freq[t];
         if (f) {
             int r = 0;
-            for (int j = 0; j < kNumLL; j++) { const uint32_t g = freq[j]; r += (g != 0) && (g < f || (g == f && j < tid)); }
-            order_ll[r] = (uint16_t)tid;
-        }
-    } else if (tid < kHistSize) {
-        const int s = tid - kNumLL;
-        const uint32_t* fq = freq + kNumLL;
-        const uint32_t f = fq[s];
-        if (f) {
-            int r = 0;
-            for (int j = 0; j < kNumD; j++) { const uint32_t g = fq[j]; r += (g != 0) && (g < f || (g == f && j < s)); }
-            order_d[r] = (uint16_t)s;
+            for (int j = lo; j < hi; j++) { const uint32_t g = freq[j]; r += (g != 0) && (g < f || (g == f && j < t)); }
+            if (isd) order_d[r] = (uint16_t)(t - kNumLL); else order_ll[r] = (uint16_t)t;
         }
     }
-    if (tid == 0) { int m = 0; for (int i = 0; i < kNumLL; i++) m += freq[i] != 0; m_ll = m; }
-    if (tid == 32) { int m = 0; for (int i = 0; i < kNumD; i++) m += freq[kNumLL + i] != 0; m_d = m; }
     __syncthreads();
-    // ---- the two trees, one thread each (different warps)
-    if (tid == 0) tree_serial(freq, order_ll, m_ll, 15, lens, w_ll, par_ll);
-    else if (tid == 32) tree_serial(freq + kNumLL, order_d, m_d, 15, lens + kNumLL, w_d, par_d);
+    // ---- the two merges, one thread each (different warps)
+    if (tid == 0) merge_serial(freq, order_ll, m_ll, w_ll, par_ll);
+    else if (tid == 32) merge_serial(freq + kNumLL, order_d, m_d, w_d, par_d);
+    __syncthreads();
+    // ---- leaf depths by pointer jumping (9 rounds cover depth < 512), both trees at once
+    {
+        const int n1 = 2 * m_ll - 1, n2 = 2 * m_d - 1, nt = n1 + n2;
+        for (int t = tid; t < nt; t += kBuildThreads) {
+            if (t < n1) dep_ll[t] = (t == n1 - 1) ? 0 : 1; else dep_d[t - n1] = (t - n1 == n2 - 1) ? 0 : 1;
+        }
+        __syncthreads();
+        constexpr int kPer = (2 * kNumLL + 2 * kNumD + kBuildThreads - 1) / kBuildThreads;
+        for (int round = 0; round < 9; round++) {
+            uint16_t nd[kPer], np[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                const int t = tid + k * kBuildThreads;
+                if (t < nt) {
+                    uint16_t* dep = t < n1 ? dep_ll : dep_d; uint16_t* par = t < n1 ? par_ll : par_d;
+                    const int i = t < n1 ? t : t - n1;
+                    const int p = par[i];
+                    nd[k] = (uint16_t)(dep[i] + dep[p]); np[k] = par[p];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                const int t = tid + k * kBuildThreads;
+                if (t < nt) {
+                    uint16_t* dep = t < n1 ? dep_ll : dep_d; uint16_t* par = t < n1 ? par_ll : par_d;
+                    const int i = t < n1 ? t : t - n1;
+                    dep[i] = nd[k]; par[i] = np[k];
+                }
+            }
+            __syncthreads();
+        }
+        for (int t = tid; t < m_ll + m_d; t += kBuildThreads) {
+            if (t < m_ll) atomicAdd(&cnt_ll[min((int)dep_ll[t], 15)], 1);
+            else atomicAdd(&cnt_d[min((int)dep_d[t - m_ll], 15)], 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) kraft_repair(cnt_ll, 15); else if (tid == 32) kraft_repair(cnt_d, 15);
+    __syncthreads();
+    // ---- lengths: the most frequent symbols get the shortest codes (sorted index j from the top)
+    for (int t = tid; t < m_ll + m_d; t += kBuildThreads) {
+        const bool isd = t >= m_ll;
+        const int m = isd ? m_d : m_ll, j = isd ? t - m_ll : t;
+        const int* cnt = isd ? cnt_d : cnt_ll;
+        const int top = m - 1 - j;
+        int l = 1, acc = cnt[1];
+        while (acc <= top && l < 15) { l++; acc += cnt[l]; }
+        if (isd) lens[kNumLL + order_d[j]] = (uint8_t)l; else lens[order_ll[j]] = (uint8_t)l;
+    }
     __syncthreads();
     // ---- canonical codes (parallel): code = first code of that length + rank among equal lengths
-    if (tid < kHistSize) {
-        const bool isd = tid >= kNumLL;
+    for (int t = tid; t < kHistSize; t += kBuildThreads) {
+        const bool isd = t >= kNumLL;
         const int lo = isd ? kNumLL : 0, hi = isd ? kHistSize : kNumLL;
-        const int l = lens[tid];
+        const int* cnt = isd ? cnt_d : cnt_ll;
+        const int l = lens[t];
         if (l) {
-            int cnt[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) cnt[k] = 0;
             int rank = 0;
-            for (int j = lo; j < hi; j++) { const int lj = lens[j]; cnt[lj]++; rank += (lj == l) && (j < tid); }
-            cnt[0] = 0;
+            for (int j = lo; j < t; j++) rank += lens[j] == l;
             uint32_t c = 0;
-            for (int k = 1; k <= l; k++) c = (c + cnt[k - 1]) << 1;
-            codes[tid] = (uint16_t)bitrev(c + rank, l);
-        } else codes[tid] = 0;
+            for (int k = 1; k <= l; k++) c = (c + (k > 1 ? cnt[k - 1] : 0)) << 1;
+            codes[t] = (uint16_t)bitrev(c + rank, l);
+        } else codes[t] = 0;
         int extra;
-        if (!isd) extra = tid >= 257 ? len_extra(tid - 257) : 0; else extra = dist_extra(tid - kNumLL);
-        cost[tid] = (uint32_t)l + (uint32_t)extra;
+        if (!isd) extra = t >= 257 ? len_extra(t - 257) : 0; else extra = dist_extra(t - kNumLL);
+        cost[t] = (uint32_t)l + (uint32_t)extra;
     }
     __syncthreads();
     // ---- header (serial) — and, in other warps, the exact bit size of every sub-chunk
@@ -254,8 +342,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_huff_build(BatchD B) {
         }
         bw.flush();
         hdr_bits_s = bw.total;
-    } else if (tid >= 64) {
-        const int warp = (tid - 64) >> 5, lane = tid & 31, nw = (kBuildThreads - 64) / 32;
+    } else if (tid >= 32) {
+        const int warp = (tid - 32) >> 5, lane = tid & 31, nw = (kBuildThreads - 32) / 32;
         for (int j = warp; j < blk.nsub; j += nw) {
             const uint32_t* h = B.sub_hist + (size_t)(blk.sub0 + j) * kHistSize;
             unsigned long long s = 0;
@@ -267,9 +355,9 @@ __global__ void __launch_bounds__(kBuildThreads) k_huff_build(BatchD B) {
     }
     __syncthreads();
     // ---- publish codes, offsets, sizes
-    if (tid < kCodeStride) {
-        B.blk_code[(size_t)b * kCodeStride + tid] = codes[tid];
-        B.blk_clen[(size_t)b * kCodeStride + tid] = lens[tid];
+    for (int t = tid; t < kCodeStride; t += kBuildThreads) {
+        B.blk_code[(size_t)b * kCodeStride + t] = codes[t];
+        B.blk_clen[(size_t)b * kCodeStride + t] = lens[t];
     }
     if (tid == 0) {
         unsigned long long off = hdr_bits_s;
