@@ -180,3 +180,39 @@ def test_full_size_properties_c2(V, synth):
         assert again.png == a.png                                          # idempotent on its own output
     single = [V.prepare_page(p).png for p in pages]
     assert single == [r.png for r in r1]                                   # batch == one at a time
+
+
+def test_many_pipelined_groups_and_lane_reuse(V, synth, monkeypatch):
+    """Host inputs are cut into groups that ping-pong over four lanes (streams + arenas); force many small groups so every
+    lane is reused several times, with pages of different sizes, and check every page."""
+    from vision_compression_project_b200.api import PagePrep
+    monkeypatch.setenv("VCP_PIPE_BYTES", str(1 << 20))          # ~1 page per group
+    eng = PagePrep(0)
+    try:
+        pages = [synth.make_page(i, size=(700 + 37 * (i % 5), 900 + 53 * (i % 3)), photo=(i % 4 == 0)) for i in range(19)]
+        res = eng.prepare_pages(pages)
+        for im, r in zip(pages, res):
+            assert r.error is None
+            U.check_png_against(r.png, im)
+            U.check_b64(r.png, r.b64)
+        again = eng.prepare_pages(pages)                        # arenas and pinned buffers are reused
+        assert [r.png for r in again] == [r.png for r in res]
+    finally:
+        eng.close()
+
+
+def test_many_device_groups(V, synth, monkeypatch):
+    """Device-resident inputs larger than one launch set (VCP_GROUP_BYTES) run as several sets on one lane."""
+    import torch
+    from vision_compression_project_b200.api import PagePrep
+    monkeypatch.setenv("VCP_GROUP_BYTES", str(1 << 20))
+    eng = PagePrep(0)
+    try:
+        pages = [synth.make_page(i, size=(640, 480 + 16 * i)) for i in range(7)]
+        dev = [torch.from_numpy(np.array(p)).cuda() for p in pages]
+        res = eng.prepare_pages(dev, max_side=320)
+        for im, r in zip(pages, res):
+            _, _, exp = PP.prepare_page_cpu(im, max_side=320)
+            U.check_png_against(r.png, exp)
+    finally:
+        eng.close()
