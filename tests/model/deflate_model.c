@@ -153,7 +153,10 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
             if (q + 2 < F && !(bc && P->capped_wins)) {   /* a capped run already outranks everything */
                 uint32_t hv = hash3(S + q, hb);
                 uint32_t h = hv * ways;
-                int hcap = lcap < limit ? lcap : limit;
+                /* lane_cap_win: a lane only needs an exact length up to the end of its window (later lanes are cut to 16 bytes);
+                   whatever is longer is 'capped' and, if it becomes the window's last token, extended cooperatively */
+                const int lcap_i = P->lane_cap_win ? ((i < 16 ? 32 : 16) < lcap ? (i < 16 ? 32 : 16) : lcap) : lcap;
+                int hcap = lcap_i < limit ? lcap_i : limit;
                 int64_t cands[8]; int nc = 0;
                 if (P->inwin) {
                     for (int j = i - 1; j >= 0; j--) {

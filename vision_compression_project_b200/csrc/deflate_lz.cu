@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         const unsigned long long mb = (unsigned long long)__ballot_sync(kFull, eba) | ((unsigned long long)__ballot_sync(kFull, ebb) << 32);
 
         const int limit = min(kMaxMatch, e - q);                                 // <= 0 for lanes past the sub-chunk
-        int bl = 0, bd = 0, be = 0; bool bcap = false;
+        int bl = 0, bd = 0; bool bcap = false;
+        // candidates are ranked by one packed key: (capped ? 127 : length) | 32768 - distance | length  — longer first, then nearer
+        uint32_t best = 0;
         const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
         const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
         const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
@@ -287,17 +289,16 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 const int r = inv ? __ffsll((long long)inv) - 1 : 64;
                 const int l = min(r, runcap);
                 const bool c = (l == runcap) && (runcap < limit);
-                const int eff = c ? 1000 : l;
-                if (l >= 3 && eff > be) { be = eff; bl = l; bd = 1; bcap = c; }
+                if (l >= 3) best = ((c ? 127u : (uint32_t)l) << 24) | (32767u << 8) | (uint32_t)l;
             }
             if (bpp > 1) {
                 const unsigned long long inv = ~(mb >> lane);
                 const int r = inv ? __ffsll((long long)inv) - 1 : 64;
                 const int l = min(r, runcap);
                 const bool c = (l == runcap) && (runcap < limit);
-                const int eff = c ? 1000 : l;
-                if (l >= 3 && eff > be) { be = eff; bl = l; bd = bpp; bcap = c; }
+                if (l >= 3) best = max(best, ((c ? 127u : (uint32_t)l) << 24) | ((uint32_t)(32768 - bpp) << 8) | (uint32_t)l);
             }
+            bcap = (best >> 24) == 127u;
             if (!bcap) {                                                          // a capped run outranks every hash candidate
                 // four candidates in lock-step: 16 bytes per round trip, all loads of a round issued together
                 const int hcap = min(kLaneCap, limit);
@@ -373,10 +374,12 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 for (int w = 0; w < 4; w++) {
                     const int l = clen[w], d = q - cpos[w];
                     const bool c = (l == hcap) && (hcap < limit);
-                    const int eff = c ? 1000 : l;
-                    if (l >= 3 && (eff > be || (eff == be && d < bd))) { be = eff; bl = l; bd = d; bcap = c; }
+                    if (l >= 3) best = max(best, ((c ? 127u : (uint32_t)l) << 24) | ((uint32_t)(32768 - d) << 8) | (uint32_t)l);
                 }
             }
+            bl = (int)(best & 0xFFu);
+            bd = best ? 32768 - (int)((best >> 8) & 0x7FFFu) : 0;
+            bcap = (best >> 24) == 127u;
             // price short matches against literals with the histogram as of the window start
             if (bl >= 3 && bl <= kCostMaxLen && ntok >= kCostWarm) {
                 const int lgN = ilog2x4(ntok + 1);
