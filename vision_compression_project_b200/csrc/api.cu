@@ -526,16 +526,29 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
     // ---- split into launch sets.  Device-resident sources: as large as group_bytes allows (fewer, fuller launches).
     //      Host sources: groups of ~pipe_bytes so that the H2D copy of group g+1 (other lane, other stream) overlaps the
     //      kernels of group g; results are collected in order.
+    //      The first and last host groups are small (1/4, 1/2 of pipe_bytes): the first copy and the last launch set are the
+    //      only parts of the pipeline nothing overlaps with.
     const size_t limit = opts->src_device ? h->group_bytes : std::min(h->group_bytes, h->pipe_bytes);
     std::vector<std::vector<int>> groups;
     {
-        size_t bytes = 0;
+        auto cost = [&](int i) { return opts->src_device ? (size_t)all[i].filt_len + (size_t)all[i].sw * all[i].sh * all[i].sc / 4
+                                                         : (size_t)all[i].sw * all[i].sh * all[i].sc; };
+        size_t rem = 0;
+        for (int i = 0; i < n; i++) if (!all[i].status) rem += cost(i);
+        size_t bytes = 0, lim = limit;
         for (int i = 0; i < n; i++) {
             if (all[i].status) continue;
-            const size_t fb = opts->src_device ? (size_t)all[i].filt_len + (size_t)all[i].sw * all[i].sh * all[i].sc / 4
-                                               : (size_t)all[i].sw * all[i].sh * all[i].sc;
-            if (groups.empty() || (bytes + fb > limit && !groups.back().empty())) { groups.emplace_back(); bytes = 0; }
-            groups.back().push_back(i); bytes += fb;
+            const size_t fb = cost(i);
+            if (groups.empty() || (bytes + fb > lim && !groups.back().empty())) {
+                groups.emplace_back(); bytes = 0;
+                lim = limit;
+                if (!opts->src_device) {
+                    const size_t g = groups.size() - 1;
+                    if (g == 0) lim = limit / 4; else if (g == 1) lim = limit / 2;
+                    if (rem <= limit - limit / 4) lim = std::min(lim, std::max(limit / 4, rem / 2));   // ramp down at the tail
+                }
+            }
+            groups.back().push_back(i); bytes += fb; rem -= fb;
         }
     }
     const int G = (int)groups.size();
