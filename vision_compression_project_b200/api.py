@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import threading
 from dataclasses import dataclass, field
 from typing import Any, List, Optional, Sequence, Tuple
@@ -165,7 +166,12 @@ class PagePrep:
         self._out_png = None
         self._out_b64 = None
         self.max_batch_bytes = 1 << 30
-        self.copy_threads = 4
+        # host threads that fill the returned bytes objects; share the box's cores between the ranks torchrun started
+        try:
+            ncpu = len(os.sched_getaffinity(0))
+        except AttributeError:  # pragma: no cover
+            ncpu = os.cpu_count() or 4
+        self.copy_threads = max(2, min(8, ncpu // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
         self.launches_total = 0
 
     def close(self):
