@@ -216,3 +216,17 @@ def test_many_device_groups(V, synth, monkeypatch):
             U.check_png_against(r.png, exp)
     finally:
         eng.close()
+
+
+def test_gray_sources_to_rgb_with_resize(V, synth):
+    """L / LA pages asked for as RGB stay single-channel through reduce + resample and are replicated by the PNG filter's
+    loader; the result must still be what Pillow gets from convert('RGB') first."""
+    rng = np.random.default_rng(31)
+    g = synth.make_page(7, "a4", 150, "L", True)
+    la = Image.merge("LA", (g, Image.fromarray(rng.integers(0, 256, (g.height, g.width), dtype=np.uint8), "L")))
+    for src in (g, la):
+        for kw in ({}, {"max_side": 640}, {"max_side": 200, "reducing_gap": 2.0}, {"size": (333, 517), "resample": V.BILINEAR}):
+            r = V.prepare_page(src, mode="RGB", **kw)
+            _, _, exp = PP.prepare_page_cpu(src, mode="RGB", **{k: (Image.Resampling.BILINEAR if k == "resample" else v) for k, v in kw.items()})
+            assert r.mode == "RGB" and r.size == exp.size
+            U.check_png_against(r.png, exp, size_tol=1.06)

@@ -115,7 +115,7 @@ constexpr size_t kNone = (size_t)-1;
 struct PagePlan {
     int status = 0;
     const uint8_t* src = nullptr; int64_t src_stride = 0;
-    int sw = 0, sh = 0, sc = 0, c = 0, fx = 1, fy = 1, rw = 0, rh = 0, w = 0, h = 0;
+    int sw = 0, sh = 0, sc = 0, c = 0, pc = 0, fx = 1, fy = 1, rw = 0, rh = 0, w = 0, h = 0;
     bool need_conv = false, need_red = false, need_h = false, need_v = false;
     float box[4] = {0, 0, 0, 0};
     size_t o_raw = kNone, o_conv = kNone, o_red = kNone, o_tmp = kNone, o_vout = kNone, o_filt = kNone;
@@ -145,7 +145,8 @@ int plan_geometry(const vcp_page_desc& d, const vcp_opts& o, PagePlan& P) {
     if (P.src_stride < (int64_t)d.width * d.channels) return fail(VCP_EINVAL, "row_stride %lld smaller than a row", (long long)d.row_stride);
     P.c = o.out_channels ? o.out_channels : d.channels;
     if (P.c != 1 && P.c != 3 && P.c != d.channels) return fail(VCP_EINVAL, "unsupported output channel count %d", P.c);
-    P.need_conv = P.c != P.sc;
+    P.pc = (P.sc <= 2 && P.c == 3) ? 1 : P.c;        // gray sources stay single-channel until the PNG filter replicates them
+    P.need_conv = P.pc != P.sc;
     P.fx = d.reduce_x > 1 ? d.reduce_x : 1; P.fy = d.reduce_y > 1 ? d.reduce_y : 1;
     P.need_red = P.fx > 1 || P.fy > 1;
     P.rw = (P.sw + P.fx - 1) / P.fx; P.rh = (P.sh + P.fy - 1) / P.fy;
@@ -204,10 +205,10 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     for (auto& P : plans) {
         if (!stream_in) {
             if (!o.src_device) P.o_raw = bump.take((size_t)P.sw * P.sc * P.sh + 16);
-            if (P.need_conv) P.o_conv = bump.take((size_t)P.sw * P.sh * P.c + 16);
-            if (P.need_red) P.o_red = bump.take((size_t)P.rw * P.rh * P.c + 16);
-            if (P.need_h) P.o_tmp = bump.take(align_up((size_t)P.w * P.c, 16) * P.rh + 16);      // rows padded to 16 B: aligned word loads in the V pass
-            if (P.need_v) P.o_vout = bump.take(align_up((size_t)P.w * P.c, 16) * P.h + 16);
+            if (P.need_conv) P.o_conv = bump.take((size_t)P.sw * P.sh * P.pc + 16);
+            if (P.need_red) P.o_red = bump.take((size_t)P.rw * P.rh * P.pc + 16);
+            if (P.need_h) P.o_tmp = bump.take(align_up((size_t)P.w * P.pc, 16) * P.rh + 16);      // rows padded to 16 B: aligned word loads in the V pass
+            if (P.need_v) P.o_vout = bump.take(align_up((size_t)P.w * P.pc, 16) * P.h + 16);
             if (P.need_h) {
                 P.ch = get_coeffs(h, P.rw, P.w, o.resample, P.box[0], P.box[2]);
                 if (!P.ch) return fail(VCP_EINVAL, "bad resample parameters");
@@ -281,24 +282,24 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     for (int i = 0; i < n; i++) {
         PagePlan& P = plans[i];
         PageD& D = hp[i];
-        D.sw = P.sw; D.sh = P.sh; D.sc = P.sc; D.c = P.c; D.fx = P.fx; D.fy = P.fy; D.rw = P.rw; D.rh = P.rh; D.w = P.w; D.h = P.h;
+        D.sw = P.sw; D.sh = P.sh; D.sc = P.sc; D.c = P.c; D.pc = P.pc; D.fx = P.fx; D.fy = P.fy; D.rw = P.rw; D.rh = P.rh; D.w = P.w; D.h = P.h;
         D.color_type = color_type_of(P.c);
         const uint8_t* cur = nullptr; int64_t cur_stride = 0;
         if (!stream_in) {
             if (o.src_device) { cur = P.src; cur_stride = P.src_stride; }
             else { cur = A + P.o_raw; cur_stride = (int64_t)P.sw * P.sc; }
             D.src = cur; D.src_stride = cur_stride;
-            if (P.need_conv) { D.conv = A + P.o_conv; cur = D.conv; cur_stride = (int64_t)P.sw * P.c; any_conv = true; }
+            if (P.need_conv) { D.conv = A + P.o_conv; cur = D.conv; cur_stride = (int64_t)P.sw * P.pc; any_conv = true; }
             D.rdin = cur; D.rdin_stride = cur_stride;
-            if (P.need_red) { D.red = A + P.o_red; cur = D.red; cur_stride = (int64_t)P.rw * P.c; any_red = true; }
+            if (P.need_red) { D.red = A + P.o_red; cur = D.red; cur_stride = (int64_t)P.rw * P.pc; any_red = true; }
             D.hin = cur; D.hin_stride = cur_stride;
             if (P.need_h) {
-                D.tmp = A + P.o_tmp; D.tmp_stride = (int64_t)align_up((size_t)P.w * P.c, 16); cur = D.tmp; cur_stride = D.tmp_stride; any_h = true;
+                D.tmp = A + P.o_tmp; D.tmp_stride = (int64_t)align_up((size_t)P.w * P.pc, 16); cur = D.tmp; cur_stride = D.tmp_stride; any_h = true;
                 D.hb = d_coeff + coeff_at[P.ch].first; D.hk = d_coeff + coeff_at[P.ch].second; D.hks = P.ch->ksize;
             }
             D.vin = cur; D.vin_stride = cur_stride;
             if (P.need_v) {
-                D.vout = A + P.o_vout; D.vout_stride = (int64_t)align_up((size_t)P.w * P.c, 16); cur = D.vout; cur_stride = D.vout_stride; any_v = true;
+                D.vout = A + P.o_vout; D.vout_stride = (int64_t)align_up((size_t)P.w * P.pc, 16); cur = D.vout; cur_stride = D.vout_stride; any_v = true;
                 D.vb = d_coeff + coeff_at[P.cv].first; D.vk = d_coeff + coeff_at[P.cv].second; D.vks = P.cv->ksize;
             }
             D.pix = cur; D.pix_stride = cur_stride;
@@ -666,7 +667,7 @@ int vcp_convert(vcp_handle* h, const void* d_src, int width, int height, int src
     Lane& L = h->lane[0]; (void)L;
     PageD D = {};
     D.src = (const uint8_t*)d_src; D.src_stride = row_stride ? row_stride : (int64_t)width * src_channels;
-    D.sw = width; D.sh = height; D.sc = src_channels; D.c = dst_channels; D.conv = (uint8_t*)d_dst;
+    D.sw = width; D.sh = height; D.sc = src_channels; D.c = dst_channels; D.pc = dst_channels; D.conv = (uint8_t*)d_dst;
     const PageD* dp; int rc = stage_page(L, D, 0, nullptr, &dp); if (rc) return rc;
     launch_convert(dp, 1, height, width, L.stream);
     CU(cudaGetLastError());
@@ -685,7 +686,7 @@ int vcp_reduce(vcp_handle* h, const void* d_src, int width, int height, int chan
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     PageD D = {};
-    D.sw = width; D.sh = height; D.sc = channels; D.c = channels; D.fx = fx; D.fy = fy;
+    D.sw = width; D.sh = height; D.sc = channels; D.c = channels; D.pc = channels; D.fx = fx; D.fy = fy;
     D.rw = (width + fx - 1) / fx; D.rh = (height + fy - 1) / fy;
     D.rdin = (const uint8_t*)d_src; D.rdin_stride = (int64_t)width * channels; D.red = (uint8_t*)d_dst;
     const PageD* dp; int rc = stage_page(L, D, 0, nullptr, &dp); if (rc) return rc;
@@ -724,7 +725,7 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
     CU(cudaMemcpyAsync(d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, L.stream));
     CU(cudaStreamSynchronize(L.stream));      // blob is pageable host memory
     PageD D = {};
-    D.c = channels; D.rw = width; D.rh = height; D.w = out_width; D.h = out_height;
+    D.c = channels; D.pc = channels; D.rw = width; D.rh = height; D.w = out_width; D.h = out_height;
     D.hin = (const uint8_t*)d_src; D.hin_stride = (int64_t)width * channels;
     const uint8_t* cur = D.hin; int64_t cur_stride = D.hin_stride;
     if (need_h) {
@@ -764,7 +765,7 @@ static int stream_plan(const void* d_stream, uint64_t len, int bpp, PagePlan& P)
     if (!d_stream || len == 0 || len >= ((uint64_t)1 << 31) - (1 << 20)) return fail(VCP_EINVAL, "bad stream length %llu", (unsigned long long)len);
     if (bpp < 1 || bpp > 4) return fail(VCP_EINVAL, "bpp must be 1..4");
     P = PagePlan();
-    P.src = (const uint8_t*)d_stream; P.c = bpp; P.w = 1; P.h = 1; P.filt_len = (int64_t)len;
+    P.src = (const uint8_t*)d_stream; P.c = bpp; P.pc = bpp; P.w = 1; P.h = 1; P.filt_len = (int64_t)len;
     P.nblk = (int)((P.filt_len + kBlockBytes - 1) / kBlockBytes);
     P.nsub = 0;
     for (int b = 0; b < P.nblk; b++) {

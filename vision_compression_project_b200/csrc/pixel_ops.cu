@@ -21,7 +21,7 @@ __global__ void k_convert(const PageD* __restrict__ pages) {
     if (!P.conv) return;
     const int y = blockIdx.y;
     if (y >= P.sh) return;
-    const int sc = P.sc, c = P.c;
+    const int sc = P.sc, c = P.pc;
     const uint8_t* __restrict__ srow = P.src + (int64_t)y * P.src_stride;
     uint8_t* __restrict__ drow = P.conv + (int64_t)y * P.sw * c;
     for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < P.sw; x += gridDim.x * blockDim.x) {
@@ -53,7 +53,7 @@ __global__ void k_reduce(const PageD* __restrict__ pages) {
     if (!P.red) return;
     const int oy = blockIdx.y;
     if (oy >= P.rh) return;
-    const int c = P.c, fx = P.fx, fy = P.fy;
+    const int c = P.pc, fx = P.fx, fy = P.fy;
     const int y0 = oy * fy, y1 = min(y0 + fy, P.sh);
     for (int ox = blockIdx.x * blockDim.x + threadIdx.x; ox < P.rw; ox += gridDim.x * blockDim.x) {
         const int x0 = ox * fx, x1 = min(x0 + fx, P.sw);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kHPix) k_resample_h(const PageD* __restrict__ 
     const PageD& P = pages[blockIdx.z];
     if (!P.tmp) return;
     if ((int)blockIdx.y * kHRows >= P.rh || (int)blockIdx.x * kHPix >= P.w) return;
-    if (P.c == 3) resample_h_tile<3>(P, sm); else resample_h_tile<1>(P, sm);
+    if (P.pc == 3) resample_h_tile<3>(P, sm); else resample_h_tile<1>(P, sm);
 }
 
 // Vertical pass: a thread owns 4 consecutive bytes of one output row (one aligned word per tap) when the rows are
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) k_resample_v(const PageD* __restrict__ pa
     if (!P.vout) return;
     const int yy = blockIdx.y;
     if (yy >= P.h) return;
-    const int wc = P.w * P.c;
+    const int wc = P.w * P.pc;
     const int ymin = __ldg(P.vb + 2 * yy), n = __ldg(P.vb + 2 * yy + 1);
     const bool aligned = ((((uintptr_t)P.vin) | (uintptr_t)P.vin_stride | ((uintptr_t)P.vout) | (uintptr_t)P.vout_stride) & 3) == 0;
     const int i4 = blockIdx.x * blockDim.x + threadIdx.x;       // word index in the row

@@ -63,6 +63,28 @@ __device__ __forceinline__ void stage_row(uint32_t* sm, const uint8_t* g, int nb
     }
 }
 
+// Gray -> RGB on the way in (Convert.c L/LA -> RGB is plain replication): `g` is a row of wpix gray bytes, the staged row is
+// the 3*wpix interleaved bytes Pillow would have produced, at shared byte kLead (alignment offset 0).
+__device__ __forceinline__ void stage_row_gray3(uint32_t* sm, const uint8_t* g, int wpix, int total_words, bool zero_row) {
+    constexpr int L = kLead / 4;
+    const int ngroups = (total_words - L + 2) / 3;          // 4 pixels -> 3 words
+    for (int j = threadIdx.x; j < L; j += kThreads) sm[j] = 0u;
+    for (int q = threadIdx.x; q < ngroups; q += kThreads) {
+        uint32_t a = 0, b = 0, c = 0, d = 0;
+        const int x = 4 * q;
+        if (!zero_row) {
+            if (x < wpix) a = __ldg(g + x);
+            if (x + 1 < wpix) b = __ldg(g + x + 1);
+            if (x + 2 < wpix) c = __ldg(g + x + 2);
+            if (x + 3 < wpix) d = __ldg(g + x + 3);
+        }
+        const int w = L + 3 * q;
+        if (w < total_words) sm[w] = a * 0x010101u | (b << 24);
+        if (w + 1 < total_words) sm[w + 1] = b * 0x0101u | (c * 0x0101u << 16);
+        if (w + 2 < total_words) sm[w + 2] = c | (d * 0x010101u << 8);
+    }
+}
+
 // The five words a thread needs for 16 row bytes starting at row byte i (multiple of 16): rs[j] = row bytes
 // [i + 4(j-1), i + 4j) for j = 0..4, i.e. rs[0] is the 4 bytes in front of the chunk.
 __device__ __forceinline__ void load_chunk(const uint32_t* sm, int o, int i, uint32_t rs[5]) {
@@ -88,6 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict
     if (y0 >= P.h) return;
     const int y1 = min(P.h, y0 + kRowsPerCta);
     const int bpp = P.c;
+    const bool gray3 = P.pc == 1 && P.c == 3;                 // single-channel pixels, RGB output: replicate while staging
     const int n = P.w * bpp;                                  // row bytes
     const int64_t L = (int64_t)n + 1;                         // output row bytes
     const int nchunks = (n + 15) >> 4;
@@ -97,14 +120,14 @@ __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict
     // previous row of the first row
     {
         const uint8_t* gprev = P.pix + (int64_t)(y0 - 1) * P.pix_stride;
-        stage_row(bufA, gprev, n, words, y0 == 0);
+        if (gray3) stage_row_gray3(bufA, gprev, P.w, words, y0 == 0); else stage_row(bufA, gprev, n, words, y0 == 0);
     }
     uint32_t* smp = bufA; uint32_t* smc = bufB;
     for (int y = y0; y < y1; y++) {
         const uint8_t* grow = P.pix + (int64_t)y * P.pix_stride;
-        const int oc = (int)((uintptr_t)grow & 3);
-        const int op = y == 0 ? 0 : (int)((uintptr_t)(grow - P.pix_stride) & 3);
-        stage_row(smc, grow, n, words, false);
+        const int oc = gray3 ? 0 : (int)((uintptr_t)grow & 3);
+        const int op = (y == 0 || gray3) ? 0 : (int)((uintptr_t)(grow - P.pix_stride) & 3);
+        if (gray3) stage_row_gray3(smc, grow, P.w, words, false); else stage_row(smc, grow, n, words, false);
         __syncthreads();
 
         // ---- is the row identical to the one above (blank paper)? then Up (or None for an all-zero row) with zero residuals

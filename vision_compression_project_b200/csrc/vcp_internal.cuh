@@ -25,6 +25,8 @@ struct PageD {
     int64_t src_stride;
     int32_t sw, sh, sc;      // source geometry
     int32_t c;               // output channels (1 or 3 [or 2/4 when kept])
+    int32_t pc;              // channels the pixel stages work in; pc = 1 with c = 3 means gray kept single-channel until the
+                             // PNG filter stages it (L/LA -> RGB replicates, so resampling one channel is exact and 3x cheaper)
     int32_t fx, fy;          // reduce factors (1 = none)
     int32_t rw, rh;          // geometry after convert+reduce
     int32_t w, h;            // final geometry
