@@ -1,0 +1,57 @@
+"""GPU: randomised parity over shapes / modes / options (hypothesis), whole path vs the Pillow composition."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+from PIL import Image
+
+from oracle import pillow_path as PP
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"L": 1, "LA": 2, "RGB": 3, "RGBA": 4}
+
+
+def _image(rng, w, h, mode, kind):
+    c = MODES[mode]
+    if kind == 0:
+        px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+    elif kind == 1:
+        px = np.full((h, w, c), int(rng.integers(0, 256)), np.uint8)
+    elif kind == 2:
+        px = (np.add.outer(np.arange(h) * 3, np.arange(w) * 5)[:, :, None] + np.arange(c) * 17).astype(np.uint8)
+    else:                                            # sparse "text": white with a few dark runs
+        px = np.full((h, w, c), 255, np.uint8)
+        for _ in range(max(1, h * w // 40)):
+            y, x, n = int(rng.integers(0, h)), int(rng.integers(0, w)), int(rng.integers(1, 6))
+            px[y, x:x + n] = rng.integers(0, 120)
+    return Image.fromarray(px[:, :, 0] if c == 1 else px, mode)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
+@given(w=st.integers(1, 300), h=st.integers(1, 200), mode=st.sampled_from(sorted(MODES)), kind=st.integers(0, 3),
+       out=st.sampled_from(["RGB", "L", None]), resize=st.integers(0, 3), flt=st.integers(1, 5), seed=st.integers(0, 2**31 - 1),
+       optimize=st.booleans())
+def test_whole_path_matches_pillow(w, h, mode, kind, out, resize, flt, seed, optimize):
+    import vision_compression_project_b200 as V
+    rng = np.random.default_rng(seed)
+    im = _image(rng, w, h, mode, kind)
+    kw = {}
+    if resize == 1:
+        kw = {"max_side": int(rng.integers(1, 260))}
+    elif resize == 2:
+        kw = {"max_side": int(rng.integers(1, 120)), "reducing_gap": float(rng.choice([1.0, 2.0, 3.0]))}
+    elif resize == 3:
+        kw = {"size": (int(rng.integers(1, 320)), int(rng.integers(1, 220)))}
+    keep_alpha = (out is None and mode in ("LA", "RGBA"))
+    target_mode = out or mode
+    will_resize = bool(kw) and PP.prepare_page_cpu(im.convert("L"), want_base64=False, **kw)[2].size != im.size
+    if keep_alpha and will_resize:
+        with pytest.raises(ValueError):
+            V.prepare_page(im, mode=out, resample=flt, **kw)
+        return
+    r = V.prepare_page(im, mode=out, resample=flt, optimize=optimize, **kw)
+    _, _, exp = PP.prepare_page_cpu(im, mode=target_mode, resample=flt, want_base64=False, **kw)
+    assert r.mode == target_mode and r.size == exp.size
+    U.check_png_against(r.png, exp, pillow_kw={"optimize": True} if optimize else None, size_tol=1.25)   # tiny images: container overhead dominates
+    U.check_b64(r.png, r.b64)
