@@ -102,6 +102,16 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
                       void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap,
                       vcp_page_result* results);
 
+/* Streaming form of vcp_prepare_batch for bindings that want to consume results while later pages are still in flight:
+ * vcp_batch_begin starts the same pipeline on a worker thread of the handle and returns at once; every vcp_batch_next blocks
+ * until the next run of pages [first_page, last_page] has its bytes in out_png / out_b64 and its results[] final (returns 1),
+ * returns 0 when the batch is finished, < 0 on error; vcp_batch_end joins the worker (always call it, from the thread that
+ * called begin).  Buffers and the pages/results arrays must stay alive until vcp_batch_end. */
+int vcp_batch_begin(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts,
+                    void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results);
+int vcp_batch_next(vcp_handle* h, int* first_page, int* last_page);
+int vcp_batch_end(vcp_handle* h);
+
 int vcp_get_stats(vcp_handle* h, vcp_stats* out);
 
 /* Host-side helper for language bindings: copy n byte ranges src_base+offs[i] .. +lens[i] into dsts[i] on `threads`

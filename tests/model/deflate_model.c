@@ -157,7 +157,7 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
                    whatever is longer is 'capped' and, if it becomes the window's last token, extended cooperatively */
                 const int lcap_i = P->lane_cap_win ? ((i < 16 ? 32 : 16) < lcap ? (i < 16 ? 32 : 16) : lcap) : lcap;
                 int hcap = lcap_i < limit ? lcap_i : limit;
-                int64_t cands[8]; int nc = 0;
+                int64_t cands[12]; int nc = 0;
                 if (P->inwin) {
                     for (int j = i - 1; j >= 0; j--) {
                         int64_t q2 = p + j;
@@ -171,6 +171,8 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
                     cands[nc++] = base + cnd;
                 }
                 if (nb2 && q + nb2 <= F) { uint32_t h2 = hashN(S + q, nb2, hb2) * ways2; for (int w = 0; w < nw2; w++) { uint16_t cnd = T2[h2 + w]; if (cnd != 0) cands[nc++] = base + cnd; } }
+                /* row probe: the byte one filtered row above (distance = 1 + width*bpp), where smooth shading repeats exactly */
+                if (P->rowlen > 0 && q - P->rowlen >= 0 && P->rowlen <= MAXD) cands[nc++] = q - P->rowlen;
                 for (int w = 0; w < nc; w++) {
                     int64_t cp = cands[w];
                     if (cp >= q || q - cp > MAXD) continue;

@@ -14,7 +14,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("bpp", "hash_bits", "ways", "lane_cap", "too_far", "lazy", "cont_min",
                                          "prime_bytes", "capped_wins", "inwin", "cont_maxd", "sub_bytes", "hash2_bytes",
                                          "hash2_bits", "noisy_thresh", "noisy_minlen", "noisy_neard", "cost_maxlen",
-                                         "cost_margin", "cost_warm", "hash2_ways", "ins_limit", "noisy_ways1", "lane_cap_win", "group_subs")] + [("block_bytes", C.c_int64)]
+                                         "cost_margin", "cost_warm", "hash2_ways", "ins_limit", "noisy_ways1", "lane_cap_win", "rowlen", "group_subs")] + [("block_bytes", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -24,7 +24,7 @@ class Stats(C.Structure):
 # the configuration csrc/deflate_lz.cu + deflate_huff.cu implement (group_subs mirrors kGroupSubs in vcp_internal.cuh)
 KERNEL_PARAMS = dict(bpp=3, hash_bits=10, ways=2, lane_cap=64, too_far=32768, lazy=16, cont_min=258, prime_bytes=32768,
                      capped_wins=1, inwin=0, cont_maxd=1, noisy_thresh=160, noisy_minlen=0, noisy_neard=0, cost_maxlen=8,
-                     cost_margin=0, cost_warm=64, hash2_ways=2, ins_limit=0, noisy_ways1=1, lane_cap_win=0, group_subs=1, hash2_bytes=4, hash2_bits=10, sub_bytes=32768,
+                     cost_margin=0, cost_warm=64, hash2_ways=2, ins_limit=0, noisy_ways1=1, lane_cap_win=0, rowlen=-1, group_subs=1, hash2_bytes=4, hash2_bits=10, sub_bytes=32768,
                      block_bytes=512 * 1024)
 
 
@@ -40,8 +40,15 @@ def load():
     return lib
 
 
-def deflate(lib, stream: bytes, **kw):
+def _params(kw):
     p = dict(KERNEL_PARAMS); p.update(kw)
+    if p["rowlen"] < 0:                  # a bare stream goes through the kernels as a 1 x 1 "page" of bpp channels
+        p["rowlen"] = 1 + p["bpp"]
+    return p
+
+
+def deflate(lib, stream: bytes, **kw):
+    p = _params(kw)
     P = Params(**p)
     src = np.concatenate([np.frombuffer(stream, np.uint8), np.zeros(512, np.uint8)])
     out = np.zeros(len(stream) + len(stream) // 8 + 4096, np.uint8)
@@ -52,7 +59,7 @@ def deflate(lib, stream: bytes, **kw):
 
 def lz_tokens(lib, stream: bytes, **kw):
     """Per sub-chunk token lists as the kernel lays them out: list of (tokens uint32 array, hist[316])."""
-    p = dict(KERNEL_PARAMS); p.update(kw)
+    p = _params(kw)
     P = Params(**p)
     F = len(stream)
     src = np.concatenate([np.frombuffer(stream, np.uint8), np.zeros(512, np.uint8)])

@@ -41,6 +41,8 @@ def decode_all(png: bytes):
                 a = a[:, :, ::-1]
             elif a.ndim == 3 and a.shape[2] == 4:
                 a = a[:, :, [2, 1, 0, 3]]
+                if im.mode == "LA":                    # OpenCV expands gray+alpha to BGRA
+                    a = a[:, :, [0, 3]]
             out.append(("cv2", a))
     except ImportError:
         pass

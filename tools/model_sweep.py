@@ -13,16 +13,19 @@ pages = {"Lph->RGB": synth.make_page(3, "letter", 200, "L", True).convert("RGB")
          "ref001": Image.open("tests/golden/ref_page_1.png"),
          "ref014": Image.open("/root/reference/output/pages/page_014.png"),
          "ref008": Image.open("/root/reference/output/pages/page_008.png"),
-         "Lph": synth.make_page(3, "letter", 200, "L", True)}
+         "Lph": synth.make_page(3, "letter", 200, "L", True),
+         "smooth": Image.fromarray(np.random.default_rng(0).integers(0, 256, (3, 4), dtype=np.uint8), "L").convert("RGB").resize((1700, 2200), 1)}
 data = {}
 for k, im in pages.items():
     ref = U.pillow_png(im)
-    data[k] = (U.png_filtered(ref), sum(len(c) for c in R.png_split(ref)[4]), len(im.getbands()))
+    data[k] = (U.png_filtered(ref), sum(len(c) for c in R.png_split(ref)[4]), len(im.getbands()), 1 + im.width * len(im.getbands()))
 variants = json.loads(sys.argv[1])
 print("variant".ljust(24), *[k.ljust(9) for k in data])
 for k, kw in variants.items():
     row = []
-    for pg, (filt, zr, bpp) in data.items():
-        z, st = M.deflate(lib, filt, bpp=bpp, **kw)
+    for pg, (filt, zr, bpp, rowlen) in data.items():
+        kw2 = dict(kw)
+        kw2.setdefault("rowlen", rowlen)          # the kernels probe one filtered row up
+        z, st = M.deflate(lib, filt, bpp=bpp, **kw2)
         row.append(f"{len(z)/zr:.3f}".ljust(9))
     print(k.ljust(24), *row, flush=True)

@@ -48,6 +48,10 @@ SYMBOLS = {
     "vcp_output_bound": (C.c_int, [C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vcp_prepare_batch": (C.c_int, [C.c_void_p, C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.c_void_p, C.c_uint64,
                                     C.c_void_p, C.c_uint64, C.POINTER(PageResult)]),
+    "vcp_batch_begin": (C.c_int, [C.c_void_p, C.POINTER(PageDesc), C.c_int, C.POINTER(Opts), C.c_void_p, C.c_uint64,
+                                  C.c_void_p, C.c_uint64, C.POINTER(PageResult)]),
+    "vcp_batch_next": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vcp_batch_end": (C.c_int, [C.c_void_p]),
     "vcp_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "vcp_host_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "vcp_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int]),

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <string>
@@ -58,9 +59,19 @@ struct Lane {
 };
 constexpr int kLanes = 4;
 
+struct BatchJob {                  // a streaming batch (vcp_batch_begin .. vcp_batch_end)
+    struct Ready { int first, last; cudaEvent_t ev; };
+    std::vector<vcp_page_desc> pages; vcp_opts opts;
+    std::thread th;
+    std::mutex m; std::condition_variable cv;
+    std::vector<Ready> ready; size_t next = 0;
+    bool done = false; int rc = 0; std::string err;
+};
+
 struct vcp_handle {
     int device = 0;
     std::mutex mu;
+    BatchJob* job = nullptr;
     Lane lane[kLanes];
     std::map<CoeffKey, Coeffs> coeff_cache;
     vcp_stats stats = {};
@@ -506,15 +517,24 @@ int vcp_output_bound(const vcp_page_desc* pages, int n, const vcp_opts* opts, ui
     return 0;
 }
 
-int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts,
-                      void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results) {
+}  // extern "C"
+
+namespace {
+
+int check_batch_args(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts, void* out_png, void* out_b64, vcp_page_result* results) {
     if (!h || n < 0 || (n > 0 && (!pages || !results)) || !opts) return fail(VCP_EINVAL, "bad arguments");
     if (n > 0 && !out_png) return fail(VCP_EINVAL, "out_png is NULL");
     if (opts->want_b64 && n > 0 && !out_b64) return fail(VCP_EINVAL, "want_b64 set but out_b64 is NULL");
     if (opts->out_channels != 0 && opts->out_channels != 1 && opts->out_channels != 3) return fail(VCP_EINVAL, "out_channels must be 0, 1 or 3");
-    std::lock_guard<std::mutex> lock(h->mu);
+    return 0;
+}
+
+// The batch pipeline (caller holds h->mu).  `publish(first_page, last_page, lane)` is called once per group, in page order, right
+// after the group's output bytes have been ENQUEUED to the caller's buffers on that lane's stream (results[] of its pages are final).
+template <class Publish>
+int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts,
+              void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results, Publish publish) {
     CU(cudaSetDevice(h->device));
-    Lane& L = h->lane[0]; (void)L;
     reset_stats(h);
     // per-page validation: a bad page gets its own status and is left out of the launch set
     std::vector<PagePlan> all(n);
@@ -584,6 +604,7 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
             h->stats.png_bytes += r.png_len; h->stats.b64_bytes += r.b64_len;
         }
         png_used += gp; b64_used += gb;
+        publish(groups[g].front(), groups[g].back(), &L);
         return 0;
     };
     int rc = 0;
@@ -607,6 +628,78 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
     h->stats.ms_total = h->stats.ms_h2d + h->stats.ms_convert + h->stats.ms_filter + h->stats.ms_lz + h->stats.ms_huff +
                         h->stats.ms_assemble + h->stats.ms_b64 + h->stats.ms_d2h;
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts,
+                      void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results) {
+    int rc = check_batch_args(h, pages, n, opts, out_png, out_b64, results);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(h->mu);
+    return run_batch(h, pages, n, opts, out_png, png_cap, out_b64, b64_cap, results, [](int, int, Lane*) {});
+}
+
+// ---- streaming variant: the pipeline runs on a worker thread of the handle; the caller picks up page ranges as their bytes land
+int vcp_batch_begin(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts,
+                    void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results) {
+    int rc = check_batch_args(h, pages, n, opts, out_png, out_b64, results);
+    if (rc) return rc;
+    h->mu.lock();                                   // released by vcp_batch_end (same calling thread)
+    BatchJob* J = new BatchJob();
+    h->job = J;
+    J->pages.assign(pages, pages + n); J->opts = *opts;
+    J->th = std::thread([=]() {
+        const int r = run_batch(h, J->pages.data(), n, &J->opts, out_png, png_cap, out_b64, b64_cap, results,
+                                [J](int first, int last, Lane* L) {
+                                    cudaEvent_t ev = nullptr;
+                                    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                                    cudaEventRecord(ev, L->stream);
+                                    std::lock_guard<std::mutex> g(J->m);
+                                    J->ready.push_back({first, last, ev});
+                                    J->cv.notify_all();
+                                });
+        std::lock_guard<std::mutex> g(J->m);
+        J->rc = r; if (r) J->err = g_err;
+        J->done = true;
+        J->cv.notify_all();
+    });
+    return 0;
+}
+
+int vcp_batch_next(vcp_handle* h, int* first_page, int* last_page) {
+    if (!h || !h->job || !first_page || !last_page) return fail(VCP_EINVAL, "no batch in flight");
+    BatchJob* J = h->job;
+    BatchJob::Ready r;
+    {
+        std::unique_lock<std::mutex> g(J->m);
+        J->cv.wait(g, [&] { return J->next < J->ready.size() || J->done; });
+        if (J->next >= J->ready.size()) {                       // finished (or failed)
+            if (J->rc) { g_err = J->err; return J->rc; }
+            return 0;
+        }
+        r = J->ready[J->next++];
+    }
+    cudaSetDevice(h->device);
+    const cudaError_t e = cudaEventSynchronize(r.ev);           // the group's bytes are now in the caller's buffers
+    if (e != cudaSuccess) return fail(VCP_ECUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+    *first_page = r.first; *last_page = r.last;
+    return 1;
+}
+
+int vcp_batch_end(vcp_handle* h) {
+    if (!h || !h->job) return fail(VCP_EINVAL, "no batch in flight");
+    BatchJob* J = h->job;
+    if (J->th.joinable()) J->th.join();
+    for (auto& r : J->ready) if (r.ev) cudaEventDestroy(r.ev);
+    const int rc = J->rc;
+    if (rc) g_err = J->err;
+    delete J;
+    h->job = nullptr;
+    h->mu.unlock();
+    return rc;
 }
 
 int vcp_get_stats(vcp_handle* h, vcp_stats* out) {

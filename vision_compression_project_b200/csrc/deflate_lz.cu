@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     const uint32_t* __restrict__ S32 = reinterpret_cast<const uint32_t*>(S);     // page streams are 256-byte aligned
     const int F = (int)pg.filt_len;
     const int bpp = pg.c;
+    const int rowlen = 1 + pg.w * pg.c;                                          // bytes of one filtered row
     const int s = (int)blk.start + (sub - blk.sub0) * kSubBytes;
     const int e = min(s + kSubBytes, (int)(blk.start + blk.len));
     const int base = s - kMaxDist;                                               // table entries are pos - base (u16), 0 = empty
@@ -304,24 +305,26 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 const int hcap = min(kLaneCap, limit);
                 const bool ok6 = q + kH2Bytes <= F;
                 const bool noisy = score >= kNoisy;                               // literal-dense stretch: older ways rarely pay for their loads
-                int cpos[4], clen[4]; bool live[4];
+                int cpos[5], clen[5]; bool live[5];
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
+                for (int w = 0; w < 5; w++) {
+                    // w = 0..3: the two ways of the two tables; w = 4: the byte one filtered row up (smooth shading repeats there)
                     const uint32_t cnd = (w == 0) ? (b3 >> 16) : (w == 1) ? (b3 & 0xFFFFu) : (w == 2) ? (b6 >> 16) : (b6 & 0xFFFFu);
-                    const int cp = base + (int)cnd;
+                    const int cp = w < 4 ? base + (int)cnd : q - rowlen;
                     const int d = q - cp;
-                    live[w] = cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist && !(noisy && (w & 1));
+                    live[w] = w < 4 ? (cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist && !(noisy && (w & 1)))
+                                    : (rowlen <= kMaxDist && cp >= 0);
                     cpos[w] = live[w] ? cp : q;
                     clen[w] = 0;
                 }
                 // stage A: the first 4 bytes only (two words per candidate, all eight loads issued before the first use) —
                 // in noisy rows almost every candidate dies here
-                uint32_t g0k[4], g1k[4];
+                uint32_t g0k[5], g1k[5];
 #pragma unroll
-                for (int w = 0; w < 4; w++) { const uint32_t* g = S32 + (cpos[w] >> 2); g0k[w] = __ldg(g); g1k[w] = __ldg(g + 1); }
+                for (int w = 0; w < 5; w++) { const uint32_t* g = S32 + (cpos[w] >> 2); g0k[w] = __ldg(g); g1k[w] = __ldg(g + 1); }
                 bool any = false;
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
+                for (int w = 0; w < 5; w++) {
                     const uint32_t x0 = cur4 ^ __funnelshift_r(g0k[w], g1k[w], (cpos[w] & 3) * 8);
                     const int n = x0 ? (__ffs(x0) - 1) >> 3 : 4;
                     clen[w] = live[w] ? min(n, hcap) : 0;
@@ -330,15 +333,15 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 }
                 // stage B: bytes 4..15 of the survivors (loads first, then the compares)
                 if (any) {
-                    uint32_t g2k[4], g3k[4], g4k[4];
+                    uint32_t g2k[5], g3k[5], g4k[5];
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
+                    for (int w = 0; w < 5; w++) {
                         g2k[w] = g3k[w] = g4k[w] = 0u;
                         if (live[w]) { const uint32_t* g = S32 + (cpos[w] >> 2); g2k[w] = __ldg(g + 2); g3k[w] = __ldg(g + 3); g4k[w] = __ldg(g + 4); }
                     }
                     any = false;
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
+                    for (int w = 0; w < 5; w++) {
                         if (live[w]) {
                             const int shc = (cpos[w] & 3) * 8;
                             const int n = eq16(0u, nxt4 ^ __funnelshift_r(g1k[w], g2k[w], shc), q8 ^ __funnelshift_r(g2k[w], g3k[w], shc),
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     const uint32_t y0 = __funnelshift_r(s0, s1, shq), y1 = __funnelshift_r(s1, s2, shq);
                     const uint32_t y2 = __funnelshift_r(s2, s3, shq), y3 = __funnelshift_r(s3, s4, shq);
 #pragma unroll
-                    for (int w = 0; w < 4; w++) {
+                    for (int w = 0; w < 5; w++) {
                         if (live[w]) {
                             const uint32_t* g = S32 + ((cpos[w] + n0) >> 2);
                             const int shc = ((cpos[w] + n0) & 3) * 8;
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     }
                 }
 #pragma unroll
-                for (int w = 0; w < 4; w++) {
+                for (int w = 0; w < 5; w++) {
                     const int l = clen[w], d = q - cpos[w];
                     const bool c = (l == hcap) && (hcap < limit);
                     if (l >= 3) best = max(best, ((c ? 127u : (uint32_t)l) << 24) | ((uint32_t)(32768 - d) << 8) | (uint32_t)l);
