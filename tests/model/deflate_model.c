@@ -172,7 +172,8 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
                 }
                 if (nb2 && q + nb2 <= F) { uint32_t h2 = hashN(S + q, nb2, hb2) * ways2; for (int w = 0; w < nw2; w++) { uint16_t cnd = T2[h2 + w]; if (cnd != 0) cands[nc++] = base + cnd; } }
                 /* row probe: the byte one filtered row above (distance = 1 + width*bpp), where smooth shading repeats exactly */
-                if (P->rowlen > 0 && q - P->rowlen >= 0 && P->rowlen <= MAXD) cands[nc++] = q - P->rowlen;
+                if (P->rowlen > 0 && q - P->rowlen >= 0 && P->rowlen <= MAXD &&
+                    !(P->row_gate == 1 && q >= 1 && S[q] == S[q - 1]) && !(P->row_gate == 2 && noisy)) cands[nc++] = q - P->rowlen;
                 for (int w = 0; w < nc; w++) {
                     int64_t cp = cands[w];
                     if (cp >= q || q - cp > MAXD) continue;

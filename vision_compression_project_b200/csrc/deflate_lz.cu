@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     const int cp = w < 4 ? base + (int)cnd : q - rowlen;
                     const int d = q - cp;
                     live[w] = w < 4 ? (cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist && !(noisy && (w & 1)))
-                                    : (rowlen <= kMaxDist && cp >= 0);
+                                    : (rowlen <= kMaxDist && cp >= 0 && !e1a);   // only where a run starts: inside a run distance 1 already serves
                     cpos[w] = live[w] ? cp : q;
                     clen[w] = 0;
                 }
