@@ -129,9 +129,11 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
         uint32_t Ntok = (uint32_t)ntok;
         int nlit = 0;
         int len[WIN], dist[WIN], capped[WIN];
+        /* exact_sel: per lane, the capped candidates (distance, length so far) and the best fully compared one */
+        int ccd[WIN][8], ccl[WIN][8], ncc[WIN], xl[WIN], xd[WIN];
         /* ---- every lane proposes */
         for (int i = 0; i < WIN; i++) {
-            int64_t q = p + i; len[i] = 0; dist[i] = 0; capped[i] = 0;
+            int64_t q = p + i; len[i] = 0; dist[i] = 0; capped[i] = 0; ncc[i] = 0; xl[i] = 0; xd[i] = 0;
             if (q >= e) continue;
             int limit = (int)((e - q) < MAXLEN ? (e - q) : MAXLEN);
             if (limit < 3) continue;
@@ -146,6 +148,8 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
                 int l = match_len(S + q, S + q - d, runcap);
                 int c = (l == runcap && runcap < limit);
                 int eff = (c && P->capped_wins) ? 1000 : l;
+                if (l >= 3 && c) { ccd[i][ncc[i]] = d; ccl[i][ncc[i]] = l; ncc[i]++; }
+                if (l >= 3 && !c && (l > xl[i] || (l == xl[i] && d < xd[i]))) { xl[i] = l; xd[i] = d; }
                 if (l >= 3 && eff > be) { be = eff; bl = l; bd = d; bc = c; }
             }
             /* hash candidates, exact up to lane_cap: the most recent earlier lane of this window with
@@ -181,6 +185,8 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
                     int c = (l == hcap && hcap < limit);
                     int d = (int)(q - cp);
                     int eff = (c && P->capped_wins) ? 1000 : l;
+                    if (l >= 3 && c) { ccd[i][ncc[i]] = d; ccl[i][ncc[i]] = l; ncc[i]++; }
+                    if (l >= 3 && !c && (l > xl[i] || (l == xl[i] && d < xd[i]))) { xl[i] = l; xd[i] = d; }
                     if (l >= 3 && (eff > be || (eff == be && d < bd))) { be = eff; bl = l; bd = d; bc = c; }
                 }
             }
@@ -210,7 +216,16 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
             int64_t q = p + i;
             if (len[i] >= 3) {
                 int L = len[i], d = dist[i];
-                if (capped[i]) {          /* cooperative extension: exact up to the limit */
+                if (capped[i] && P->exact_sel) {
+                    /* a selected token with capped candidates: compare every one of them (and the best exact one) to the limit */
+                    int limit = (int)((e - q) < MAXLEN ? (e - q) : MAXLEN);
+                    L = xl[i]; d = xd[i];
+                    for (int k = 0; k < ncc[i]; k++) {
+                        int dk = ccd[i][k];
+                        int Lk = ccl[i][k] + match_len(S + q + ccl[i][k], S + q + ccl[i][k] - dk, limit - ccl[i][k]);
+                        if (Lk > L || (Lk == L && dk < d)) { L = Lk; d = dk; }
+                    }
+                } else if (capped[i]) {          /* cooperative extension: exact up to the limit */
                     int limit = (int)((e - q) < MAXLEN ? (e - q) : MAXLEN);
                     L += match_len(S + q + L, S + q + L - d, limit - L);
                 }

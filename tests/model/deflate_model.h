@@ -32,6 +32,7 @@ typedef struct {
     int32_t lane_cap_win; /* 1: lanes 0-15 compare candidates up to 32 bytes, lanes 16-31 up to 16 */
     int32_t rowlen;       /* > 0: extra candidate at distance rowlen (one filtered row up) */
     int32_t row_gate;     /* 0: always probe; 1: only where S[q] != S[q-1]; 2: not in noisy windows */
+    int32_t exact_sel;    /* 1: a selected token whose lane has capped candidates compares all of them to the limit */
     int32_t group_subs;   /* consecutive sub-chunks of a page that share one pair of tables (first primed, rest continue) */
     int64_t block_bytes;  /* deflate block (multiple of sub_bytes) */
 } dm_params;

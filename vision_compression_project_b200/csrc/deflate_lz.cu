@@ -34,7 +34,7 @@ constexpr int HB3 = 10;               // 3-byte-hash table: 2^10 buckets, u32 = 
 constexpr int HB6 = 10;               // 4-byte-hash table: 2^10 buckets, same bucket format
 constexpr int kH2Bytes = 4;           // bytes keyed by the second table
 constexpr int kLzWarps = 2;           // warps (= sub-chunks) per CTA
-constexpr int kLaneCap = 64;          // exact compare length of a hash candidate inside a lane
+constexpr int kLaneCap = 16;          // compare depth of a hash candidate inside a lane (deeper only for tokens the parse selects)
 constexpr int kLazyMax = 16;
 constexpr int kCostMaxLen = 8;
 constexpr int kCostWarm = 64;
@@ -278,8 +278,15 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
 
         const int limit = min(kMaxMatch, e - q);                                 // <= 0 for lanes past the sub-chunk
         int bl = 0, bd = 0; bool bcap = false;
-        // candidates are ranked by one packed key: (capped ? 127 : length) | 32768 - distance | length  — longer first, then nearer
-        uint32_t best = 0;
+        // A lane compares its candidates only 16 bytes deep.  Fully compared ones are ranked in xbest (longer, then nearer);
+        // the ones that hit the cap are remembered in capm and only measured to the end — cooperatively, 128 bytes per
+        // round trip — if the greedy parse actually starts a token at this lane.
+        uint32_t xbest = 0;                                                       // (length << 16) | (32768 - distance)
+        uint32_t cbest = 0;                                                       // nearest capped candidate: ((32768 - distance) << 8) | length so far
+        uint32_t capm = 0;                                                        // bits 0..4: table ways / row probe, 5: distance-1 run, 6: distance-bpp run
+        int cpos[5];
+#pragma unroll
+        for (int w = 0; w < 5; w++) cpos[w] = q;
         const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
         const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
         const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
@@ -290,22 +297,23 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 const int r = inv ? __ffsll((long long)inv) - 1 : 64;
                 const int l = min(r, runcap);
                 const bool c = (l == runcap) && (runcap < limit);
-                if (l >= 3) best = ((c ? 127u : (uint32_t)l) << 24) | (32767u << 8) | (uint32_t)l;
+                if (l >= 3) { if (c) { capm |= 32u; cbest = (32767u << 8) | (uint32_t)l; } else xbest = ((uint32_t)l << 16) | 32767u; }
             }
             if (bpp > 1) {
                 const unsigned long long inv = ~(mb >> lane);
                 const int r = inv ? __ffsll((long long)inv) - 1 : 64;
                 const int l = min(r, runcap);
                 const bool c = (l == runcap) && (runcap < limit);
-                if (l >= 3) best = max(best, ((c ? 127u : (uint32_t)l) << 24) | ((uint32_t)(32768 - bpp) << 8) | (uint32_t)l);
+                if (l >= 3) {
+                    if (c) { capm |= 64u; cbest = max(cbest, ((uint32_t)(32768 - bpp) << 8) | (uint32_t)l); }
+                    else xbest = max(xbest, ((uint32_t)l << 16) | (uint32_t)(32768 - bpp));
+                }
             }
-            bcap = (best >> 24) == 127u;
-            if (!bcap) {                                                          // a capped run outranks every hash candidate
-                // four candidates in lock-step: 16 bytes per round trip, all loads of a round issued together
+            if (!capm) {                                                          // a capped run outranks every hash candidate
                 const int hcap = min(kLaneCap, limit);
                 const bool ok6 = q + kH2Bytes <= F;
                 const bool noisy = score >= kNoisy;                               // literal-dense stretch: older ways rarely pay for their loads
-                int cpos[5], clen[5]; bool live[5];
+                int clen[5]; bool live[5];
 #pragma unroll
                 for (int w = 0; w < 5; w++) {
                     // w = 0..3: the two ways of the two tables; w = 4: the byte one filtered row up (smooth shading repeats there)
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     cpos[w] = live[w] ? cp : q;
                     clen[w] = 0;
                 }
-                // stage A: the first 4 bytes only (two words per candidate, all eight loads issued before the first use) —
+                // stage A: the first 4 bytes only (two words per candidate, all ten loads issued before the first use) —
                 // in noisy rows almost every candidate dies here
                 uint32_t g0k[5], g1k[5];
 #pragma unroll
@@ -339,7 +347,6 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                         g2k[w] = g3k[w] = g4k[w] = 0u;
                         if (live[w]) { const uint32_t* g = S32 + (cpos[w] >> 2); g2k[w] = __ldg(g + 2); g3k[w] = __ldg(g + 3); g4k[w] = __ldg(g + 4); }
                     }
-                    any = false;
 #pragma unroll
                     for (int w = 0; w < 5; w++) {
                         if (live[w]) {
@@ -347,42 +354,21 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                             const int n = eq16(0u, nxt4 ^ __funnelshift_r(g1k[w], g2k[w], shc), q8 ^ __funnelshift_r(g2k[w], g3k[w], shc),
                                                q12 ^ __funnelshift_r(g3k[w], g4k[w], shc));
                             clen[w] = min(n, hcap);
-                            live[w] = n == 16 && hcap > 16;
-                            any |= live[w];
-                        }
-                    }
-                }
-                for (int n0 = 16; any; n0 += 16) {                                // rounds 2..4: only candidates still matching
-                    any = false;
-                    const uint32_t* gq = S32 + ((q + n0) >> 2);
-                    const int shq = ((q + n0) & 3) * 8;
-                    const uint32_t s0 = __ldg(gq), s1 = __ldg(gq + 1), s2 = __ldg(gq + 2), s3 = __ldg(gq + 3), s4 = __ldg(gq + 4);
-                    const uint32_t y0 = __funnelshift_r(s0, s1, shq), y1 = __funnelshift_r(s1, s2, shq);
-                    const uint32_t y2 = __funnelshift_r(s2, s3, shq), y3 = __funnelshift_r(s3, s4, shq);
-#pragma unroll
-                    for (int w = 0; w < 5; w++) {
-                        if (live[w]) {
-                            const uint32_t* g = S32 + ((cpos[w] + n0) >> 2);
-                            const int shc = ((cpos[w] + n0) & 3) * 8;
-                            const uint32_t g0 = __ldg(g), g1 = __ldg(g + 1), g2 = __ldg(g + 2), g3 = __ldg(g + 3), g4 = __ldg(g + 4);
-                            const int n = eq16(y0 ^ __funnelshift_r(g0, g1, shc), y1 ^ __funnelshift_r(g1, g2, shc),
-                                               y2 ^ __funnelshift_r(g2, g3, shc), y3 ^ __funnelshift_r(g3, g4, shc));
-                            clen[w] = min(n0 + n, hcap);
-                            live[w] = n == 16 && n0 + 16 < hcap;
-                            any |= live[w];
                         }
                     }
                 }
 #pragma unroll
                 for (int w = 0; w < 5; w++) {
                     const int l = clen[w], d = q - cpos[w];
-                    const bool c = (l == hcap) && (hcap < limit);
-                    if (l >= 3) best = max(best, ((c ? 127u : (uint32_t)l) << 24) | ((uint32_t)(32768 - d) << 8) | (uint32_t)l);
+                    if (l >= 3) {
+                        if (l == hcap && hcap < limit) { capm |= 1u << w; cbest = max(cbest, ((uint32_t)(32768 - d) << 8) | (uint32_t)l); }
+                        else xbest = max(xbest, ((uint32_t)l << 16) | (uint32_t)(32768 - d));
+                    }
                 }
             }
-            bl = (int)(best & 0xFFu);
-            bd = best ? 32768 - (int)((best >> 8) & 0x7FFFu) : 0;
-            bcap = (best >> 24) == 127u;
+            bcap = capm != 0u;
+            if (bcap) { bl = (int)(cbest & 0xFFu); bd = 32768 - (int)(cbest >> 8); }
+            else if (xbest) { bl = (int)(xbest >> 16); bd = 32768 - (int)(xbest & 0xFFFFu); }
             // price short matches against literals with the histogram as of the window start
             if (bl >= 3 && bl <= kCostMaxLen && ntok >= kCostWarm) {
                 const int lgN = ilog2x4(ntok + 1);
@@ -397,37 +383,78 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 const int ls = bl - 3, ds = dist_sym(bd);                         // bl <= 8: no length extra bits
                 const int dx = ds < 4 ? 0 : (ds >> 1) - 1;
                 const int mc = (lgN - ilog2x4(M.hist[257 + ls] + 1)) + (lgN - ilog2x4(M.hist[286 + ds] + 1)) + 4 * dx;
-                if (mc >= lit) { bl = 0; bd = 0; bcap = false; }
+                if (mc >= lit) { bl = 0; bd = 0; }
             }
         }
         // ---- one-step lazy rule between neighbouring lanes
         {
             const int nxt = __shfl_down_sync(kFull, bl, 1);
-            if (lane < 31 && bl >= 3 && bl < kLazyMax && nxt > bl) { bl = 0; bd = 0; bcap = false; }
+            if (lane < 31 && bl >= 3 && bl < kLazyMax && nxt > bl) { bl = 0; bd = 0; }
         }
-        // ---- greedy parse from lane 0 by pointer jumping
+        // ---- greedy parse from lane 0 by pointer jumping; whenever the parse starts a token on a lane with capped candidates,
+        //      those are measured to the end (the best fully compared one competes too) and the parse is redone from there
         const int nvalid = min(32, e - p);
-        int J = lane + (bl ? bl : 1);
-        if (J >= nvalid) J = 32;
-        uint32_t Msel = 1u << lane;
+        uint32_t sel;
+        for (;;) {
+            int J = lane + (bl ? bl : 1);
+            if (J >= nvalid) J = 32;
+            uint32_t Msel = 1u << lane;
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const uint32_t Mj = __shfl_sync(kFull, Msel, J & 31);
-            const int Jj = __shfl_sync(kFull, J, J & 31);
-            if (J < 32) { Msel |= Mj; J = Jj; }
+            for (int r = 0; r < 5; r++) {
+                const uint32_t Mj = __shfl_sync(kFull, Msel, J & 31);
+                const int Jj = __shfl_sync(kFull, J, J & 31);
+                if (J < 32) { Msel |= Mj; J = Jj; }
+            }
+            sel = __shfl_sync(kFull, Msel, 0);
+            const uint32_t cm = __ballot_sync(kFull, bcap) & sel;
+            if (!cm) break;
+            const int f = __ffs(cm) - 1;
+            const int qf = p + f;
+            const int limf = min(kMaxMatch, e - qf);
+            const int rcf = min(64 - f, limf), hcf = min(kLaneCap, limf);
+            const uint32_t capf = __shfl_sync(kFull, capm, f);
+            uint32_t bestk = __shfl_sync(kFull, xbest, f);
+            if (capf & 0x1Fu) {
+                // table / row candidates: the next 128 bytes of all of them in ONE round trip (the q side is shared)
+                const int off = hcf + 4 * lane;
+                const uint32_t xq = ldu(S32, qf + off);
+                int dw[5]; uint32_t xw[5];
+#pragma unroll
+                for (int w = 0; w < 5; w++) {
+                    const int cpw = __shfl_sync(kFull, cpos[w], f);
+                    dw[w] = qf - cpw;
+                    xw[w] = ((capf >> w) & 1u) ? (xq ^ ldu(S32, cpw + off)) : 0u;
+                }
+#pragma unroll
+                for (int w = 0; w < 5; w++) {
+                    if ((capf >> w) & 1u) {
+                        const uint32_t mism = __ballot_sync(kFull, xw[w] != 0u);
+                        int Lw = hcf + 128;
+                        if (mism) {
+                            const int first = __ffs(mism) - 1;
+                            const uint32_t xx = __shfl_sync(kFull, xw[w], first);
+                            Lw = hcf + 4 * first + ((__ffs(xx) - 1) >> 3);
+                        } else if (Lw < limf) {
+                            Lw += coop_match(S32, qf + Lw, dw[w], limf - Lw, lane);      // rare: more than 144 equal bytes
+                        }
+                        bestk = max(bestk, ((uint32_t)min(Lw, limf) << 16) | (uint32_t)(32768 - dw[w]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = 5; w < 7; w++) {                                         // capped runs (then no table candidate was looked at)
+                if ((capf >> w) & 1u) {
+                    const int d = (w == 5) ? 1 : bpp;
+                    const int Lw = rcf + coop_match(S32, qf + rcf, d, limf - rcf, lane);
+                    bestk = max(bestk, ((uint32_t)Lw << 16) | (uint32_t)(32768 - d));
+                }
+            }
+            if (lane == f) { bl = (int)(bestk >> 16); bd = 32768 - (int)(bestk & 0xFFFFu); bcap = false; }
         }
-        const uint32_t sel = __shfl_sync(kFull, Msel, 0);
         const int last = 31 - __clz(sel);
-        // ---- the last token may be capped: extend it cooperatively
-        int Ll = __shfl_sync(kFull, bl, last);
+        const int Ll = __shfl_sync(kFull, bl, last);
         const int dl = __shfl_sync(kFull, bd, last);
-        const bool capl = __shfl_sync(kFull, (int)bcap, last) != 0;
         const int ql = p + last;
-        if (capl) {
-            const int lim = min(kMaxMatch, e - ql);
-            Ll += coop_match(S32, ql + Ll, dl, lim - Ll, lane);
-        }
-        if (lane == last) bl = Ll;
         __syncwarp();                                                            // all histogram reads of this window are done
         // ---- emit tokens + histogram
         if ((sel >> lane) & 1u) {
