@@ -101,8 +101,17 @@ def test_parse_pnm():
 
 def test_input_normalisation_and_planning():
     from vision_compression_project_b200.api import PagePrep, _as_source
-    s = _as_source(Image.new("RGB", (5, 4)), None)
-    assert (s.w, s.h, s.c, s.stride, s.device) == (5, 4, 3, 15, False)
+    s = _as_source(Image.new("RGB", (5, 4)), None)                        # Pillow's own RGBX storage, zero copy (Arrow capsule)
+    assert (s.w, s.h, s.c, s.logical_c, s.stride, s.device) == (5, 4, 4, 3, 20, False)
+    s = _as_source(Image.new("L", (5, 4)), None)
+    assert (s.w, s.h, s.c, s.logical_c, s.stride) == (5, 4, 1, 1, 5)
+    s = _as_source(Image.new("LA", (5, 4)), None)                         # packed copy
+    assert (s.w, s.h, s.c, s.stride) == (5, 4, 2, 10)
+    px = np.arange(5 * 4 * 3, dtype=np.uint8).reshape(4, 5, 3)
+    s = _as_source(Image.fromarray(px, "RGB"), None)
+    import ctypes
+    raw = np.ctypeslib.as_array((ctypes.c_uint8 * (5 * 4 * 4)).from_address(s.ptr)).reshape(4, 5, 4)
+    assert np.array_equal(raw[:, :, :3], px)
     s = _as_source(np.zeros((4, 10, 3), np.uint8)[:, :5], None)           # row-strided view is passed through
     assert (s.w, s.h, s.c, s.stride) == (5, 4, 3, 30)
     s = _as_source(b"P5\n3 2\n255\n" + bytes(6), None)
