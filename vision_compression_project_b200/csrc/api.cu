@@ -55,6 +55,7 @@ struct Lane {
     cudaStream_t stream = nullptr;
     uint8_t* arena = nullptr; size_t arena_cap = 0;
     uint8_t* meta = nullptr; size_t meta_cap = 0;          // pinned host staging: descriptors up, results down
+    uint8_t* stage = nullptr; size_t stage_cap = 0;        // pinned bounce buffer for pageable page sources (filled by host threads)
     cudaEvent_t ev[EV_COUNT] = {};
 };
 constexpr int kLanes = 4;
@@ -77,6 +78,7 @@ struct vcp_handle {
     vcp_stats stats = {};
     size_t group_bytes = (size_t)2 << 30;                  // max filtered bytes per launch set
     size_t pipe_bytes = (size_t)96 << 20;                  // host inputs: source bytes per pipelined group
+    int copy_threads = 8;                                  // host threads that fill the bounce buffer
 };
 
 namespace {
@@ -97,6 +99,37 @@ int ensure_meta(Lane& L, size_t need) {
     CU(cudaMallocHost(&L.meta, cap));
     L.meta_cap = cap;
     return 0;
+}
+
+int ensure_stage(Lane& L, size_t need) {
+    if (need <= L.stage_cap) return 0;
+    if (L.stage) { CU(cudaStreamSynchronize(L.stream)); CU(cudaFreeHost(L.stage)); L.stage = nullptr; L.stage_cap = 0; }
+    const size_t cap = align_up(need + need / 4, (size_t)1 << 20);
+    CU(cudaMallocHost(&L.stage, cap));
+    L.stage_cap = cap;
+    return 0;
+}
+
+// copy n byte ranges on T host threads, splitting the total evenly (a page of rows counts as one range per row when strided)
+struct CopyJob { uint8_t* dst; const uint8_t* src; size_t len; };
+void parallel_copy(const std::vector<CopyJob>& jobs, int T) {
+    size_t total = 0;
+    for (auto& j : jobs) total += j.len;
+    T = std::max(1, std::min(T, 16));
+    if (T == 1 || total < ((size_t)1 << 20)) { for (auto& j : jobs) memcpy(j.dst, j.src, j.len); return; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; t++) {
+        const size_t lo = total * t / T, hi = total * (t + 1) / T;
+        pool.emplace_back([&jobs, lo, hi]() {
+            size_t pos = 0;
+            for (size_t i = 0; i < jobs.size() && pos < hi; i++) {
+                const size_t a = std::max(lo, pos), b = std::min(hi, pos + jobs[i].len);
+                if (a < b) memcpy(jobs[i].dst + (a - pos), jobs[i].src + (a - pos), b - a);
+                pos += jobs[i].len;
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
 }
 
 const Coeffs* get_coeffs(vcp_handle* h, int in_size, int out_size, int filter, float b0, float b1) {
@@ -374,9 +407,37 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     CU(cudaMemcpyAsync(A + o_coeff, M, desc_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(R, 0, (o_cnt + 256) - o_res, st));
     if (!stream_in && !o.src_device) {
-        for (auto& P : plans) {
+        // Pinned (or registered) sources are DMA'd where they lie.  Pageable ones — e.g. Pillow's own pixel storage — would make
+        // cudaMemcpyAsync stage them on one thread at ~11 GB/s: pack them into the lane's pinned bounce buffer on several host
+        // threads instead (the previous group's DMA and kernels run meanwhile) and DMA from there.
+        std::vector<CopyJob> jobs;
+        std::vector<size_t> stage_off(n, kNone);
+        size_t stage_need = 0;
+        for (int i = 0; i < n; i++) {
+            cudaPointerAttributes at;
+            const bool pinned = cudaPointerGetAttributes(&at, plans[i].src) == cudaSuccess &&
+                                (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+            cudaGetLastError();
+            if (!pinned) { stage_off[i] = stage_need; stage_need += align_up((size_t)plans[i].sw * plans[i].sc * plans[i].sh, 256); }
+        }
+        if (stage_need) {
+            rc = ensure_stage(L, stage_need);
+            if (rc) return rc;
+            for (int i = 0; i < n; i++) {
+                if (stage_off[i] == kNone) continue;
+                const PagePlan& P = plans[i];
+                const size_t rowb = (size_t)P.sw * P.sc;
+                uint8_t* d = L.stage + stage_off[i];
+                if ((size_t)P.src_stride == rowb) jobs.push_back({d, P.src, rowb * P.sh});
+                else for (int y = 0; y < P.sh; y++) jobs.push_back({d + (size_t)y * rowb, P.src + (size_t)y * P.src_stride, rowb});
+            }
+            parallel_copy(jobs, h->copy_threads);
+        }
+        for (int i = 0; i < n; i++) {
+            const PagePlan& P = plans[i];
             const size_t rowb = (size_t)P.sw * P.sc;
-            if ((size_t)P.src_stride == rowb) CU(cudaMemcpyAsync(A + P.o_raw, P.src, rowb * P.sh, cudaMemcpyHostToDevice, st));
+            if (stage_off[i] != kNone) CU(cudaMemcpyAsync(A + P.o_raw, L.stage + stage_off[i], rowb * P.sh, cudaMemcpyHostToDevice, st));
+            else if ((size_t)P.src_stride == rowb) CU(cudaMemcpyAsync(A + P.o_raw, P.src, rowb * P.sh, cudaMemcpyHostToDevice, st));
             else CU(cudaMemcpy2DAsync(A + P.o_raw, rowb, P.src, (size_t)P.src_stride, rowb, (size_t)P.sh, cudaMemcpyHostToDevice, st));
         }
     }
@@ -478,6 +539,13 @@ int vcp_init(int device, vcp_handle** out) {
         if (e != cudaSuccess) { delete h; return fail(VCP_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         for (int i = 0; i < EV_COUNT; i++) cudaEventCreate(&L.ev[i]);
     }
+    {
+        const unsigned hc = std::thread::hardware_concurrency();
+        int lw = 1;
+        if (const char* g = getenv("LOCAL_WORLD_SIZE")) lw = std::max(1, atoi(g));
+        h->copy_threads = std::max(2, std::min(8, (int)(hc ? hc : 8) / lw));
+        if (const char* g = getenv("VCP_COPY_THREADS")) h->copy_threads = std::max(1, atoi(g));
+    }
     if (const char* g = getenv("VCP_PIPE_BYTES")) { const long long v = atoll(g); if (v >= (1 << 20)) h->pipe_bytes = (size_t)v; }
     if (const char* g = getenv("VCP_GROUP_BYTES")) { const long long v = atoll(g); if (v >= (1 << 20)) h->group_bytes = (size_t)v; }
     *out = h;
@@ -491,6 +559,7 @@ void vcp_destroy(vcp_handle* h) {
         if (L.stream) cudaStreamSynchronize(L.stream);
         if (L.arena) cudaFree(L.arena);
         if (L.meta) cudaFreeHost(L.meta);
+        if (L.stage) cudaFreeHost(L.stage);
         for (int i = 0; i < EV_COUNT; i++) if (L.ev[i]) cudaEventDestroy(L.ev[i]);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
