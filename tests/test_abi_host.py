@@ -99,6 +99,16 @@ def test_parse_pnm():
             V.parse_pnm(bad)
 
 
+def test_split_pnm_stream():
+    a = b"P6\n4 2\n255\n" + bytes(range(24))
+    b = b"P5\n3 3\n255\n" + bytes(range(9))
+    parts = V.split_pnm_stream(a + b + b"\n" + a)
+    assert [bytes(p) for p in parts] == [a, b, a]
+    assert V.split_pnm_stream(b"") == []
+    with pytest.raises(ValueError):
+        V.split_pnm_stream(a + b"garbage")
+
+
 def test_input_normalisation_and_planning():
     from vision_compression_project_b200.api import PagePrep, _as_source
     s = _as_source(Image.new("RGB", (5, 4)), None)                        # Pillow's own RGBX storage, zero copy (Arrow capsule)

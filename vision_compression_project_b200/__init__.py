@@ -5,7 +5,7 @@ this package is the Python host mirror of the reference's call sites.  Importing
 calling `prepare_page(s)` without the built library or without a B200 raises.
 """
 from .api import (BICUBIC, BILINEAR, BOX, HAMMING, LANCZOS, PagePrep, PreparedPage, parse_pnm, prepare_page,
-                  prepare_pages, thumbnail_size)
+                  prepare_pages, split_pnm_stream, thumbnail_size)
 
-__all__ = ["prepare_page", "prepare_pages", "PagePrep", "PreparedPage", "thumbnail_size", "parse_pnm",
+__all__ = ["prepare_page", "prepare_pages", "PagePrep", "PreparedPage", "thumbnail_size", "parse_pnm", "split_pnm_stream",
            "LANCZOS", "BILINEAR", "BICUBIC", "BOX", "HAMMING"]

@@ -96,6 +96,23 @@ def parse_pnm(data) -> Tuple[int, int, int, int]:
     return w, h, ch, pos
 
 
+def split_pnm_stream(data) -> list:
+    """`pdftoppm` writes the pages of a range back to back on one pipe (pdf2image parses that stream the same way,
+    backend/app/pipeline/pdf_extract.py:109-122 via convert_from_path).  Returns one zero-copy memoryview per P6/P5 image."""
+    mv = memoryview(data)
+    out, pos = [], 0
+    while pos < len(mv):
+        while pos < len(mv) and mv[pos] in b" \t\r\n":
+            pos += 1
+        if pos >= len(mv):
+            break
+        w, h, ch, off = parse_pnm(mv[pos:])
+        end = pos + off + w * h * ch
+        out.append(mv[pos:end])
+        pos = end
+    return out
+
+
 class _Source:
     __slots__ = ("keep", "ptr", "w", "h", "c", "stride", "device", "logical_c")
 
@@ -392,30 +409,45 @@ class PagePrep:
         self.last_timing = {"plan_ms": 1e3 * (t_1 - t_0), "call_ms": 1e3 * (t_2 - t_1), "bytes_ms": 1e3 * t_bytes}
 
 
-_tls = threading.local()
+class _EnginePool:
+    """Engines (library handles with their arenas and pinned buffers) are expensive to create (~0.1 s of cudaMalloc /
+    cudaMallocHost) and cheap to keep.  Callers borrow one for the duration of a call, so the reference's pattern — a fresh
+    5-thread pool per request (pdf_extract.py:313-333) — reuses warm engines instead of initialising one per new thread."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._free: dict = {}
+
+    def borrow(self, device: int) -> PagePrep:
+        with self._lock:
+            lst = self._free.setdefault(device, [])
+            if lst:
+                return lst.pop()
+        return PagePrep(device)
+
+    def give_back(self, eng: PagePrep) -> None:
+        with self._lock:
+            self._free.setdefault(eng.device, []).append(eng)
 
 
-def _engine(device: int) -> PagePrep:
-    engines = getattr(_tls, "engines", None)
-    if engines is None:
-        engines = _tls.engines = {}
-    e = engines.get(device)
-    if e is None:
-        e = engines[device] = PagePrep(device)
-    return e
+_pool = _EnginePool()
 
 
 def prepare_pages(images: Sequence[Any], *, device: int = 0, **kw) -> List[PreparedPage]:
     """Batched fast path: one launch set for all pages.  A page that cannot be processed gets `.error` set and
     `.png is None`; the others are unaffected (the reference collects failed pages the same way,
     pdf_extract.py:342-350)."""
-    return _engine(device).prepare_pages(images, **kw)
+    eng = _pool.borrow(device)
+    try:
+        return eng.prepare_pages(images, **kw)
+    finally:
+        _pool.give_back(eng)
 
 
 def prepare_page(image: Any, *, device: int = 0, **kw) -> PreparedPage:
     """Single page; raises (ValueError / MemoryError / RuntimeError) like the Pillow calls it replaces, so the
     reference's per-page try/except (pdf_extract.py:133-136) keeps working."""
-    r = _engine(device).prepare_pages([image], **kw)[0]
+    r = prepare_pages([image], device=device, **kw)[0]
     if r.error is not None:
         kind, _, msg = r.error.partition(": ")
         raise {"ValueError": ValueError, "TypeError": TypeError, "MemoryError": MemoryError}.get(kind, RuntimeError)(msg or r.error)
