@@ -230,3 +230,19 @@ def test_gray_sources_to_rgb_with_resize(V, synth):
             _, _, exp = PP.prepare_page_cpu(src, mode="RGB", **{k: (Image.Resampling.BILINEAR if k == "resample" else v) for k, v in kw.items()})
             assert r.mode == "RGB" and r.size == exp.size
             U.check_png_against(r.png, exp, size_tol=1.06)
+
+
+def test_incompressible_batch_retries_with_full_bound(V):
+    """The binding first offers a quarter of the worst-case output bound; incompressible pages overflow it (VCP_ESIZE from the
+    streaming worker) and the call is repeated with the full bound.  Stored blocks keep the PNG within 0.1 % of the raw size."""
+    rng = np.random.default_rng(41)
+    pages = [rng.integers(0, 256, (2200, 1700, 3), dtype=np.uint8) for _ in range(4)]
+    pages = pages * 4                                                       # 16 pages, 180 MB of noise > 4 x 32 MB
+    res = V.prepare_pages(pages, want_base64=False)
+    raw = 2200 * (1 + 1700 * 3)
+    for a, r in zip(pages, res):
+        assert r.error is None and r.b64 is None
+        assert len(r.png) <= raw * 1.001 + 1024
+    dec = np.asarray(Image.open(io.BytesIO(res[5].png)))
+    assert np.array_equal(dec, pages[5])
+    assert res[1].png == res[5].png == res[9].png

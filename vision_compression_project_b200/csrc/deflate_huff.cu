@@ -182,7 +182,7 @@ __device__ void kraft_repair(int* cnt, int maxbits) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kBuildThreads) k_huff_build(BatchD B) {
+__global__ void __launch_bounds__(kBuildThreads, 10) k_huff_build(BatchD B) {   // <= 40 registers: all 1408 blocks of a 64-page batch resident at once
     __shared__ uint32_t freq[kCodeStride];          // [0,286) lit/len, [286,316) dist (patched copies)
     __shared__ uint16_t order_ll[kNumLL], order_d[kNumD];
     __shared__ uint8_t lens[kCodeStride];
