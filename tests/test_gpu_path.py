@@ -246,3 +246,35 @@ def test_incompressible_batch_retries_with_full_bound(V):
     dec = np.asarray(Image.open(io.BytesIO(res[5].png)))
     assert np.array_equal(dec, pages[5])
     assert res[1].png == res[5].png == res[9].png
+
+
+def test_all_recorded_reference_pages(V, fixtures, golden_dir):
+    """Every PNG the reference recorded (output/page_1.png + output/pages/page_001..022.png, digests in fixtures.json): decoded
+    pixels are the real Poppler pages; our PNG must decode to them, carry Pillow's exact filter decisions (sha of the filtered
+    stream, Adler-32), and be no larger than 1.05 x both local Pillow's re-encode and the recorded file."""
+    import os
+    import zlib
+    from oracle import restate as R
+    rec = os.path.join(golden_dir, "_recorded")
+    names = [n for n in fixtures["fixtures"] if os.path.exists(os.path.join(rec, n))]
+    if not names:
+        pytest.skip("recorded PNGs not fetched (python tests/golden/fetch_recorded.py in the build container)")
+    ims = []
+    for n in names:
+        im = Image.open(os.path.join(rec, n)); im.load()
+        ims.append(im)
+    res = V.prepare_pages(ims)
+    tot_ours = tot_pillow = tot_rec = 0
+    for n, im, r in zip(names, ims, res):
+        fx = fixtures["fixtures"][n]
+        assert r.error is None and r.size == tuple(fx["size"])
+        w, h, bd, ct, idat, ok = R.png_split(r.png)
+        assert ok and ct == fx["color_type"]
+        filt = zlib.decompress(b"".join(idat))
+        assert U.sha(filt) == fx["sha_filtered"] and f"{r.adler32:08x}" == fx["adler32"], n
+        dec = Image.open(io.BytesIO(r.png)); dec.load()
+        assert U.sha(dec.tobytes()) == fx["sha_px"], n
+        assert r.b64 == base64.b64encode(r.png)
+        assert len(r.png) <= 1.05 * fx["pillow_png_bytes"] and len(r.png) <= 1.05 * fx["bytes"], (n, len(r.png), fx["pillow_png_bytes"], fx["bytes"])
+        tot_ours += len(r.png); tot_pillow += fx["pillow_png_bytes"]; tot_rec += fx["bytes"]
+    print(f"{len(names)} recorded pages: ours {tot_ours} B, local Pillow {tot_pillow} B ({tot_ours / tot_pillow:.3f}), recorded files {tot_rec} B ({tot_ours / tot_rec:.3f})")
