@@ -278,3 +278,15 @@ def test_all_recorded_reference_pages(V, fixtures, golden_dir):
         assert len(r.png) <= 1.05 * fx["pillow_png_bytes"] and len(r.png) <= 1.05 * fx["bytes"], (n, len(r.png), fx["pillow_png_bytes"], fx["bytes"])
         tot_ours += len(r.png); tot_pillow += fx["pillow_png_bytes"]; tot_rec += fx["bytes"]
     print(f"{len(names)} recorded pages: ours {tot_ours} B, local Pillow {tot_pillow} B ({tot_ours / tot_pillow:.3f}), recorded files {tot_rec} B ({tot_ours / tot_rec:.3f})")
+
+
+def test_all_gpus_in_one_process(V, synth):
+    """Page ranges over every visible GPU from one process (threads); identical bytes to the single-GPU call, page order kept."""
+    import torch
+    pages = [synth.make_page(i, size=(700 + 20 * (i % 3), 900)) for i in range(9)] + [b"junk"]
+    ref = V.prepare_pages(pages)
+    got = V.prepare_pages_all_gpus(pages)
+    assert [r.png for r in got] == [r.png for r in ref] and got[-1].error
+    if torch.cuda.device_count() >= 2:
+        got2 = V.prepare_pages_all_gpus(pages, devices=[1, 0])
+        assert [r.png for r in got2] == [r.png for r in ref]

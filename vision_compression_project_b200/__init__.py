@@ -7,5 +7,7 @@ calling `prepare_page(s)` without the built library or without a B200 raises.
 from .api import (BICUBIC, BILINEAR, BOX, HAMMING, LANCZOS, PagePrep, PreparedPage, parse_pnm, prepare_page,
                   prepare_pages, split_pnm_stream, thumbnail_size)
 
-__all__ = ["prepare_page", "prepare_pages", "PagePrep", "PreparedPage", "thumbnail_size", "parse_pnm", "split_pnm_stream",
+from .sharding import prepare_pages_all_gpus  # noqa: E402
+
+__all__ = ["prepare_pages_all_gpus", "prepare_page", "prepare_pages", "PagePrep", "PreparedPage", "thumbnail_size", "parse_pnm", "split_pnm_stream",
            "LANCZOS", "BILINEAR", "BICUBIC", "BOX", "HAMMING"]

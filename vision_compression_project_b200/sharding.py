@@ -44,6 +44,44 @@ def prepare_pages_sharded(images: Sequence, rank: int, world: int, device: int |
     return lo, prepare_pages(images[lo:hi], device=rank if device is None else device, **kw)
 
 
+def prepare_pages_all_gpus(images: Sequence, devices: Sequence[int] | None = None, **kw) -> list:
+    """One process, every GPU of the box: contiguous page ranges (balanced by W*H*C), one host thread per device (the C ABI
+    releases the GIL), results back in page order.  No exchange between devices — the multi-GPU analogue of the reference's
+    page pool (pdf_extract.py:313-350)."""
+    import threading
+    import torch
+    from .api import _as_source, prepare_pages
+    if devices is None:
+        devices = list(range(torch.cuda.device_count()))
+    if not devices:
+        raise RuntimeError("no CUDA device")
+    if len(devices) == 1 or len(images) <= 1:
+        return prepare_pages(images, device=devices[0], **kw)
+
+    def weight(im):
+        try:
+            s = _as_source(im, kw.get("raw_shape"))
+            return s.w * s.h * s.c
+        except (ValueError, TypeError):
+            return 1
+    ranges = balanced_ranges([weight(im) for im in images], len(devices))
+    out: list = [None] * len(images)
+    errs: list = []
+
+    def work(dev, lo, hi):
+        try:
+            if hi > lo:
+                out[lo:hi] = prepare_pages(images[lo:hi], device=dev, **kw)
+        except BaseException as e:  # noqa: BLE001 - re-raised in the caller
+            errs.append(e)
+    ths = [threading.Thread(target=work, args=(d, lo, hi)) for d, (lo, hi) in zip(devices, ranges)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    if errs:
+        raise errs[0]
+    return out
+
+
 def gather_in_page_order(local: Sequence, lo: int, n_pages: int, group=None) -> list | None:
     """Host-side concatenation of per-rank results in page order on rank 0 (variable-length byte strings; this is
     control-plane traffic over the default process group, not a data-path collective)."""
