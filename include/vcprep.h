@@ -12,8 +12,8 @@
  *
  * Plain C: POD structs, raw pointers and sizes only.  Every function returns 0 or a negative VCP_E*;
  * the message of the last error on the calling thread is vcp_last_error().
- * A handle owns one CUDA stream and its scratch arena; calls on one handle are serialised by a mutex,
- * different handles are independent (the reference calls the path from 5 threads: pdf_extract.py:313-333).
+ * A handle owns four lanes (CUDA stream + device arena + pinned staging each; host batches rotate over them so copies and
+ * kernels overlap); calls on one handle are serialised by a mutex, different handles are independent (the reference calls the path from 5 threads: pdf_extract.py:313-333).
  */
 #ifndef VCPREP_H
 #define VCPREP_H

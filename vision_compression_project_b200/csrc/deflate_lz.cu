@@ -6,23 +6,25 @@
 // validity and size <= 1.05 x Pillow's default); tests compare the token stream
 // bit-for-bit with the sequential model in tests/model/deflate_model.c and inflate the result with zlib.
 //
-// Decomposition: the filtered stream of a page is cut into 32 KiB sub-chunks, one WARP each.  A warp
-// owns two small hash tables in shared memory (3-byte hash: 2^11 buckets x 2 ways, 4-byte hash: 2^10 x 2,
-// u16 positions relative to sub-chunk start - 32 KiB, so the previous 32 KiB of the page are addressable
-// history and are inserted before the sub-chunk starts).  It then walks its sub-chunk in windows of 32
-// positions, one per lane:
+// Decomposition: the filtered stream of a page is cut into 32 KiB sub-chunks, one WARP each (persistent warps pull
+// sub-chunks from a work queue in stream order).  A warp owns two small hash tables in shared memory (3-byte and
+// 4-byte keys, 2^10 buckets x 2 ways each, u16 positions relative to sub-chunk start - 32 KiB, so the previous 32 KiB
+// of the page are addressable history and are inserted before the sub-chunk starts; 9.25 KB per warp -> 22 warps/SM).
+// It then walks its sub-chunk in windows of 32 positions, one per lane:
 //   1. the stream is pulled through three 128-byte register chunks per warp (current, next, prefetched), so a
 //      window's bytes come from shuffles and the global-load latency is hidden behind the previous windows;
-//   2. every lane proposes a match: distance-1 and distance-bpp runs from two 64-bit ballot masks,
-//      up to four hash candidates verified against global memory — all four are loaded at once, 16 bytes per
-//      round trip, in lock-step (exact up to 64 bytes);
-//      short matches are priced against literals with the running histogram (quarter-bit log2);
-//   3. one-step lazy rule between neighbouring lanes (a shuffle), greedy parse from lane 0 resolved by
-//      5 rounds of pointer jumping, last token extended cooperatively to <= 258; a maximal distance-1 run is
-//      measured 1 KiB per round trip and emitted as a burst of 258-tokens without re-hashing;
+//   2. every lane proposes a match: distance-1 and distance-bpp runs from two 64-bit ballot masks; four table
+//      candidates and the byte one filtered row up, compared 16 bytes deep (first 4, then 12, the loads of a
+//      stage issued together); fully compared candidates are ranked by one packed key, the ones that hit the
+//      16-byte cap are only remembered; short matches are priced against literals with the running histogram;
+//   3. one-step lazy rule between neighbouring lanes (a shuffle); greedy parse from lane 0 by 5 rounds of pointer
+//      jumping; when the parse starts a token on a lane with capped candidates, all of them are measured to the
+//      258-byte limit cooperatively (128 bytes of every candidate in one round trip), the best wins, and the parse
+//      is redone from there (at most two or three times per window); a maximal distance-1 run is measured 1 KiB
+//      per round trip and emitted as a burst of 258-tokens without re-hashing;
 //   4. tokens written compactly (rank = popc of the selection mask), histogram by shared atomics,
 //      window positions inserted with atomicMax (highest position wins -> deterministic).
-// Integer/latency bound, not HBM bound: the stream is read ~once from L2/HBM; see DESIGN.md §5.
+// Integer-issue / latency bound, not HBM bound: the stream is read ~once from L2/HBM; see DESIGN.md §4.
 #include "vcp_internal.cuh"
 #include <algorithm>
 
