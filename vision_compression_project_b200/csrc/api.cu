@@ -278,6 +278,8 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     const size_t o_sub_ntok = bump.take((size_t)nsub * 4 + 4);
     const size_t o_sub_hist = bump.take((size_t)nsub * kHistSize * 4 + 4);
     const size_t o_row_adler = bump.take((size_t)nrows * 4 + 4);
+    const size_t o_row_busy = bump.take((size_t)nrows + 4);
+    const size_t o_lz_order = bump.take((size_t)nsub * 4 + 4);
     const size_t o_page_adler = bump.take((size_t)n * 4);
     const size_t o_blk_code = bump.take((size_t)nblocks * kCodeStride * 2 + 4);
     const size_t o_blk_clen = bump.take((size_t)nblocks * kCodeStride + 4);
@@ -380,6 +382,8 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     B.sub_ntok = reinterpret_cast<uint32_t*>(A + o_sub_ntok);
     B.sub_hist = reinterpret_cast<uint32_t*>(A + o_sub_hist);
     B.row_adler = reinterpret_cast<uint32_t*>(A + o_row_adler);
+    B.row_busy = stream_in ? nullptr : A + o_row_busy;
+    B.lz_order = (stream_in || nsub < 4096) ? nullptr : reinterpret_cast<uint32_t*>(A + o_lz_order);   // small sets: order does not matter
     B.blk_code = reinterpret_cast<uint16_t*>(A + o_blk_code);
     B.blk_clen = A + o_blk_clen;
     B.blk_hdr = A + o_blk_hdr;
@@ -454,7 +458,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     }
     CU(cudaEventRecord(L.ev[EV_PIXEL], st));
     if (!stream_in) {
-        launches += launch_png_filter(B.pages, n, max_h, max_wc, o.optimize, B.row_adler, st);
+        launches += launch_png_filter(B.pages, n, max_h, max_wc, o.optimize, B.row_adler, B.row_busy, st);
         launches += launch_adler_combine(B.pages, n, B.row_adler, B.page_adler, st);
     } else {
         for (int i = 0; i < n; i++)     // stage-level: Adler-32 of a given stream (scratch: row_adler is unused here)
@@ -462,7 +466,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
                                           reinterpret_cast<uint32_t*>(A + o_tokens), B.page_adler + i, st);
     }
     CU(cudaEventRecord(L.ev[EV_FILTER], st));
-    if (need_lz) launches += launch_lz(B, st);
+    if (need_lz) { launches += launch_lz_order(B, st); launches += launch_lz(B, st); }
     CU(cudaEventRecord(L.ev[EV_LZ], st));
     if (need_huff) {
         launches += launch_huff_build(B, st);

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     if (lane == 0) item = (int)atomicAdd(&B.counters[0], 1u);
     item = __shfl_sync(kFull, item, 0);
     if (item >= B.nitems) return;
+    if (B.lz_order) item = (int)B.lz_order[item];                             // heaviest sub-chunks first: the queue drains into cheap ones
     const int sub_first = (int)B.item2sub[item];
     const int sub_count = (item + 1 < B.nitems ? (int)B.item2sub[item + 1] : B.nsub) - sub_first;
    for (int si = 0; si < sub_count; si++) {
@@ -510,6 +511,40 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     __syncwarp();
    }
   }
+}
+
+// Work items sorted by a cost hint, heaviest first (longest-processing-time-first scheduling): a sub-chunk costs roughly in
+// proportion to the rows with content it covers (blank rows are one long run).  Counting sort with 9 keys in one CTA; the order
+// inside a key is arbitrary — it only changes scheduling, never the output.
+__global__ void __launch_bounds__(1024) k_lz_order(BatchD B) {
+    __shared__ uint32_t cnt[9], cur[9];
+    if (threadIdx.x < 9) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    auto key_of = [&](int item) -> int {
+        const int sub = (int)B.item2sub[item];
+        const BlockD& blk = B.blocks[B.sub2blk[sub]];
+        const PageD& pg = B.pages[blk.page];
+        const long long rowlen = 1 + (long long)pg.w * pg.c;
+        const long long s = blk.start + (long long)(sub - blk.sub0) * kSubBytes;
+        const long long e0 = s + (long long)kSubBytes, e1 = (long long)(blk.start + blk.len);
+        const long long e = e0 < e1 ? e0 : e1;
+        const int y0 = (int)(s / rowlen), y1 = (int)((e - 1) / rowlen);
+        const int n = y1 - y0 + 1, step = max(1, n / 8);
+        int busy = 0, seen = 0;
+        for (int y = y0; y <= y1 && seen < 8; y += step, seen++) busy += B.row_busy[pg.row0 + y];
+        return seen ? (busy * 8 + seen - 1) / seen : 0;                       // 0..8
+    };
+    for (int i = threadIdx.x; i < B.nitems; i += blockDim.x) atomicAdd(&cnt[key_of(i)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t o = 0; for (int k = 8; k >= 0; k--) { cur[k] = o; o += cnt[k]; } }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B.nitems; i += blockDim.x) B.lz_order[atomicAdd(&cur[key_of(i)], 1u)] = (uint32_t)i;
+}
+
+int launch_lz_order(const BatchD& b, cudaStream_t st) {
+    if (b.nitems == 0 || !b.lz_order || !b.row_busy) return 0;
+    k_lz_order<<<1, 1024, 0, st>>>(b);
+    return 1;
 }
 
 int launch_lz(const BatchD& b, cudaStream_t st) {

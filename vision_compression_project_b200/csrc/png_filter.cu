@@ -101,7 +101,7 @@ __device__ __forceinline__ void load_chunk(const uint32_t* sm, int o, int i, uin
 
 // dynamic smem: 3 row buffers (prev / cur rotate, out) of `words` words each; words = (max_rowbytes + 64) / 4 rounded to 4
 __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict__ pages, int optimize,
-                                                         uint32_t* __restrict__ row_adler, int words) {
+                                                         uint32_t* __restrict__ row_adler, uint8_t* __restrict__ row_busy, int words) {
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t red[5][kThreads / 32];
     __shared__ uint32_t red2[2][kThreads / 32];
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict
             for (int j = 1; j < 5; j++) { diff |= c[j] ^ p[j]; nonzero |= c[j]; }   // bytes past the row are zero in both
         }
         const int any_diff = __syncthreads_or((int)diff);
+        if (threadIdx.x == 0 && row_busy) row_busy[P.row0 + y] = any_diff ? 1 : 0;      // cost hint for the LZ work queue
         int ftype;
         if (!any_diff) {
             const int any_nz = __syncthreads_or((int)nonzero);
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict
 }
 
 int launch_png_filter(const PageD* d_pages, int npages, int max_h, int max_rowbytes, int optimize,
-                         uint32_t* row_adler, cudaStream_t st) {
+                         uint32_t* row_adler, uint8_t* row_busy, cudaStream_t st) {
     if (npages == 0 || max_h == 0) return 0;
     const int words = ((max_rowbytes + 64) / 4 + 3) & ~3;
     const size_t smem = (size_t)words * 3 * sizeof(uint32_t);
@@ -268,7 +269,7 @@ int launch_png_filter(const PageD* d_pages, int npages, int max_h, int max_rowby
         configured = smem;
     }
     dim3 grid((max_h + kRowsPerCta - 1) / kRowsPerCta, npages);
-    k_png_filter<<<grid, kThreads, smem, st>>>(d_pages, optimize, row_adler, words);
+    k_png_filter<<<grid, kThreads, smem, st>>>(d_pages, optimize, row_adler, row_busy, words);
     return 1;
 }
 

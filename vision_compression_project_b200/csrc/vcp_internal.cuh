@@ -88,7 +88,9 @@ struct BatchD {
     uint64_t* b64_off; uint64_t* b64_len;
     uint64_t* totals;        // [0] = png bytes used, [1] = b64 bytes used
     uint32_t* err;           // [0] != 0: capacity exceeded
-    uint32_t* counters;      // zeroed per launch set: [0] = next LZ sub-chunk (work queue of k_lz)
+    uint32_t* counters;      // zeroed per launch set: [0] = next LZ sub-chunk (work queue of k_lz), [8..24) = scratch of k_lz_order
+    uint8_t* row_busy;       // per row: 1 = the PNG filter found content (0 = identical to the row above), nullptr when unknown
+    uint32_t* lz_order;      // LZ work items sorted by estimated cost, heaviest first (nullptr: stream order)
     int32_t framed;          // 1 = PNG container (sig/IHDR/IDAT/IEND); 0 = bare zlib stream (vcp_deflate)
     int32_t level;           // 0 = stored only
     int32_t want_b64;
@@ -100,7 +102,8 @@ int launch_reduce(const PageD* d_pages, int npages, int max_rh, int max_rw, cuda
 int launch_resample_h(const PageD* d_pages, int npages, int max_rh, int max_w, cudaStream_t st);
 int launch_resample_v(const PageD* d_pages, int npages, int max_h, int max_wc, cudaStream_t st);
 int launch_png_filter(const PageD* d_pages, int npages, int max_h, int max_rowbytes, int optimize,
-                      uint32_t* row_adler, cudaStream_t st);
+                      uint32_t* row_adler, uint8_t* row_busy, cudaStream_t st);
+int launch_lz_order(const BatchD& b, cudaStream_t st);
 int launch_adler_combine(const PageD* d_pages, int npages, const uint32_t* row_adler, uint32_t* page_adler, cudaStream_t st);
 int launch_lz(const BatchD& b, cudaStream_t st);
 int launch_huff_build(const BatchD& b, cudaStream_t st);
