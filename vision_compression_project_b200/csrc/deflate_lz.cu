@@ -514,11 +514,12 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
 }
 
 // Work items sorted by a cost hint, heaviest first (longest-processing-time-first scheduling): a sub-chunk costs roughly in
-// proportion to the rows with content it covers (blank rows are one long run).  Counting sort with 9 keys in one CTA; the order
+// proportion to the rows with content it covers (blank rows are one long run).  Counting sort with 64 keys in one CTA; the order
 // inside a key is arbitrary — it only changes scheduling, never the output.
 __global__ void __launch_bounds__(1024) k_lz_order(BatchD B) {
-    __shared__ uint32_t cnt[9], cur[9];
-    if (threadIdx.x < 9) cnt[threadIdx.x] = 0;
+    constexpr int kKeys = 64;
+    __shared__ uint32_t cnt[kKeys], cur[kKeys];
+    if (threadIdx.x < kKeys) cnt[threadIdx.x] = 0;
     __syncthreads();
     auto key_of = [&](int item) -> int {
         const int sub = (int)B.item2sub[item];
@@ -532,11 +533,11 @@ __global__ void __launch_bounds__(1024) k_lz_order(BatchD B) {
         const int n = y1 - y0 + 1, step = max(1, n / 8);
         int busy = 0, seen = 0;
         for (int y = y0; y <= y1 && seen < 8; y += step, seen++) busy += B.row_busy[pg.row0 + y];
-        return seen ? (busy * 8 + seen - 1) / seen : 0;                       // 0..8
+        return seen ? min(kKeys - 1, (busy * 8 / seen + 31) >> 5) : 0;        // scaled to 8 rows, 64 bins
     };
     for (int i = threadIdx.x; i < B.nitems; i += blockDim.x) atomicAdd(&cnt[key_of(i)], 1u);
     __syncthreads();
-    if (threadIdx.x == 0) { uint32_t o = 0; for (int k = 8; k >= 0; k--) { cur[k] = o; o += cnt[k]; } }
+    if (threadIdx.x == 0) { uint32_t o = 0; for (int k = kKeys - 1; k >= 0; k--) { cur[k] = o; o += cnt[k]; } }
     __syncthreads();
     for (int i = threadIdx.x; i < B.nitems; i += blockDim.x) B.lz_order[atomicAdd(&cur[key_of(i)], 1u)] = (uint32_t)i;
 }

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict
             for (int j = 1; j < 5; j++) { diff |= c[j] ^ p[j]; nonzero |= c[j]; }   // bytes past the row are zero in both
         }
         const int any_diff = __syncthreads_or((int)diff);
-        if (threadIdx.x == 0 && row_busy) row_busy[P.row0 + y] = any_diff ? 1 : 0;      // cost hint for the LZ work queue
+        if (threadIdx.x == 0 && row_busy && !any_diff) row_busy[P.row0 + y] = 0;          // cost hint for the LZ work queue
         int ftype;
         if (!any_diff) {
             const int any_nz = __syncthreads_or((int)nonzero);
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kThreads) k_png_filter(const PageD* __restrict
             if (best > 0 && tot[2] < best) { best = tot[2]; ftype = 1; }
             if (optimize && best > 0 && tot[3] < best) { best = tot[3]; ftype = 3; }
             if (best > 0 && tot[4] < best) { best = tot[4]; ftype = 4; }
+            if (threadIdx.x == 0 && row_busy) row_busy[P.row0 + y] = (uint8_t)(1u + min(254u, best >> 9));   // more ink, more LZ work
 
             // ---- pass 2: materialise the winner as words (smo word kLead/4 + g = residual of row bytes 4g..4g+3,
             //      the word in front of it carries the filter byte in its top byte), Adler partials on the way
