@@ -13,7 +13,10 @@ kinds = {
     "noise": lambda i: np.random.default_rng(i).integers(0, 256, (2200, 1700, 3), dtype=np.uint8),
     "smooth": lambda i: (np.add.outer(np.arange(2200) // 3, np.arange(1700) // 2)[:, :, None] + np.array([0, 40, 90])).astype(np.uint8),
 }
+only = sys.argv[1].split(',') if len(sys.argv) > 1 else list(kinds)
 for name, fn in kinds.items():
+    if name not in only:
+        continue
     uniq = [torch.from_numpy(fn(i).copy()).cuda() for i in range(4)]
     dev = [uniq[i % 4] for i in range(n)]
     descs = (N.PageDesc * n)()

@@ -191,49 +191,79 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     }
     __syncwarp();
 
-    // ---- prime with the previous 32 KiB of the page: 128 bytes (4 windows) per load, next chunk prefetched.
-    //      Per window the arithmetic is the main loop's insert: the highest lane of a bucket group wins (atomicMax)
-    //      and shifts the bucket once.
+    // ---- prime with the previous 32 KiB of the page.  The history streams through 512-byte register blocks (one uint4 per
+    //      lane, two blocks ahead in flight: priming is bound by bytes in flight, not by instructions).  Per window the
+    //      arithmetic is the main loop's insert: the highest lane of a bucket group wins (atomicMax) and shifts the bucket once.
+    //      A block — or a 128-byte chunk — that is one repeated byte (white paper after filtering: most of a text page) hashes
+    //      every position to the same two buckets: its windows' inserts collapse to one store per table.
     if (si == 0) {
-        const int h0 = max(0, s - kMaxDist);                                     // multiple of 128 (s is a multiple of 32 KiB)
-        uint32_t cw = 0u, cn = 0u;                                               // current chunk, next chunk; a third is in flight
-        if (h0 < s) { cw = __ldg(S32 + (h0 >> 2) + lane); cn = __ldg(S32 + ((h0 + 128) >> 2) + lane); }
-        for (int w0 = h0; w0 < s; w0 += 128) {
-            const uint32_t cf = __ldg(S32 + ((w0 + 256) >> 2) + lane);           // <= 256 bytes past s: inside the stream or its pad
-            // a chunk that is one repeated byte (white paper after filtering: most of a text page) hashes every position
-            // to the same two buckets: the four windows' inserts collapse to one store per table
-            const uint32_t c00 = __shfl_sync(kFull, cw, 0), cn0 = __shfl_sync(kFull, cn, 0);
-            if (__all_sync(kFull, cw == c00) && c00 == __funnelshift_l(c00, c00, 8) && cn0 == c00 && w0 + 132 <= F) {
+        const int h0 = max(0, s - kMaxDist);                                     // multiple of 512 (s is a multiple of 32 KiB)
+        const uint4* __restrict__ S128 = reinterpret_cast<const uint4*>(S);
+        uint4 bc = make_uint4(0, 0, 0, 0), bn = bc;
+        if (h0 < s) { bc = __ldg(S128 + (h0 >> 4) + lane); bn = __ldg(S128 + ((h0 + 512) >> 4) + lane); }
+        for (int b0 = h0; b0 < s; b0 += 512) {
+            const uint4 bf = __ldg(S128 + ((b0 + 1024) >> 4) + lane);            // <= 1.5 KiB past s: inside the stream or its pad
+            const uint32_t c00 = __shfl_sync(kFull, bc.x, 0), n00 = __shfl_sync(kFull, bn.x, 0);
+            if (__all_sync(kFull, bc.x == c00 && bc.y == c00 && bc.z == c00 && bc.w == c00) && c00 == __funnelshift_l(c00, c00, 8) &&
+                n00 == c00 && b0 + 516 <= F) {
                 if (lane == 0) {
                     const uint32_t h3 = ((c00 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
                     const uint32_t h6 = (c00 * 0x9E3779B1u) >> (32 - HB6);
-                    const uint32_t v = ((uint32_t)(w0 + 127 - base) << 16) | (uint32_t)(w0 + 95 - base);
+                    const uint32_t v = ((uint32_t)(b0 + 511 - base) << 16) | (uint32_t)(b0 + 479 - base);
                     M.t3[h3] = v; M.t6[h6] = v;
                 }
                 __syncwarp();
-                cw = cn; cn = cf;
+                bc = bn; bn = bf;
                 continue;
             }
-            const int sh = (lane & 3) * 8;
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int i = 8 * t + (lane >> 2);
-                const uint32_t a0 = __shfl_sync(kFull, cw, i);
-                uint32_t a1 = __shfl_sync(kFull, cw, (i + 1) & 31);
-                if (t == 3) { const uint32_t b1 = __shfl_sync(kFull, cn, (i + 1) & 31); if (i + 1 >= 32) a1 = b1; }
-                const uint32_t cur4 = __funnelshift_r(a0, a1, sh);
-                const int q = w0 + 32 * t + lane;
-                const bool ok3 = q + 2 < F, ok6 = q + kH2Bytes <= F;
-                const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
-                const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
-                const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
-                __syncwarp();
-                const uint32_t pos = (uint32_t)(q - base);
-                if (ok3) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
-                if (ok6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
-                __syncwarp();
+            for (int kc = 0; kc < 4; kc++) {
+                // words 32*kc + lane (this chunk) and 32*(kc+1) + lane (the next one) of the block
+                const int w0 = b0 + 128 * kc;
+                const int src = 8 * kc + (lane >> 2), srcn = (8 * (kc + 1) + (lane >> 2)) & 31;
+                const uint4& nb = kc < 3 ? bc : bn;
+                uint32_t cw, cn;
+                {
+                    const uint32_t v0 = __shfl_sync(kFull, bc.x, src), v1 = __shfl_sync(kFull, bc.y, src);
+                    const uint32_t v2 = __shfl_sync(kFull, bc.z, src), v3 = __shfl_sync(kFull, bc.w, src);
+                    const uint32_t u0 = __shfl_sync(kFull, nb.x, srcn), u1 = __shfl_sync(kFull, nb.y, srcn);
+                    const uint32_t u2 = __shfl_sync(kFull, nb.z, srcn), u3 = __shfl_sync(kFull, nb.w, srcn);
+                    const int cmp = lane & 3;
+                    cw = cmp == 0 ? v0 : cmp == 1 ? v1 : cmp == 2 ? v2 : v3;
+                    cn = cmp == 0 ? u0 : cmp == 1 ? u1 : cmp == 2 ? u2 : u3;
+                }
+                const uint32_t k00 = __shfl_sync(kFull, cw, 0), kn0 = __shfl_sync(kFull, cn, 0);
+                if (__all_sync(kFull, cw == k00) && k00 == __funnelshift_l(k00, k00, 8) && kn0 == k00 && w0 + 132 <= F) {
+                    if (lane == 0) {
+                        const uint32_t h3 = ((k00 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
+                        const uint32_t h6 = (k00 * 0x9E3779B1u) >> (32 - HB6);
+                        const uint32_t v = ((uint32_t)(w0 + 127 - base) << 16) | (uint32_t)(w0 + 95 - base);
+                        M.t3[h3] = v; M.t6[h6] = v;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                const int sh = (lane & 3) * 8;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int i = 8 * t + (lane >> 2);
+                    const uint32_t a0 = __shfl_sync(kFull, cw, i);
+                    uint32_t a1 = __shfl_sync(kFull, cw, (i + 1) & 31);
+                    if (t == 3) { const uint32_t b1 = __shfl_sync(kFull, cn, (i + 1) & 31); if (i + 1 >= 32) a1 = b1; }
+                    const uint32_t cur4 = __funnelshift_r(a0, a1, sh);
+                    const int q = w0 + 32 * t + lane;
+                    const bool ok3 = q + 2 < F, ok6 = q + kH2Bytes <= F;
+                    const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
+                    const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
+                    const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
+                    __syncwarp();
+                    const uint32_t pos = (uint32_t)(q - base);
+                    if (ok3) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
+                    if (ok6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
+                    __syncwarp();
+                }
             }
-            cw = cn; cn = cf;
+            bc = bn; bn = bf;
         }
     }
 
