@@ -279,7 +279,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     const size_t o_sub_hist = bump.take((size_t)nsub * kHistSize * 4 + 4);
     const size_t o_row_adler = bump.take((size_t)nrows * 4 + 4);
     const size_t o_row_busy = bump.take((size_t)nrows + 4);
-    const size_t o_lz_order = bump.take((size_t)nsub * 4 + 4);
+    const size_t o_lz_order = bump.take((size_t)nsub * 5 + 8);        // u32 order + u8 keys
     const size_t o_page_adler = bump.take((size_t)n * 4);
     const size_t o_blk_code = bump.take((size_t)nblocks * kCodeStride * 2 + 4);
     const size_t o_blk_clen = bump.take((size_t)nblocks * kCodeStride + 4);
@@ -294,7 +294,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     // results block (copied down in one piece): png_off[n] png_len[n] b64_off[n] b64_len[n] totals[2] adler[n] err[2]
     const size_t res_bytes = (size_t)n * 8 * 4 + 16 + align_up((size_t)n * 4, 8) + 8;
     const size_t o_res = bump.take(res_bytes);
-    const size_t o_cnt = bump.take(256);
+    const size_t o_cnt = bump.take(1024);
     const size_t o_png = need_huff ? bump.take((size_t)png_cap + 64) : kNone;
     const size_t o_b64 = (need_huff && o.want_b64) ? bump.take((size_t)b64_cap + 64) : kNone;
     const size_t o_coeff = bump.take(coeff_blob.size() * 4 + 4);
@@ -409,7 +409,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     uint64_t launches = 0;
     CU(cudaEventRecord(L.ev[EV_START], st));
     CU(cudaMemcpyAsync(A + o_coeff, M, desc_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(R, 0, (o_cnt + 256) - o_res, st));
+    CU(cudaMemsetAsync(R, 0, (o_cnt + 1024) - o_res, st));
     if (!stream_in && !o.src_device) {
         // Pinned (or registered) sources are DMA'd where they lie.  Pageable ones — e.g. Pillow's own pixel storage — would make
         // cudaMemcpyAsync stage them on one thread at ~11 GB/s: pack them into the lane's pinned bounce buffer on several host

@@ -544,38 +544,50 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
 }
 
 // Work items sorted by a cost hint, heaviest first (longest-processing-time-first scheduling): a sub-chunk costs roughly in
-// proportion to the rows with content it covers (blank rows are one long run).  Counting sort with 64 keys in one CTA; the order
-// inside a key is arbitrary — it only changes scheduling, never the output.
-__global__ void __launch_bounds__(1024) k_lz_order(BatchD B) {
-    constexpr int kKeys = 64;
-    __shared__ uint32_t cnt[kKeys], cur[kKeys];
-    if (threadIdx.x < kKeys) cnt[threadIdx.x] = 0;
+// proportion to the ink of the rows it covers (the PNG filter's winning |residual| sum; blank rows are one long run).
+// Counting sort with 64 keys: k_lz_keys bins the items (global histogram in B.counters[64..128)), k_lz_scatter places them
+// (cursors in B.counters[128..192)).  The order inside a key is arbitrary — it only changes scheduling, never the output.
+constexpr int kOrderKeys = 64;
+
+__device__ __forceinline__ int lz_item_key(const BatchD& B, int item) {
+    const int sub = (int)B.item2sub[item];
+    const BlockD& blk = B.blocks[B.sub2blk[sub]];
+    const PageD& pg = B.pages[blk.page];
+    const int rowlen = 1 + pg.w * pg.c;
+    const int s = (int)blk.start + (sub - blk.sub0) * kSubBytes;
+    const int e = min(s + kSubBytes, (int)(blk.start + blk.len));
+    const int y0 = s / rowlen, y1 = (e - 1) / rowlen;
+    const int n = y1 - y0 + 1, step = max(1, n / 8);
+    int busy = 0, seen = 0;
+    for (int y = y0; y <= y1 && seen < 8; y += step, seen++) busy += B.row_busy[pg.row0 + y];
+    return seen ? min(kOrderKeys - 1, (busy * 8 / seen + 31) >> 5) : 0;       // scaled to 8 rows
+}
+
+__global__ void __launch_bounds__(256) k_lz_keys(BatchD B, uint8_t* __restrict__ keys) {
+    __shared__ uint32_t cnt[kOrderKeys];
+    if (threadIdx.x < kOrderKeys) cnt[threadIdx.x] = 0;
     __syncthreads();
-    auto key_of = [&](int item) -> int {
-        const int sub = (int)B.item2sub[item];
-        const BlockD& blk = B.blocks[B.sub2blk[sub]];
-        const PageD& pg = B.pages[blk.page];
-        const long long rowlen = 1 + (long long)pg.w * pg.c;
-        const long long s = blk.start + (long long)(sub - blk.sub0) * kSubBytes;
-        const long long e0 = s + (long long)kSubBytes, e1 = (long long)(blk.start + blk.len);
-        const long long e = e0 < e1 ? e0 : e1;
-        const int y0 = (int)(s / rowlen), y1 = (int)((e - 1) / rowlen);
-        const int n = y1 - y0 + 1, step = max(1, n / 8);
-        int busy = 0, seen = 0;
-        for (int y = y0; y <= y1 && seen < 8; y += step, seen++) busy += B.row_busy[pg.row0 + y];
-        return seen ? min(kKeys - 1, (busy * 8 / seen + 31) >> 5) : 0;        // scaled to 8 rows, 64 bins
-    };
-    for (int i = threadIdx.x; i < B.nitems; i += blockDim.x) atomicAdd(&cnt[key_of(i)], 1u);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.nitems) { const int k = lz_item_key(B, i); keys[i] = (uint8_t)k; atomicAdd(&cnt[k], 1u); }
     __syncthreads();
-    if (threadIdx.x == 0) { uint32_t o = 0; for (int k = kKeys - 1; k >= 0; k--) { cur[k] = o; o += cnt[k]; } }
+    if (threadIdx.x < kOrderKeys && cnt[threadIdx.x]) atomicAdd(&B.counters[64 + threadIdx.x], cnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_lz_scatter(BatchD B, const uint8_t* __restrict__ keys) {
+    __shared__ uint32_t first[kOrderKeys];                  // first slot of every key, heaviest key first
+    if (threadIdx.x == 0) { uint32_t o = 0; for (int k = kOrderKeys - 1; k >= 0; k--) { first[k] = o; o += B.counters[64 + k]; } }
     __syncthreads();
-    for (int i = threadIdx.x; i < B.nitems; i += blockDim.x) B.lz_order[atomicAdd(&cur[key_of(i)], 1u)] = (uint32_t)i;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B.nitems) { const int k = keys[i]; B.lz_order[first[k] + atomicAdd(&B.counters[128 + k], 1u)] = (uint32_t)i; }
 }
 
 int launch_lz_order(const BatchD& b, cudaStream_t st) {
     if (b.nitems == 0 || !b.lz_order || !b.row_busy) return 0;
-    k_lz_order<<<1, 1024, 0, st>>>(b);
-    return 1;
+    uint8_t* keys = reinterpret_cast<uint8_t*>(b.lz_order + b.nitems);         // the order buffer has room for the keys behind it
+    const int ctas = (b.nitems + 255) / 256;
+    k_lz_keys<<<ctas, 256, 0, st>>>(b, keys);
+    k_lz_scatter<<<ctas, 256, 0, st>>>(b, keys);
+    return 2;
 }
 
 int launch_lz(const BatchD& b, cudaStream_t st) {

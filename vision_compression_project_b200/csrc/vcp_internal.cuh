@@ -88,7 +88,7 @@ struct BatchD {
     uint64_t* b64_off; uint64_t* b64_len;
     uint64_t* totals;        // [0] = png bytes used, [1] = b64 bytes used
     uint32_t* err;           // [0] != 0: capacity exceeded
-    uint32_t* counters;      // zeroed per launch set: [0] = next LZ sub-chunk (work queue of k_lz), [8..24) = scratch of k_lz_order
+    uint32_t* counters;      // zeroed per launch set: [0] = next LZ sub-chunk (work queue of k_lz), [64..192) = histogram and cursors of the work-item sort
     uint8_t* row_busy;       // per row: 1 = the PNG filter found content (0 = identical to the row above), nullptr when unknown
     uint32_t* lz_order;      // LZ work items sorted by estimated cost, heaviest first (nullptr: stream order)
     int32_t framed;          // 1 = PNG container (sig/IHDR/IDAT/IEND); 0 = bare zlib stream (vcp_deflate)
