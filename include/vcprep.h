@@ -58,7 +58,8 @@ typedef struct {
 typedef struct {
     int32_t out_channels;   /* 3 = convert('RGB'), 1 = convert('L')                                  */
     int32_t resample;       /* VCP_LANCZOS ...                                                        */
-    int32_t compress_level; /* 0 = stored blocks (Pillow compress_level=0); otherwise GPU deflate     */
+    int32_t compress_level; /* Pillow's compress_level: 0 = stored blocks; 1-3 fast, 4-6 default,      */
+                            /* 7-9 best effort class of the GPU deflate (size/speed trade like zlib's)  */
     int32_t optimize;       /* 1 = Pillow optimize=True filter rule (Avg candidate included)          */
     int32_t want_b64;       /* 1 = also produce base64.b64encode(png)                                 */
     int32_t src_device;     /* 1 = page src pointers are device pointers (no H2D)                     */

@@ -124,7 +124,7 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
     int64_t p = s;
     int score = 0;                     /* EMA of literal tokens per window (x8) */
     while (p < e) {
-        const int noisy = P->noisy_thresh > 0 && score >= P->noisy_thresh;
+        const int noisy = P->noisy_thresh < 0 || (P->noisy_thresh > 0 && score >= P->noisy_thresh);   /* < 0: always */
         uint32_t hsnap[316]; memcpy(hsnap, hist, sizeof hsnap);   /* costs use the counts as of the window start */
         uint32_t Ntok = (uint32_t)ntok;
         int nlit = 0;

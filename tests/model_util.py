@@ -28,6 +28,18 @@ KERNEL_PARAMS = dict(bpp=3, hash_bits=10, ways=2, lane_cap=16, too_far=32768, la
                      block_bytes=512 * 1024)
 
 
+# effort classes of csrc/deflate_lz.cu (CfgFast / CfgDefault / CfgBest), selected by compress_level
+LEVEL_PARAMS = {
+    "fast": dict(hash_bits=9, hash2_bits=9, noisy_thresh=-1, lazy=0, rowlen=0),
+    "default": {},
+    "best": dict(hash_bits=11, hash2_bits=12, noisy_thresh=0, row_gate=0),
+}
+
+
+def params_for_level(level: int) -> dict:
+    return dict(LEVEL_PARAMS["best" if level >= 7 else "fast" if 1 <= level <= 3 else "default"])
+
+
 def load():
     if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
         subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-o", SO, SRC], check=True)

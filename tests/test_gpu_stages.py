@@ -191,3 +191,24 @@ def test_deflate_bytes_match_sequential_model(S, ref_page):
         z = S.deflate(d, bpp=3)
         zm, st = M.deflate(lib, d)
         assert z == zm, (name, len(z), len(zm))
+
+
+def test_effort_classes_match_model_and_order_by_size(S, ref_page):
+    """compress_level 1-3 / 4-6 / 7-9 select the fast / default / best instantiation of the LZ kernel: each equals its model
+    configuration byte for byte, every stream inflates, and on page rows more effort never gives a larger stream."""
+    lib = M.load()
+    streams = _streams(ref_page)
+    sizes = {}
+    for level in (2, 6, 9):
+        for name in ("abc", "lowent600k", "page_rows", "z524289"):
+            d = streams[name]
+            z = S.deflate(d, bpp=3, level=level)
+            assert zlib.decompress(z) == d, (level, name)
+            kw = M.params_for_level(level)
+            if "rowlen" not in kw:
+                kw["rowlen"] = -1
+            zm, _ = M.deflate(lib, d, **kw)
+            assert z == zm, (level, name, len(z), len(zm))
+            sizes[(level, name)] = len(z)
+    assert sizes[(9, "page_rows")] <= sizes[(6, "page_rows")] <= sizes[(2, "page_rows")]
+    print({k: v for k, v in sizes.items() if k[1] == "page_rows"})

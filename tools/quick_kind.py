@@ -22,7 +22,7 @@ for name, fn in kinds.items():
     descs = (N.PageDesc * n)()
     for d, t in zip(descs, dev):
         d.src, d.width, d.height, d.channels = t.data_ptr(), t.shape[1], t.shape[0], 3
-    o = N.Opts(); o.out_channels = 3; o.compress_level = 6; o.want_b64 = 1; o.src_device = 1; o.dst_device = 1
+    o = N.Opts(); o.out_channels = 3; o.compress_level = int(__import__('os').environ.get('LEVEL', '6')); o.want_b64 = 1; o.src_device = 1; o.dst_device = 1
     bp, bb = e.output_bound(descs, n, o)
     op = torch.empty(bp, dtype=torch.uint8, device="cuda"); ob = torch.empty(bb, dtype=torch.uint8, device="cuda")
     for it in range(3):

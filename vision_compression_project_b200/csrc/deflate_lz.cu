@@ -32,20 +32,25 @@ namespace vcp {
 
 namespace {
 
-constexpr int HB3 = 10;               // 3-byte-hash table: 2^10 buckets, u32 = (newest<<16) | older
-constexpr int HB6 = 10;               // 4-byte-hash table: 2^10 buckets, same bucket format
+// Effort classes, selected by Pillow's compress_level (1-3 fast, 4-6 default, 7-9 best).  Each is one instantiation of k_lz.
+//   HB3 / HB6   log2 buckets of the 3-byte / 4-byte hash tables (u32 bucket = (newest << 16) | older)
+//   NOISY       literal EMA (8 x literals per window) from which only the newest way of each table is verified
+//   LAZY        one-step lazy rule applies to matches shorter than this (0 = greedy)
+//   PROBE       row-above candidate: 0 none, 1 only where a run starts, 2 everywhere
+struct CfgFast    { static constexpr int HB3 = 9,  HB6 = 9,  NOISY = 0,          LAZY = 0,  PROBE = 0; };
+struct CfgDefault { static constexpr int HB3 = 10, HB6 = 10, NOISY = 160,        LAZY = 16, PROBE = 1; };
+struct CfgBest    { static constexpr int HB3 = 11, HB6 = 12, NOISY = 0x7fffffff, LAZY = 16, PROBE = 2; };
 constexpr int kH2Bytes = 4;           // bytes keyed by the second table
 constexpr int kLzWarps = 2;           // warps (= sub-chunks) per CTA
 constexpr int kLaneCap = 16;          // compare depth of a hash candidate inside a lane (deeper only for tokens the parse selects)
-constexpr int kLazyMax = 16;
 constexpr int kCostMaxLen = 8;
 constexpr int kCostWarm = 64;
-constexpr int kNoisy = 160;            // literal EMA (8 x literals per window) at which only the newest way of each table is verified
 constexpr unsigned kFull = 0xffffffffu;
 
+template <class Cfg>
 struct __align__(16) WarpMem {
-    uint32_t t3[1 << HB3];
-    uint32_t t6[1 << HB6];
+    uint32_t t3[1 << Cfg::HB3];
+    uint32_t t6[1 << Cfg::HB6];
     uint32_t hist[320];
 };
 
@@ -140,7 +145,10 @@ __device__ __forceinline__ int run_end(const uint8_t* __restrict__ S, int from, 
 
 }  // namespace
 
+template <class Cfg>
 __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
+    constexpr int HB3 = Cfg::HB3, HB6 = Cfg::HB6;
+    using WarpMem = vcp::WarpMem<Cfg>;
     extern __shared__ __align__(16) unsigned char lz_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpMem& M = reinterpret_cast<WarpMem*>(lz_smem)[warp];
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             if (!capm) {                                                          // a capped run outranks every hash candidate
                 const int hcap = min(kLaneCap, limit);
                 const bool ok6 = q + kH2Bytes <= F;
-                const bool noisy = score >= kNoisy;                               // literal-dense stretch: older ways rarely pay for their loads
+                const bool noisy = score >= Cfg::NOISY;                               // literal-dense stretch: older ways rarely pay for their loads
                 int clen[5]; bool live[5];
 #pragma unroll
                 for (int w = 0; w < 5; w++) {
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                     const int cp = w < 4 ? base + (int)cnd : q - rowlen;
                     const int d = q - cp;
                     live[w] = w < 4 ? (cnd != 0 && (w < 2 || ok6) && d > 0 && d <= kMaxDist && !(noisy && (w & 1)))
-                                    : (rowlen <= kMaxDist && cp >= 0 && !e1a);   // only where a run starts: inside a run distance 1 already serves
+                                    : (Cfg::PROBE != 0 && rowlen <= kMaxDist && cp >= 0 && (Cfg::PROBE == 2 || !e1a));   // default: only where a run starts (inside a run distance 1 already serves)
                     cpos[w] = live[w] ? cp : q;
                     clen[w] = 0;
                 }
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
         // ---- one-step lazy rule between neighbouring lanes
         {
             const int nxt = __shfl_down_sync(kFull, bl, 1);
-            if (lane < 31 && bl >= 3 && bl < kLazyMax && nxt > bl) { bl = 0; bd = 0; }
+            if (lane < 31 && bl >= 3 && bl < Cfg::LAZY && nxt > bl) { bl = 0; bd = 0; }
         }
         // ---- greedy parse from lane 0 by pointer jumping; whenever the parse starts a token on a lane with capped candidates,
         //      those are measured to the end (the best fully compared one competes too) and the parse is redone from there
@@ -590,21 +598,28 @@ int launch_lz_order(const BatchD& b, cudaStream_t st) {
     return 2;
 }
 
-int launch_lz(const BatchD& b, cudaStream_t st) {
-    if (b.nitems == 0) return 0;
-    const size_t smem = sizeof(WarpMem) * kLzWarps;
+template <class Cfg>
+static int launch_lz_cfg(const BatchD& b, cudaStream_t st) {
+    const size_t smem = sizeof(WarpMem<Cfg>) * kLzWarps;
     static int resident = 0;                                  // CTAs the device can hold at once (persistent grid)
     if (!resident) {
-        cudaFuncSetAttribute(k_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_lz<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 0, dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz, kLzWarps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz<Cfg>, kLzWarps * 32, smem);
         resident = std::max(1, per_sm) * sms;
     }
     const int ctas = std::min((b.nitems + kLzWarps - 1) / kLzWarps, resident);
-    k_lz<<<ctas, kLzWarps * 32, smem, st>>>(b);
+    k_lz<Cfg><<<ctas, kLzWarps * 32, smem, st>>>(b);
     return 1;
+}
+
+int launch_lz(const BatchD& b, cudaStream_t st) {
+    if (b.nitems == 0) return 0;
+    if (b.level >= 7) return launch_lz_cfg<CfgBest>(b, st);
+    if (b.level >= 1 && b.level <= 3) return launch_lz_cfg<CfgFast>(b, st);
+    return launch_lz_cfg<CfgDefault>(b, st);                  // 4..6 (and 0: stored blocks are decided later, tokens unused)
 }
 
 }  // namespace vcp
