@@ -113,6 +113,18 @@ int vcp_batch_begin(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_
 int vcp_batch_next(vcp_handle* h, int* first_page, int* last_page);
 int vcp_batch_end(vcp_handle* h);
 
+/* ---- PNG decode (re-reading the images/page_###.png cache of backend/README.md:238-243, and checking
+ * this library's own output at speed).  Replaces Image.open(png).load(): PngImagePlugin chunk parsing, zlib inflate and
+ * libImaging/ZipDecode.c un-filtering.  8-bit gray / gray+alpha / RGB / RGBA, non-interlaced, any zlib stream.
+ * Pixels come out interleaved, W*H*C per page, pages 256-byte aligned inside out_pixels. */
+typedef struct {
+    int32_t status;                    /* VCP_OK or VCP_E* for this PNG                                  */
+    int32_t width, height, channels;
+    uint64_t pix_off, pix_len;         /* byte range inside out_pixels                                   */
+} vcp_decode_result;
+int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs /* host pointers */, const uint64_t* png_lens, int n,
+                         void* out_pixels, uint64_t out_cap, int dst_device, vcp_decode_result* results);
+
 int vcp_get_stats(vcp_handle* h, vcp_stats* out);
 
 /* Host-side helper for language bindings: copy n byte ranges src_base+offs[i] .. +lens[i] into dsts[i] on `threads`

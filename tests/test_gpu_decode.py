@@ -1,0 +1,83 @@
+"""GPU: PNG decode (inflate + un-filter) against Pillow, for this library's PNGs and for Pillow's own."""
+import io
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def V():
+    import vision_compression_project_b200 as v
+    return v
+
+
+def _px(im):
+    a = np.asarray(im)
+    return a.reshape(im.height, im.width, -1)
+
+
+def test_decode_own_pngs_round_trip(V, ref_page):
+    from vision_compression_project_b200 import synth
+    pages = [ref_page, synth.make_page(1, "letter", 200, photo=True), synth.make_page(2, size=(333, 517), mode="L"),
+             Image.fromarray(np.random.default_rng(0).integers(0, 256, (300, 400, 3), dtype=np.uint8), "RGB")]   # incl. stored blocks
+    res = V.prepare_pages(pages, mode=None, want_base64=False)
+    dec = V.decode_pages([r.png for r in res])
+    for im, d in zip(pages, dec):
+        assert not isinstance(d, Exception)
+        assert np.array_equal(d, _px(im))
+    dev = V.decode_pages([res[0].png], to_device=True)[0]
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), _px(ref_page))
+
+
+def test_decode_pillow_pngs_all_filters_and_modes(V):
+    rng = np.random.default_rng(3)
+    pngs, exp = [], []
+    for t in range(40):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        mode = ["L", "RGB", "RGBA", "LA"][t % 4]
+        c = {"L": 1, "LA": 2, "RGB": 3, "RGBA": 4}[mode]
+        kind = t % 3
+        if kind == 0:
+            px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        elif kind == 1:
+            px = np.full((h, w, c), int(rng.integers(0, 256)), np.uint8)
+        else:
+            px = (np.add.outer(np.arange(h) * 3, np.arange(w) * 5)[:, :, None] + np.arange(c) * 17).astype(np.uint8)
+        im = Image.fromarray(px[:, :, 0] if c == 1 else px, mode)
+        kw = [{}, {"optimize": True}, {"compress_level": 0}, {"compress_level": 1}, {"compress_level": 9}][t % 5]
+        pngs.append(U.pillow_png(im, **kw)); exp.append(px)
+    # hand-made streams: fixed-Huffman blocks (zlib picks them for tiny inputs) and every filter type in one image
+    px = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    from oracle import restate as R
+    rows = []
+    for y in range(5):
+        prev = px[y - 1].reshape(-1) if y else np.zeros(21, np.uint8)
+        cur = px[y].reshape(-1).astype(np.int32)
+        left = np.concatenate([np.zeros(3, np.int32), cur[:-3]]); ul = np.concatenate([np.zeros(3, np.int32), prev[:-3].astype(np.int32)])
+        pred = [np.zeros(21, np.int32), left, prev.astype(np.int32), (left + prev) >> 1, R._paeth(left, prev, ul)][y]
+        rows.append(bytes([y]) + ((cur - pred) & 255).astype(np.uint8).tobytes())
+    pngs.append(R.png_wrap(7, 5, 3, zlib.compress(b"".join(rows), 9))); exp.append(px)
+    dec = V.decode_pages(pngs)
+    for k, (d, e) in enumerate(zip(dec, exp)):
+        assert not isinstance(d, Exception), k
+        assert np.array_equal(d, e), k
+
+
+def test_decode_recorded_reference_png_and_errors(V, golden_dir, ref_page):
+    import os
+    raw = open(os.path.join(golden_dir, "ref_page_1.png"), "rb").read()        # written by another zlib build (the reference's run)
+    bad_crc_ok = bytearray(raw)
+    trunc = raw[:len(raw) // 2]
+    corrupt = bytearray(raw); corrupt[5000:5040] = bytes(40)
+    dec = V.decode_pages([raw, b"not a png", trunc, bytes(corrupt)])
+    assert np.array_equal(dec[0], _px(ref_page))
+    assert all(isinstance(d, ValueError) for d in dec[1:3])
+    assert isinstance(dec[3], ValueError) or not np.array_equal(dec[3], _px(ref_page))
+    pal = io.BytesIO(); Image.new("P", (4, 4)).save(pal, format="PNG")
+    assert isinstance(V.decode_pages([pal.getvalue()])[0], ValueError)

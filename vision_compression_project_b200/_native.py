@@ -28,6 +28,11 @@ class PageResult(C.Structure):
                 ("adler32", C.c_uint32), ("n_idat", C.c_uint32)]
 
 
+class DecodeResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+                ("pix_off", C.c_uint64), ("pix_len", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_convert", "ms_resample", "ms_filter", "ms_lz", "ms_huff",
                                          "ms_assemble", "ms_b64", "ms_d2h", "ms_total")] + \
@@ -52,6 +57,8 @@ SYMBOLS = {
                                   C.c_void_p, C.c_uint64, C.POINTER(PageResult)]),
     "vcp_batch_next": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vcp_batch_end": (C.c_int, [C.c_void_p]),
+    "vcp_png_decode_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_int, C.c_void_p, C.c_uint64,
+                                       C.c_int, C.POINTER(DecodeResult)]),
     "vcp_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "vcp_host_scatter": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "vcp_convert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int]),

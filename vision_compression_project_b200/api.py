@@ -273,6 +273,43 @@ class PagePrep:
             setattr(self, which, cur)
         return cur
 
+    # ------------------------------------------------------------------ decode
+    def decode_pages(self, pngs: Sequence[bytes], to_device: bool = False) -> list:
+        """PNG bytes -> pixels on the GPU (inflate + un-filter): the reverse of prepare_pages, for re-reading a PNG cache or
+        checking output at speed.  Returns one (H, W, C) uint8 array per PNG (numpy, or CUDA tensors with to_device=True);
+        a PNG that cannot be decoded gives a ValueError instance in its slot."""
+        n = len(pngs)
+        if n == 0:
+            return []
+        bufs = [np.frombuffer(p, np.uint8) for p in pngs]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        lens = (C.c_uint64 * n)(*[b.size for b in bufs])
+        total = 0
+        for b in bufs:                                       # IHDR sits at a fixed place: size the output from it
+            if b.size >= 33:
+                w = int.from_bytes(b[16:20].tobytes(), "big"); h = int.from_bytes(b[20:24].tobytes(), "big")
+                ch = {0: 1, 4: 2, 2: 3, 6: 4}.get(int(b[25]), 4)
+                total += ((w * h * ch + 255) // 256) * 256 if 0 < w < (1 << 24) and 0 < h < (1 << 24) else 0
+        total += 4096
+        if to_device:
+            out = self._torch.empty(total, dtype=self._torch.uint8, device=f"cuda:{self.device}")
+        else:
+            out = self._pinned("_out_png", total)
+        res = (N.DecodeResult * n)()
+        N.check(self.lib.vcp_png_decode_batch(self.handle, ptrs, lens, n, out.data_ptr(), out.numel(), int(to_device), res))
+        result = []
+        host = None if to_device else out.numpy()
+        for r in res:
+            if r.status != 0:
+                result.append(ValueError("PNG rejected by libvcprep (unsupported or corrupt)"))
+                continue
+            shape = (r.height, r.width, r.channels)
+            if to_device:
+                result.append(out[r.pix_off:r.pix_off + r.pix_len].view(shape))
+            else:
+                result.append(host[r.pix_off:r.pix_off + r.pix_len].reshape(shape).copy())
+        return result
+
     # ------------------------------------------------------------------ planning
     @staticmethod
     def _plan(src: _Source, size, max_side, mode, resample, reducing_gap) -> N.PageDesc:
@@ -440,6 +477,15 @@ def prepare_pages(images: Sequence[Any], *, device: int = 0, **kw) -> List[Prepa
     eng = _pool.borrow(device)
     try:
         return eng.prepare_pages(images, **kw)
+    finally:
+        _pool.give_back(eng)
+
+
+def decode_pages(pngs: Sequence[bytes], *, device: int = 0, to_device: bool = False) -> list:
+    """GPU PNG decode of a batch (see PagePrep.decode_pages)."""
+    eng = _pool.borrow(device)
+    try:
+        return eng.decode_pages(pngs, to_device=to_device)
     finally:
         _pool.give_back(eng)
 

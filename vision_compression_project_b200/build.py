@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "pixel_ops.cu", "png_filter.cu", "deflate_lz.cu", "deflate_huff.cu", "png_container.cu"]
+SOURCES = ["api.cu", "pixel_ops.cu", "png_filter.cu", "deflate_lz.cu", "deflate_huff.cu", "png_container.cu", "png_decode.cu"]
 LIB = os.path.join(HERE, "libvcprep.so")
 
 

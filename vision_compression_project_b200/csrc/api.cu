@@ -775,6 +775,105 @@ int vcp_batch_end(vcp_handle* h) {
     return rc;
 }
 
+// ------------------------------------------------------------------------------------------ PNG decode
+int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t* png_lens, int n,
+                         void* out_pixels, uint64_t out_cap, int dst_device, vcp_decode_result* results) {
+    if (!h || n < 0 || (n > 0 && (!pngs || !png_lens || !results || !out_pixels))) return fail(VCP_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> lock(h->mu);
+    CU(cudaSetDevice(h->device));
+    Lane& L = h->lane[0];
+    struct Idat { const uint8_t* p; size_t n; };
+    std::vector<std::vector<Idat>> idats(n);
+    std::vector<DecPageD> dp(n);
+    auto be32 = [](const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    // ---- container parse on the host (PngImagePlugin's chunk loop): IHDR, IDAT ranges, IEND
+    for (int i = 0; i < n; i++) {
+        memset(&results[i], 0, sizeof results[i]);
+        DecPageD& D = dp[i]; memset(&D, 0, sizeof D);
+        const uint8_t* p = (const uint8_t*)pngs[i]; const size_t len = (size_t)png_lens[i];
+        int st = VCP_OK;
+        if (!p || len < 8 + 25 + 12 || memcmp(p, sig, 8) != 0) st = fail(VCP_EINVAL, "PNG %d: not a PNG", i);
+        size_t off = 8; bool seen_end = false, seen_hdr = false;
+        while (st == VCP_OK && !seen_end) {
+            if (off + 12 > len) { st = fail(VCP_EINVAL, "PNG %d: truncated chunk header", i); break; }
+            const size_t cl = be32(p + off);
+            if (off + 12 + cl > len) { st = fail(VCP_EINVAL, "PNG %d: truncated chunk", i); break; }
+            const uint8_t* tag = p + off + 4; const uint8_t* data = p + off + 8;
+            if (!memcmp(tag, "IHDR", 4)) {
+                if (cl != 13) { st = fail(VCP_EINVAL, "PNG %d: bad IHDR", i); break; }
+                D.w = (int32_t)be32(data); D.h = (int32_t)be32(data + 4);
+                const int depth = data[8], ct = data[9], il = data[12];
+                D.c = ct == 0 ? 1 : ct == 4 ? 2 : ct == 2 ? 3 : ct == 6 ? 4 : 0;
+                if (depth != 8 || !D.c || il != 0 || data[10] != 0 || data[11] != 0 || D.w <= 0 || D.h <= 0 ||
+                    (int64_t)D.w * D.c > (1 << 24) || D.h > (1 << 24))
+                    { st = fail(VCP_EINVAL, "PNG %d: only 8-bit gray/gray+alpha/RGB/RGBA non-interlaced images are on the path", i); break; }
+                seen_hdr = true;
+            } else if (!memcmp(tag, "IDAT", 4)) {
+                if (!seen_hdr) { st = fail(VCP_EINVAL, "PNG %d: IDAT before IHDR", i); break; }
+                if (cl) idats[i].push_back({data, cl});
+            } else if (!memcmp(tag, "IEND", 4)) seen_end = true;
+            off += 12 + cl;
+        }
+        if (st == VCP_OK && (!seen_hdr || idats[i].empty())) st = fail(VCP_EINVAL, "PNG %d: no image data", i);
+        if (st == VCP_OK) {
+            D.filt_len = (unsigned long long)D.h * (1ull + (unsigned long long)D.w * D.c);
+            if (D.filt_len >= (1ull << 32)) st = fail(VCP_EINVAL, "PNG %d: too large", i);
+        }
+        results[i].status = st;
+        D.status = st;
+    }
+    // ---- arena + bounce buffer
+    Bump bump; size_t zoff_total = 0;
+    std::vector<size_t> o_z(n, kNone), o_f(n, kNone), o_p(n, kNone), s_z(n, 0);
+    uint64_t pix_total = 0;
+    for (int i = 0; i < n; i++) {
+        if (dp[i].status) continue;
+        size_t zl = 0; for (auto& c : idats[i]) zl += c.n;
+        dp[i].zlen = zl;
+        s_z[i] = zoff_total; zoff_total += align_up(zl + 16, 256);
+        o_f[i] = bump.take((size_t)dp[i].filt_len + 16);
+    }
+    const size_t o_zreg = bump.take(zoff_total + 256);
+    const size_t o_preg = bump.take(0);
+    for (int i = 0; i < n; i++) {
+        if (dp[i].status) continue;
+        const size_t pl = (size_t)dp[i].w * dp[i].h * dp[i].c;
+        o_p[i] = bump.take(pl);
+        results[i].pix_off = (o_p[i] - o_preg); results[i].pix_len = pl;
+        results[i].width = dp[i].w; results[i].height = dp[i].h; results[i].channels = dp[i].c;
+        pix_total = (o_p[i] - o_preg) + pl;
+    }
+    const size_t o_desc = bump.take((size_t)n * sizeof(DecPageD) + 16);
+    if (pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)pix_total);
+    int rc = ensure_arena(L, bump.off + 256); if (rc) return rc;
+    rc = ensure_stage(L, zoff_total + (size_t)n * sizeof(DecPageD) + 512); if (rc) return rc;
+    uint8_t* A = L.arena;
+    std::vector<CopyJob> jobs;
+    for (int i = 0; i < n; i++) {
+        if (dp[i].status) continue;
+        size_t o = s_z[i];
+        for (auto& c : idats[i]) { jobs.push_back({L.stage + o, c.p, c.n}); o += c.n; }
+        dp[i].z = A + o_zreg + s_z[i]; dp[i].filt = A + o_f[i]; dp[i].pix = A + o_p[i];
+    }
+    parallel_copy(jobs, h->copy_threads);
+    DecPageD* hd = reinterpret_cast<DecPageD*>(L.stage + align_up(zoff_total, 256));
+    memcpy(hd, dp.data(), (size_t)n * sizeof(DecPageD));
+    cudaStream_t st = L.stream;
+    if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(A + o_desc, hd, (size_t)n * sizeof(DecPageD), cudaMemcpyHostToDevice, st));
+    DecPageD* dd = reinterpret_cast<DecPageD*>(A + o_desc);
+    launch_inflate(dd, n, st);
+    launch_unfilter(dd, n, st);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hd, dd, (size_t)n * sizeof(DecPageD), cudaMemcpyDeviceToHost, st));
+    if (pix_total) CU(cudaMemcpyAsync(out_pixels, A + o_preg, pix_total, dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++)
+        if (!results[i].status && hd[i].status) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: corrupt zlib stream or filter byte (code %d)", i, hd[i].status); }
+    return 0;
+}
+
 int vcp_get_stats(vcp_handle* h, vcp_stats* out) {
     if (!h || !out) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);

@@ -96,7 +96,18 @@ struct BatchD {
     int32_t want_b64;
 };
 
+// One PNG being decoded (png_decode.cu).
+struct DecPageD {
+    const uint8_t* z; unsigned long long zlen;      // concatenated IDAT payloads (one zlib stream)
+    uint8_t* filt; unsigned long long filt_len;     // h * (1 + w*c)
+    uint8_t* pix;                                   // w*h*c
+    int32_t w, h, c;
+    int32_t status;                                 // 0 or a negative inflate / un-filter error
+};
+
 // ---- launchers (each returns the number of kernels it launched) ----
+int launch_inflate(DecPageD* d_pages, int n, cudaStream_t st);
+int launch_unfilter(DecPageD* d_pages, int n, cudaStream_t st);
 int launch_convert(const PageD* d_pages, int npages, int max_rows, int max_w, cudaStream_t st);
 int launch_reduce(const PageD* d_pages, int npages, int max_rh, int max_rw, cudaStream_t st);
 int launch_resample_h(const PageD* d_pages, int npages, int max_rh, int max_w, cudaStream_t st);
