@@ -8,7 +8,8 @@ import vision_compression_project_b200 as V
 from vision_compression_project_b200 import synth
 from tests import util as U
 n = 64
-pages = [synth.make_page(i, "letter", 200, photo=(i % 4 == 3)) for i in range(8)]
+kind = sys.argv[1] if len(sys.argv) > 1 else "mix"
+pages = [synth.make_page(i, "letter", 200, photo=(kind == "photo") or (kind == "mix" and i % 4 == 3)) for i in range(8)]
 ours = [r.png for r in V.prepare_pages(pages, want_base64=False)]
 pil = [U.pillow_png(p) for p in pages]
 for name, src in (("ours", ours), ("pillow", pil)):

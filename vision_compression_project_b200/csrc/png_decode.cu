@@ -32,21 +32,36 @@ struct InflMem {
     uint16_t sorted_ll[288], sorted_d[32];
     uint16_t cnt_ll[16], cnt_d[16];
     uint8_t lens[320];
+    uint32_t tok[32];                     // one batch of tokens: literal = bit 31 | byte, match = distance << 9 | length
 };
 
+// LSB-first bit reader over a byte stream that has >= 8 addressable bytes of slack behind it; refills 32 bits at a time from two
+// aligned words (one of them already in a register from the previous refill)
 struct BitReader {
-    const uint8_t* z; unsigned long long n, pos; unsigned long long buf; int cnt; bool over;
+    const uint32_t* zw; int mis;                 // aligned word pointer of the stream start, byte misalignment 0..3
+    unsigned long long n, pos;                   // stream length, bytes fetched so far
+    unsigned long long buf; int cnt; bool over;
+    uint32_t nextw;                              // aligned word (pos + mis) / 4, prefetched
+    __device__ void init(const uint8_t* z, unsigned long long len) {
+        mis = (int)((uintptr_t)z & 3); zw = reinterpret_cast<const uint32_t*>(z - mis);
+        n = len; pos = 0; buf = 0; cnt = 0; over = false;
+        nextw = __ldg(zw);
+    }
     __device__ void refill() {
-        while (cnt <= 56) {
-            unsigned long long b = 0;
-            if (pos < n) b = z[pos]; else if (pos > n + 8) over = true;
-            pos++;
-            buf |= b << cnt; cnt += 8;
+        if (cnt <= 32) {
+            const unsigned long long w = (pos + mis) >> 2;
+            const uint32_t hi = __ldg(zw + w + 1);
+            const uint32_t v = __funnelshift_r(nextw, hi, 8 * (int)((pos + mis) & 3));   // bytes [pos, pos + 4)
+            nextw = hi;
+            buf |= (unsigned long long)v << cnt; cnt += 32; pos += 4;
+            if (pos > n + 12) over = true;
         }
     }
     __device__ uint32_t peek(int k) { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
     __device__ void drop(int k) { buf >>= k; cnt -= k; }
     __device__ uint32_t bits(int k) { if (cnt < k) refill(); const uint32_t v = peek(k); drop(k); return v; }
+    __device__ unsigned long long byte_pos() const { return pos - (unsigned long long)(cnt >> 3); }   // first byte not consumed (cnt % 8 == 0)
+    __device__ void seek(unsigned long long p) { pos = p; buf = 0; cnt = 0; nextw = __ldg(zw + ((p + mis) >> 2)); }
 };
 
 __constant__ uint16_t kLenBase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
@@ -107,7 +122,7 @@ __global__ void __launch_bounds__(kInflWarps * 32) k_inflate(DecPageD* __restric
     uint8_t* __restrict__ out = P.filt;
     const unsigned long long cap = P.filt_len;
     unsigned long long pos = 0;
-    BitReader br{P.z, P.zlen, 0, 0, 0, false};
+    BitReader br; br.init(P.z, P.zlen);
     int status = INF_OK;
     if (lane == 0) {
         const uint32_t cmf = br.bits(8), flg = br.bits(8);
@@ -127,9 +142,8 @@ __global__ void __launch_bounds__(kInflWarps * 32) k_inflate(DecPageD* __restric
                 const uint32_t l = br.bits(16), nl = br.bits(16);
                 if ((l ^ nl) != 0xFFFFu) status = INF_BAD_BLOCK;
                 len = (int)l;
-                src = br.pos - (unsigned long long)(br.cnt >> 3);          // first byte not yet consumed
-                if (src + len > br.n) status = INF_SHORT;
-                br.pos = src + len; br.buf = 0; br.cnt = 0;
+                src = br.byte_pos();
+                if (src + len > br.n) status = INF_SHORT; else br.seek(src + len);
             }
             status = __shfl_sync(kFull, status, 0); len = __shfl_sync(kFull, len, 0); src = __shfl_sync(kFull, src, 0);
             if (status == INF_OK && pos + len > cap) status = INF_OVERRUN;
@@ -183,44 +197,62 @@ __global__ void __launch_bounds__(kInflWarps * 32) k_inflate(DecPageD* __restric
         }
         status = __shfl_sync(kFull, status, 0);
         __syncwarp();
-        // ---- tokens: lane 0 decodes, the warp executes
-        while (status == INF_OK) {
-            int len = 0, dist = 0;                // len = -1: literal in dist; len = 0: end of block
+        // ---- tokens: lane 0 decodes a batch of up to 32 into shared memory, the warp executes it: sizes are scanned, all
+        //      literals are stored at once, matches run in order (each copied by the whole warp)
+        bool eob = false;
+        while (status == INF_OK && !eob) {
+            int ntok = 0;
             if (lane == 0) {
-                const int s = decode_sym(br, M.fast_ll, M.cnt_ll, M.sorted_ll);
-                if (s < 0 || br.over) status = INF_BAD_CODE;
-                else if (s < 256) { len = -1; dist = s; }
-                else if (s == 256) len = 0;
-                else if (s > 285) status = INF_BAD_CODE;
-                else {
+                for (; ntok < 32; ntok++) {
+                    const int s = decode_sym(br, M.fast_ll, M.cnt_ll, M.sorted_ll);
+                    if (s < 0 || br.over) { status = INF_BAD_CODE; break; }
+                    if (s < 256) { M.tok[ntok] = 0x80000000u | (uint32_t)s; continue; }
+                    if (s == 256) { eob = true; break; }
+                    if (s > 285) { status = INF_BAD_CODE; break; }
                     const int ls = s - 257;
-                    len = kLenBase[ls] + (int)br.bits(kLenExtra[ls]);
+                    const int len = kLenBase[ls] + (int)br.bits(kLenExtra[ls]);
                     const int ds = decode_sym(br, M.fast_d, M.cnt_d, M.sorted_d);
-                    if (ds < 0 || ds > 29) status = INF_BAD_CODE;
-                    else dist = kDistBase[ds] + (int)br.bits(kDistExtra[ds]);
+                    if (ds < 0 || ds > 29) { status = INF_BAD_CODE; break; }
+                    const int dist = kDistBase[ds] + (int)br.bits(kDistExtra[ds]);
+                    M.tok[ntok] = ((uint32_t)dist << 9) | (uint32_t)len;
                 }
             }
-            status = __shfl_sync(kFull, status, 0); len = __shfl_sync(kFull, len, 0); dist = __shfl_sync(kFull, dist, 0);
-            if (status != INF_OK || len == 0) break;
-            if (len < 0) {
-                if (pos >= cap) { status = INF_OVERRUN; break; }
-                if (lane == 0) out[pos] = (uint8_t)dist;
-                pos++;
-            } else {
-                if ((unsigned long long)dist > pos) { status = INF_BAD_DIST; break; }
-                if (pos + len > cap) { status = INF_OVERRUN; break; }
-                if (dist >= 32) {
+            status = __shfl_sync(kFull, status, 0); ntok = __shfl_sync(kFull, ntok, 0); eob = __shfl_sync(kFull, (int)eob, 0) != 0;
+            if (status != INF_OK) break;
+            __syncwarp();
+            const uint32_t t = lane < ntok ? M.tok[lane] : 0u;
+            const bool lit = (t >> 31) != 0u;
+            const int size = lane < ntok ? (lit ? 1 : (int)(t & 511u)) : 0;
+            int incl = size;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(kFull, incl, 31);
+            if (pos + total > cap) { status = INF_OVERRUN; break; }
+            const unsigned long long my = pos + (unsigned long long)(incl - size);
+            if (lit && lane < ntok) out[my] = (uint8_t)t;
+            uint32_t mm = __ballot_sync(kFull, lane < ntok && !lit);
+            __syncwarp();
+            while (mm) {
+                const int f = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t tf = __shfl_sync(kFull, t, f);
+                const unsigned long long at = __shfl_sync(kFull, my, f);
+                const int len = (int)(tf & 511u), dist = (int)(tf >> 9);
+                if ((unsigned long long)dist > at) { status = INF_BAD_DIST; break; }
+                if (dist >= len) {                                  // no overlap: every byte's source already exists
+                    for (int k = lane; k < len; k += 32) out[at + k] = out[at + k - dist];
+                } else if (dist >= 32) {
                     for (int k0 = 0; k0 < len; k0 += 32) {
                         const int k = k0 + lane;
-                        if (k < len) out[pos + k] = out[pos + k - dist];
+                        if (k < len) out[at + k] = out[at + k - dist];
                         __syncwarp();
                     }
-                } else {
-                    for (int k = lane; k < len; k += 32) out[pos + k] = out[pos - dist + (k % dist)];
+                } else {                                            // periodic: the source is the `dist` bytes in front
+                    for (int k = lane; k < len; k += 32) out[at + k] = out[at - dist + (k % dist)];
                 }
-                pos += len;
+                __syncwarp();
             }
-            __syncwarp();
+            if (status != INF_OK) break;
+            pos += total;
         }
     }
     if (status == INF_OK && pos != cap) status = INF_SHORT;
