@@ -81,3 +81,81 @@ def test_decode_recorded_reference_png_and_errors(V, golden_dir, ref_page):
     assert isinstance(dec[3], ValueError) or not np.array_equal(dec[3], _px(ref_page))
     pal = io.BytesIO(); Image.new("P", (4, 4)).save(pal, format="PNG")
     assert isinstance(V.decode_pages([pal.getvalue()])[0], ValueError)
+
+
+def _png_from_idats(w, h, c, idats):
+    from oracle import restate as R
+    import struct
+    out = [R.PNG_SIG, R.png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, R.COLOR_TYPE[c], 0, 0, 0))]
+    out += [R.png_chunk(b"IDAT", d) for d in idats]
+    out.append(R.png_chunk(b"IEND", b""))
+    return b"".join(out)
+
+
+def _filtered(px):
+    """Filter type 4/2/1/3/0 cycling per row (restated Paeth etc. from the oracle), returns the filtered stream."""
+    from oracle import restate as R
+    h, w, c = px.shape
+    nb = w * c
+    rows = []
+    for y in range(h):
+        prev = px[y - 1].reshape(-1).astype(np.int32) if y else np.zeros(nb, np.int32)
+        cur = px[y].reshape(-1).astype(np.int32)
+        left = np.concatenate([np.zeros(c, np.int32), cur[:-c]]); ul = np.concatenate([np.zeros(c, np.int32), prev[:-c]])
+        ft = (4, 2, 1, 3, 0)[y % 5]
+        pred = {0: np.zeros(nb, np.int32), 1: left, 2: prev, 3: (left + prev) >> 1, 4: R._paeth(left, prev, ul)}[ft]
+        rows.append(bytes([ft]) + ((cur - pred) & 255).astype(np.uint8).tobytes())
+    return b"".join(rows)
+
+
+def test_decode_segment_parallel_foreign_streams(V):
+    """IDATs that each hold whole deflate blocks (zlib Z_SYNC_FLUSH cuts, history kept across the cut) take the
+    segment-parallel path; segments shorter than the 32 KiB window chain their windows; cuts that are not block
+    boundaries, or an Adler-32 in its own IDAT, must fall back to the serial path with the same pixels."""
+    rng = np.random.default_rng(11)
+    pngs, exp = [], []
+    for t, (h, w, c, piece) in enumerate([(240, 301, 3, 5000), (64, 4000, 1, 70000), (500, 257, 4, 1000), (130, 97, 2, 40000), (90, 1000, 3, 33000)]):
+        base = rng.integers(0, 256, (8, w, c), dtype=np.uint8)
+        px = np.concatenate([base[rng.permutation(8)] for _ in range((h + 7) // 8)])[:h].copy()      # rows repeat: long far matches
+        px[rng.integers(0, h, 40), rng.integers(0, w, 40)] ^= 0x55
+        filt = _filtered(px)
+        co = zlib.compressobj(6)
+        idats = []
+        for off in range(0, len(filt), piece):
+            idats.append(co.compress(filt[off:off + piece]) + co.flush(zlib.Z_SYNC_FLUSH))
+        tail = co.flush()
+        variant = t % 3
+        if variant == 0:
+            idats[-1] += tail                                   # final (empty) block + Adler in the last IDAT: fully parallel
+        elif variant == 1:
+            idats.append(tail)                                  # final block + Adler as their own IDAT: still whole blocks
+        else:
+            idats[-1] += tail[:-2]; idats.append(tail[-2:])     # Adler split across IDATs: not parallel, serial fallback
+        assert zlib.decompress(b"".join(idats)) == filt
+        pngs.append(_png_from_idats(w, h, c, idats)); exp.append(px)
+    # cuts in the middle of blocks
+    px = rng.integers(0, 4, (200, 300, 3), dtype=np.uint8) * 60
+    z = zlib.compress(_filtered(px), 6)
+    pngs.append(_png_from_idats(300, 200, 3, [z[i:i + 777] for i in range(0, len(z), 777)])); exp.append(px)
+    dec = V.decode_pages(pngs)
+    for k, (d, e) in enumerate(zip(dec, exp)):
+        assert not isinstance(d, Exception), k
+        assert np.array_equal(d, e), k
+
+
+def test_decode_large_batch_mixed_and_corrupt_segment(V):
+    from vision_compression_project_b200 import synth
+    pages = [synth.make_page(i, "letter", 200, photo=(i % 2 == 1)) for i in range(4)]
+    pages.append(synth.make_page(5, size=(2000, 2600), mode="L"))
+    pages.append(Image.fromarray(np.random.default_rng(5).integers(0, 256, (1200, 900, 4), dtype=np.uint8), "RGBA"))
+    ours = [r.png for r in V.prepare_pages(pages, mode=None, want_base64=False)]
+    pil = [U.pillow_png(p) for p in pages]
+    bad = bytearray(ours[0]); bad[len(bad) // 2:len(bad) // 2 + 64] = bytes(64)      # inside one IDAT of a multi-IDAT PNG
+    batch = ours + pil + [bytes(bad)] + ours
+    dec = V.decode_pages(batch, to_device=True)
+    for k, d in enumerate(dec):
+        if k == 2 * len(pages):
+            assert isinstance(d, ValueError) or not np.array_equal(d.cpu().numpy(), _px(pages[0]))
+            continue
+        assert not isinstance(d, Exception), k
+        assert np.array_equal(d.cpu().numpy(), _px(pages[k % len(pages) if k < 2 * len(pages) else k - 2 * len(pages) - 1])), k

@@ -536,6 +536,7 @@ int vcp_init(int device, vcp_handle** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(VCP_ECUDA, "libvcprep is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    if (decode_kernel_setup()) return fail(VCP_ECUDA, "cudaFuncSetAttribute (decode kernels): %s", cudaGetErrorString(cudaGetLastError()));
     vcp_handle* h = new vcp_handle();
     h->device = device;
     for (Lane& L : h->lane) {
@@ -825,14 +826,28 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     }
     // ---- arena + bounce buffer
     Bump bump; size_t zoff_total = 0;
-    std::vector<size_t> o_z(n, kNone), o_f(n, kNone), o_p(n, kNone), s_z(n, 0);
+    std::vector<size_t> o_z(n, kNone), o_f(n, kNone), o_p(n, kNone), o_s(n, kNone), s_z(n, 0);
+    std::vector<DecSegD> segs;
+    std::vector<uint32_t> chunk_page, chunk_pos;
+    constexpr unsigned long long kResolveChunk = 32768;      // keep in step with png_decode.cu
     uint64_t pix_total = 0;
+    int nbands = 0;
     for (int i = 0; i < n; i++) {
+        dp[i].band0 = nbands;
         if (dp[i].status) continue;
         size_t zl = 0; for (auto& c : idats[i]) zl += c.n;
+        if (zl >= (1ull << 32)) { results[i].status = dp[i].status = fail(VCP_EINVAL, "PNG %d: too large", i); continue; }
         dp[i].zlen = zl;
-        s_z[i] = zoff_total; zoff_total += align_up(zl + 16, 256);
+        s_z[i] = zoff_total; zoff_total += align_up(zl + 64, 256);
         o_f[i] = bump.take((size_t)dp[i].filt_len + 16);
+        nbands += (dp[i].h + 31) / 32;
+        if (idats[i].size() >= 2) {          // candidates for segment-parallel inflate: one segment per IDAT
+            dp[i].seg0 = (int32_t)segs.size(); dp[i].nseg = (int32_t)idats[i].size();
+            size_t o = 0;
+            for (auto& c : idats[i]) { segs.push_back({(uint32_t)i, (uint32_t)o, (uint32_t)c.n, 0u, 0u, 0}); o += c.n; }
+            o_s[i] = bump.take(((size_t)dp[i].filt_len + 16) * 2);
+            for (unsigned long long p = 0; p < dp[i].filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)i); chunk_pos.push_back((uint32_t)p); }
+        }
     }
     const size_t o_zreg = bump.take(zoff_total + 256);
     const size_t o_preg = bump.take(0);
@@ -844,10 +859,15 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         results[i].width = dp[i].w; results[i].height = dp[i].h; results[i].channels = dp[i].c;
         pix_total = (o_p[i] - o_preg) + pl;
     }
-    const size_t o_desc = bump.take((size_t)n * sizeof(DecPageD) + 16);
+    const size_t desc_bytes = align_up((size_t)n * sizeof(DecPageD), 256), seg_bytes = align_up(segs.size() * sizeof(DecSegD), 256),
+                 chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256);
+    const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes;
+    const size_t o_desc = bump.take(meta_bytes + 16);
+    const size_t flag_bytes = align_up(((size_t)nbands + 64) * sizeof(uint32_t), 256);
+    const size_t o_flag = bump.take(flag_bytes);
     if (pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)pix_total);
     int rc = ensure_arena(L, bump.off + 256); if (rc) return rc;
-    rc = ensure_stage(L, zoff_total + (size_t)n * sizeof(DecPageD) + 512); if (rc) return rc;
+    rc = ensure_stage(L, zoff_total + meta_bytes + 512); if (rc) return rc;
     uint8_t* A = L.arena;
     std::vector<CopyJob> jobs;
     for (int i = 0; i < n; i++) {
@@ -855,16 +875,33 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         size_t o = s_z[i];
         for (auto& c : idats[i]) { jobs.push_back({L.stage + o, c.p, c.n}); o += c.n; }
         dp[i].z = A + o_zreg + s_z[i]; dp[i].filt = A + o_f[i]; dp[i].pix = A + o_p[i];
+        dp[i].sym = o_s[i] == kNone ? nullptr : reinterpret_cast<uint16_t*>(A + o_s[i]);
     }
     parallel_copy(jobs, h->copy_threads);
-    DecPageD* hd = reinterpret_cast<DecPageD*>(L.stage + align_up(zoff_total, 256));
+    uint8_t* hm = L.stage + align_up(zoff_total, 256);
+    DecPageD* hd = reinterpret_cast<DecPageD*>(hm);
     memcpy(hd, dp.data(), (size_t)n * sizeof(DecPageD));
+    if (!segs.empty()) memcpy(hm + desc_bytes, segs.data(), segs.size() * sizeof(DecSegD));
+    if (!chunk_page.empty()) {
+        memcpy(hm + desc_bytes + seg_bytes, chunk_page.data(), chunk_page.size() * sizeof(uint32_t));
+        memcpy(hm + desc_bytes + seg_bytes + chunk_bytes, chunk_pos.data(), chunk_pos.size() * sizeof(uint32_t));
+    }
     cudaStream_t st = L.stream;
     if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(A + o_desc, hd, (size_t)n * sizeof(DecPageD), cudaMemcpyHostToDevice, st));
-    DecPageD* dd = reinterpret_cast<DecPageD*>(A + o_desc);
-    launch_inflate(dd, n, st);
-    launch_unfilter(dd, n, st);
+    CU(cudaMemcpyAsync(A + o_desc, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(A + o_flag, 0, flag_bytes, st));
+    DecBatchD B; memset(&B, 0, sizeof B);
+    B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = n;
+    B.segs = reinterpret_cast<DecSegD*>(A + o_desc + desc_bytes); B.nsegs = (int32_t)segs.size();
+    B.chunk_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes);
+    B.chunk_pos = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + chunk_bytes);
+    B.nchunks = (int32_t)chunk_page.size();
+    B.counters = reinterpret_cast<uint32_t*>(A + o_flag);
+    B.band_flag = B.counters + 64; B.nbands = nbands;
+    if (const char* g = getenv("VCP_DBG_UF_NOWAIT")) B.dbg_nowait = atoi(g);
+    DecPageD* dd = B.pages;
+    launch_inflate(B, st);
+    launch_unfilter(B, st);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(hd, dd, (size_t)n * sizeof(DecPageD), cudaMemcpyDeviceToHost, st));
     if (pix_total) CU(cudaMemcpyAsync(out_pixels, A + o_preg, pix_total, dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

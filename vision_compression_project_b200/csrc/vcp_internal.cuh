@@ -101,13 +101,35 @@ struct DecPageD {
     const uint8_t* z; unsigned long long zlen;      // concatenated IDAT payloads (one zlib stream)
     uint8_t* filt; unsigned long long filt_len;     // h * (1 + w*c)
     uint8_t* pix;                                   // w*h*c
+    uint16_t* sym;                                  // filt_len symbolic bytes (segment-parallel inflate), nullptr when nseg == 0
     int32_t w, h, c;
     int32_t status;                                 // 0 or a negative inflate / un-filter error
+    int32_t seg0, nseg;                             // IDAT segments of this page in the DecSegD array (nseg == 0: serial inflate only)
+    int32_t mode;                                   // written by k_infl_plan: 1 = every IDAT is a run of whole deflate blocks -> segment-parallel
+    int32_t band0;                                  // first 32-row band of this page in the un-filter's band numbering
+};
+
+// One IDAT chunk of a PNG being decoded: a candidate for independent inflation.
+struct DecSegD {
+    uint32_t page;
+    uint32_t zoff, zlen;     // byte range inside the page's zlib stream
+    uint32_t olen, opos;     // bytes it inflates to (k_infl_probe) and where they start in the filtered stream (k_infl_plan)
+    int32_t ok;              // 1 = the range is a whole number of deflate blocks (and ends the stream iff it is the last one)
+};
+
+struct DecBatchD {
+    DecPageD* pages; int32_t npages;
+    DecSegD* segs; int32_t nsegs;
+    const uint32_t* chunk_page; const uint32_t* chunk_pos; int32_t nchunks;   // resolve work list: 32 Ki positions each
+    uint32_t* band_flag; int32_t nbands;                                      // un-filter progress per band (zeroed per launch)
+    uint32_t* counters;                                                       // [0] un-filter CTA ticket (zeroed per launch)
+    int32_t dbg_nowait;                                                       // timing experiments only: bands do not wait (wrong pixels)
 };
 
 // ---- launchers (each returns the number of kernels it launched) ----
-int launch_inflate(DecPageD* d_pages, int n, cudaStream_t st);
-int launch_unfilter(DecPageD* d_pages, int n, cudaStream_t st);
+int launch_inflate(const DecBatchD& b, cudaStream_t st);
+int launch_unfilter(const DecBatchD& b, cudaStream_t st);
+int decode_kernel_setup();
 int launch_convert(const PageD* d_pages, int npages, int max_rows, int max_w, cudaStream_t st);
 int launch_reduce(const PageD* d_pages, int npages, int max_rh, int max_rw, cudaStream_t st);
 int launch_resample_h(const PageD* d_pages, int npages, int max_rh, int max_w, cudaStream_t st);
