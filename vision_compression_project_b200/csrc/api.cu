@@ -829,26 +829,37 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     std::vector<size_t> o_z(n, kNone), o_f(n, kNone), o_p(n, kNone), o_s(n, kNone), s_z(n, 0);
     std::vector<DecSegD> segs;
     std::vector<uint32_t> chunk_page, chunk_pos;
-    constexpr unsigned long long kResolveChunk = 32768;      // keep in step with png_decode.cu
+    constexpr unsigned long long kResolveChunk = 32768, kCkpt = 65536;      // keep in step with png_decode.cu
     uint64_t pix_total = 0;
     int nbands = 0;
+    size_t nslots = 0, iv_total = 0;
     for (int i = 0; i < n; i++) {
-        dp[i].band0 = nbands;
+        dp[i].band0 = nbands; dp[i].iv0 = (int32_t)iv_total; dp[i].seg0 = (int32_t)segs.size();
         if (dp[i].status) continue;
         size_t zl = 0; for (auto& c : idats[i]) zl += c.n;
-        if (zl >= (1ull << 32)) { results[i].status = dp[i].status = fail(VCP_EINVAL, "PNG %d: too large", i); continue; }
+        if (zl >= (1ull << 32) || idats[i].size() > (1u << 20)) { results[i].status = dp[i].status = fail(VCP_EINVAL, "PNG %d: too large", i); continue; }
         dp[i].zlen = zl;
         s_z[i] = zoff_total; zoff_total += align_up(zl + 64, 256);
         o_f[i] = bump.take((size_t)dp[i].filt_len + 16);
+        o_s[i] = bump.take(((size_t)dp[i].filt_len + 16) * 2);
         nbands += (dp[i].h + 31) / 32;
-        if (idats[i].size() >= 2) {          // candidates for segment-parallel inflate: one segment per IDAT
-            dp[i].seg0 = (int32_t)segs.size(); dp[i].nseg = (int32_t)idats[i].size();
-            size_t o = 0;
-            for (auto& c : idats[i]) { segs.push_back({(uint32_t)i, (uint32_t)o, (uint32_t)c.n, 0u, 0u, 0}); o += c.n; }
-            o_s[i] = bump.take(((size_t)dp[i].filt_len + 16) * 2);
-            for (unsigned long long p = 0; p < dp[i].filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)i); chunk_pos.push_back((uint32_t)p); }
+        // one segment per IDAT: each is a place a parse may begin.  A parse that begins at IDAT s can produce at most the whole
+        // page, and at most 1032 bytes per byte of input that is left: that bounds the checkpoint slots it may need.
+        dp[i].nseg = (int32_t)idats[i].size();
+        const unsigned long long page_iv = dp[i].filt_len / kCkpt + 2;
+        size_t o = 0;
+        for (auto& c : idats[i]) {
+            DecSegD S; memset(&S, 0, sizeof S);
+            S.page = (uint32_t)i; S.zoff = (uint32_t)o; S.zlen = (uint32_t)c.n;
+            S.iv0 = (uint32_t)nslots; S.iv_cap = (uint32_t)std::min<unsigned long long>(page_iv, (unsigned long long)(zl - o) * 1032ull / kCkpt + 2);
+            nslots += S.iv_cap;
+            segs.push_back(S); o += c.n;
         }
+        dp[i].iv_cap = (int32_t)(page_iv + idats[i].size());
+        iv_total += (size_t)dp[i].iv_cap;
+        for (unsigned long long p = 0; p < dp[i].filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)i); chunk_pos.push_back((uint32_t)p); }
     }
+    if (nslots >= (1ull << 31) || iv_total >= (1ull << 31)) return fail(VCP_ESIZE, "PNG batch too large");
     const size_t o_zreg = bump.take(zoff_total + 256);
     const size_t o_preg = bump.take(0);
     for (int i = 0; i < n; i++) {
@@ -861,10 +872,21 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     }
     const size_t desc_bytes = align_up((size_t)n * sizeof(DecPageD), 256), seg_bytes = align_up(segs.size() * sizeof(DecSegD), 256),
                  chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256);
-    const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes;
+    // un-filter work list: band b of every page that has one, for b = 0, 1, ...
+    std::vector<uint32_t> band_page, band_idx;
+    band_page.reserve(nbands); band_idx.reserve(nbands);
+    {
+        int maxb = 0;
+        for (int i = 0; i < n; i++) if (!dp[i].status) maxb = std::max(maxb, (dp[i].h + 31) / 32);
+        for (int bnd = 0; bnd < maxb; bnd++)
+            for (int i = 0; i < n; i++) if (!dp[i].status && bnd < (dp[i].h + 31) / 32) { band_page.push_back((uint32_t)i); band_idx.push_back((uint32_t)bnd); }
+    }
+    const size_t band_bytes = align_up(band_page.size() * sizeof(uint32_t), 256);
+    const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes;
     const size_t o_desc = bump.take(meta_bytes + 16);
     const size_t flag_bytes = align_up(((size_t)nbands + 64) * sizeof(uint32_t), 256);
     const size_t o_flag = bump.take(flag_bytes);
+    const size_t o_slots = bump.take((nslots + 1) * sizeof(DecIvD)), o_ivs = bump.take((iv_total + 1) * sizeof(DecIvD));
     if (pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)pix_total);
     int rc = ensure_arena(L, bump.off + 256); if (rc) return rc;
     rc = ensure_stage(L, zoff_total + meta_bytes + 512); if (rc) return rc;
@@ -875,7 +897,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         size_t o = s_z[i];
         for (auto& c : idats[i]) { jobs.push_back({L.stage + o, c.p, c.n}); o += c.n; }
         dp[i].z = A + o_zreg + s_z[i]; dp[i].filt = A + o_f[i]; dp[i].pix = A + o_p[i];
-        dp[i].sym = o_s[i] == kNone ? nullptr : reinterpret_cast<uint16_t*>(A + o_s[i]);
+        dp[i].sym = reinterpret_cast<uint16_t*>(A + o_s[i]);
     }
     parallel_copy(jobs, h->copy_threads);
     uint8_t* hm = L.stage + align_up(zoff_total, 256);
@@ -886,6 +908,10 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         memcpy(hm + desc_bytes + seg_bytes, chunk_page.data(), chunk_page.size() * sizeof(uint32_t));
         memcpy(hm + desc_bytes + seg_bytes + chunk_bytes, chunk_pos.data(), chunk_pos.size() * sizeof(uint32_t));
     }
+    if (!band_page.empty()) {
+        memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes, band_page.data(), band_page.size() * sizeof(uint32_t));
+        memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes, band_idx.data(), band_idx.size() * sizeof(uint32_t));
+    }
     cudaStream_t st = L.stream;
     if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(A + o_desc, hm, meta_bytes, cudaMemcpyHostToDevice, st));
@@ -893,11 +919,15 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     DecBatchD B; memset(&B, 0, sizeof B);
     B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = n;
     B.segs = reinterpret_cast<DecSegD*>(A + o_desc + desc_bytes); B.nsegs = (int32_t)segs.size();
+    B.slots = reinterpret_cast<DecIvD*>(A + o_slots);
+    B.ivs = reinterpret_cast<DecIvD*>(A + o_ivs); B.iv_total = (int32_t)iv_total;
     B.chunk_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes);
     B.chunk_pos = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + chunk_bytes);
     B.nchunks = (int32_t)chunk_page.size();
     B.counters = reinterpret_cast<uint32_t*>(A + o_flag);
     B.band_flag = B.counters + 64; B.nbands = nbands;
+    B.band_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes);
+    B.band_idx = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes);
     if (const char* g = getenv("VCP_DBG_UF_NOWAIT")) B.dbg_nowait = atoi(g);
     DecPageD* dd = B.pages;
     launch_inflate(B, st);

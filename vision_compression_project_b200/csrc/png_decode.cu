@@ -5,26 +5,29 @@
 // (backend/README.md:238-243) and validating this library's own PNGs at speed.  Restated for tests by
 // oracle/restate.py:png_unfilter and Python's zlib.
 //
-// Inflate.  A deflate stream is serial, but a PNG cuts it into IDAT chunks, and an encoder that ends every chunk on a block
-// boundary (this library: one byte-aligned deflate block per IDAT) leaves chunks that can be parsed independently.  Whether a
-// foreign PNG has that property is *checked*, not assumed:
-//   k_infl_probe   one warp per IDAT: parse it as if it began a block, count the bytes it produces, and record whether it ended
-//                  exactly on its last byte at a block boundary.  IDAT 0 really does begin a block, so if every IDAT passes, by
-//                  induction every IDAT begins one (no speculation left) and the page is inflated segment-parallel.
-//   k_infl_plan    one warp per page: all IDATs passed and the byte counts add up -> output offsets per IDAT, mode = parallel.
-//   k_infl_seg     one warp per IDAT of a parallel page.  Matches may reach up to 32 KiB behind the IDAT's first byte, into output
-//                  another warp is still producing, so the warp inflates *symbolically*: 16-bit elements, 0..255 = a byte,
-//                  256 + j = "byte j of the 32 KiB in front of this IDAT".  Copies move symbols like bytes.  The 32 Ki-entry window
-//                  is a ring in shared memory (64 KiB per warp), so a match costs a shared-memory round trip, not a global one.
-//   k_infl_window  one CTA per page walks the IDATs in order and makes the last 32 KiB of each concrete (each step a 32 Ki-wide
+// Inflate.  Parsing a deflate stream is serial (a code starts where the last one ended); *executing* its tokens is not, once it is
+// known where in the output each stretch of tokens lands.  So the stream is parsed twice:
+//   k_infl_probe   one warp per IDAT chunk, parse only.  The warp treats its IDAT as the start of a deflate block and counts output
+//                  bytes until a block ends exactly on the last bit of an IDAT (its own or a later one) or the final block ends.
+//                  Every 64 KiB of output it writes a checkpoint: bit position, bit position of the enclosing block header,
+//                  output offset.  IDAT 0 really does begin a block, so its result is true, and so is the result of the IDAT
+//                  its parse stopped in front of, and so on: a chain of true results (k_infl_plan walks it).  An encoder that
+//                  ends every IDAT on a block boundary (this library) gives a chain through all IDATs, each parsed by its own
+//                  warp; Pillow's 64 KiB cuts fall mid-block, the chain is IDAT 0's warp alone, the parse is serial — but still
+//                  a parse only.  Warps that began mid-block produce garbage that no chain reaches.
+//   k_infl_plan    one warp per page: walk the chain, give every interval between checkpoints its output offset, in order.
+//   k_infl_exec    one warp per interval: rebuild the block's code tables, seek to the checkpoint, parse again and execute the tokens.
+//                  A match may reach up to 32 KiB in front of the interval, into output another warp is still producing, so the
+//                  warp works on 16-bit symbols: 0..255 = a byte, 256 + j = "byte j of the 32 KiB in front of this interval".
+//                  Copies move symbols like bytes.  No shared-memory window: at ~8 KB of shared memory per warp 27 warps fit an SM,
+//                  and their number, not the latency of one match through L2, sets the pace.
+//   k_infl_window  one CTA per page walks the intervals in order and makes the last 32 KiB of each concrete (each step a 32 Ki-wide
 //                  gather through the previous, already concrete, window).
-//   k_infl_resolve every other position of every IDAT in parallel: symbol -> byte through the window in front of its IDAT.
-//   k_inflate      the serial path for everything else (Pillow's 64 KiB IDAT cuts fall mid-block): one warp per page, lane 0 parses
-//                  32 tokens at a time, the warp executes them against a 32 KiB byte ring in shared memory.
+//   k_infl_resolve every other position in parallel: symbol -> byte through the window in front of its interval.
 // Un-filter.  Pixel (x, y) needs (x-1, y), (x, y-1), (x-1, y-1): a wavefront.
 //   k_unfilter     one warp per band of 32 rows, lane l on row y0 + l running l pixels behind lane l - 1, so the pixel above
 //                  arrives by one shuffle per step; rows are staged through shared memory 32 pixels at a time with coalesced
-//                  loads and stores.  Bands of a page run concurrently two chunks apart: lane 0 reads the last row of the band
+//                  loads and stores.  Bands of a page run concurrently three chunks apart: lane 0 reads the last row of the band
 //                  above from global memory once that band's progress flag (release / acquire) covers it.  CTAs take their band
 //                  range from a ticket, so a band only ever waits on bands that are already running.
 // Every loop is bounded by the stream / output length: malformed input ends in a status, never in a hang.
@@ -35,22 +38,27 @@ namespace vcp {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kFastBits = 10;
+constexpr int kFastLL = 10, kFastD = 9;   // index bits of the lit/len and distance lookup tables
 constexpr int kWin = 32768;
-constexpr int kZWords = 512;              // compressed-input ring (words) the warp keeps filled ahead of lane 0's parser
+constexpr int kZWords = 256;              // compressed-input ring (words) the warp keeps filled ahead of lane 0's parser
 constexpr int kResolveChunk = 32768;      // positions per CTA of k_infl_resolve (keep in step with api.cu)
+constexpr uint32_t kCkpt = 65536;         // output bytes between checkpoints (keep in step with api.cu)
 
 enum { INF_OK = 0, INF_BAD_HEADER = -101, INF_BAD_BLOCK = -102, INF_BAD_CODE = -103, INF_OVERRUN = -104, INF_BAD_DIST = -105,
        INF_SHORT = -106, INF_BAD_FILTER = -107, INF_SEG = -108 };
 
+// Table entry: value << 16 | kind << 8 | extra bits << 4 | code length (0 = not in the fast table).
+enum { K_LIT = 0, K_LEN = 1, K_EOB = 2, K_BAD = 3 };
+
 struct InflMem {
-    uint16_t fast_ll[1 << kFastBits];     // (symbol << 4) | length, 0 = not in the fast table
-    uint16_t fast_d[1 << kFastBits];
+    uint32_t fast_ll[1 << kFastLL];
+    uint32_t fast_d[1 << kFastD];
+    uint32_t zbuf[kZWords];               // the compressed stream in front of the parser: word w of the stream at zbuf[w % kZWords]
+    uint32_t tok[32];                     // one batch of tokens: literal = bit 31 | byte, match = distance << 9 | length
     uint16_t sorted_ll[288], sorted_d[32];
     uint16_t cnt_ll[16], cnt_d[16];
-    uint8_t lens[320];
-    uint32_t tok[32];                     // one batch of tokens: literal = bit 31 | byte, match = distance << 9 | length
-    uint32_t zbuf[kZWords];               // the compressed stream in front of the parser: word w of the stream at zbuf[w % kZWords]
+    uint16_t offs[16], fcode[16];         // table building: first index / first code of every length
+    uint8_t lens[384];                    // [0, 288) lit/len, [288, 318) distance code lengths; scratch while a header is read
 };
 
 // LSB-first bit reader (lane 0) over a byte stream that has >= 64 addressable bytes of slack behind it.  It refills 32 bits at a
@@ -63,29 +71,30 @@ struct BitReader {
     unsigned long long buf; int cnt; bool over;
     uint32_t nextw;                              // aligned word (pos + mis) / 4
     uint32_t maxw;                               // last word index that may be read
+    uint32_t limw;                               // a refill from a word beyond this one means the parse ran off the stream
     __device__ void init(const uint8_t* z, unsigned long long len, const uint32_t* ring) {
         mis = (int)((uintptr_t)z & 3); zw = reinterpret_cast<const uint32_t*>(z - mis); zs = ring;
         n = len; pos = 0; buf = 0; cnt = 0; over = false;
         maxw = (uint32_t)((len + mis + 60) >> 2);
+        limw = (uint32_t)((len + mis + 12) >> 2);
         nextw = __ldg(zw);
     }
     __device__ uint32_t word() const { return (uint32_t)((pos + mis) >> 2); }
-    __device__ void refill() {
-        if (cnt <= 32) {
-            const uint32_t w = word();
-            const uint32_t hi = zs[(w + 1) & (kZWords - 1)];
-            const uint32_t v = __funnelshift_r(nextw, hi, 8 * (int)((pos + mis) & 3));   // bytes [pos, pos + 4)
-            nextw = hi;
-            buf |= (unsigned long long)v << cnt; cnt += 32; pos += 4;
-            if (pos > n + 12) over = true;
-        }
+    __device__ __forceinline__ void refill() {   // call with cnt <= 32
+        const uint32_t w = word();
+        const uint32_t hi = zs[(w + 1) & (kZWords - 1)];
+        const uint32_t v = __funnelshift_r(nextw, hi, 8 * (int)((pos + mis) & 3));   // bytes [pos, pos + 4)
+        nextw = hi;
+        buf |= (unsigned long long)v << cnt; cnt += 32; pos += 4;
+        if (w > limw) over = true;
     }
-    __device__ uint32_t peek(int k) { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
-    __device__ void drop(int k) { buf >>= k; cnt -= k; }
-    __device__ uint32_t bits(int k) { if (cnt < k) refill(); const uint32_t v = peek(k); drop(k); return v; }
+    __device__ __forceinline__ void need33() { if (cnt <= 32) refill(); }            // afterwards at least 33 bits are buffered
+    __device__ __forceinline__ uint32_t peek(int k) { return (uint32_t)buf & ((1u << k) - 1u); }   // k <= 16
+    __device__ __forceinline__ void drop(int k) { buf >>= k; cnt -= k; }
+    __device__ uint32_t bits(int k) { need33(); const uint32_t v = peek(k); drop(k); return v; }   // k <= 16
     __device__ unsigned long long bits_used() const { return pos * 8ull - (unsigned long long)cnt; }
     __device__ unsigned long long byte_pos() const { return pos - (unsigned long long)(cnt >> 3); }   // first byte not consumed (cnt % 8 == 0)
-    __device__ void seek(unsigned long long p) { pos = p; buf = 0; cnt = 0; nextw = __ldg(zw + ((p + mis) >> 2)); }
+    __device__ void seek(unsigned long long p) { pos = p; buf = 0; cnt = 0; nextw = __ldg(zw + min((uint32_t)((p + mis) >> 2), maxw)); }
 };
 
 // Whole warp: load stream words [filled, ...) into the ring until it reaches kZWords ahead of word w0 (lane 0's position).
@@ -100,277 +109,195 @@ __device__ __forceinline__ void topup(InflMem& M, const BitReader& br, uint32_t&
     __syncwarp();
 }
 
+// Whole warp (every lane keeps an identical reader): continue at bit `bit` of the stream.
+__device__ void seek_bit(InflMem& M, BitReader& br, uint32_t& filled, unsigned long long bit) {
+    br.seek(bit >> 3);
+    filled = 0;
+    topup(M, br, filled, br.word());
+    br.refill();
+    br.drop((int)(bit & 7));
+}
+
 __constant__ uint16_t kLenBase[29] = {3,4,5,6,7,8,9,10,11,13,15,17,19,23,27,31,35,43,51,59,67,83,99,115,131,163,195,227,258};
 __constant__ uint8_t kLenExtra[29] = {0,0,0,0,0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,4,5,5,5,5,0};
 __constant__ uint16_t kDistBase[30] = {1,2,3,4,5,7,9,13,17,25,33,49,65,97,129,193,257,385,513,769,1025,1537,2049,3073,4097,6145,8193,12289,16385,24577};
 __constant__ uint8_t kDistExtra[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13};
 __constant__ uint8_t kClOrd[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
-// Build canonical decode structures for n symbols with code lengths L (one thread).  Returns false for an over-subscribed code.
-__device__ bool build_table(const uint8_t* L, int n, uint16_t* cnt, uint16_t* sorted, uint16_t* fast) {
-    for (int i = 0; i < 16; i++) cnt[i] = 0;
-    for (int i = 0; i < n; i++) cnt[L[i]]++;
-    cnt[0] = 0;
-    int left = 1;
-    for (int l = 1; l < 16; l++) { left <<= 1; left -= cnt[l]; if (left < 0) return false; }
-    uint16_t offs[16]; offs[1] = 0;
-    for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + cnt[l];
-    for (int i = 0; i < n; i++) if (L[i]) sorted[offs[L[i]]++] = (uint16_t)i;
-    for (int i = 0; i < (1 << kFastBits); i++) fast[i] = 0;
-    // fast table: canonical codes of length <= kFastBits, bit-reversed (the stream is LSB first)
-    uint32_t code = 0; int idx = 0;
-    for (int l = 1; l <= kFastBits; l++) {
-        for (int k = 0; k < cnt[l]; k++, idx++, code++) {
-            const uint32_t r = __brev(code) >> (32 - l);
-            for (uint32_t e = r; e < (1u << kFastBits); e += 1u << l) fast[e] = (uint16_t)((sorted[idx] << 4) | l);
-        }
-        code <<= 1;
+enum { T_LL = 0, T_D = 1, T_CL = 2 };
+
+// what a decoded symbol means, in table-entry form (without the code length)
+template <int KIND>
+__device__ __forceinline__ uint32_t sym_entry(int s) {
+    if (KIND == T_CL) return (uint32_t)s << 16;
+    if (KIND == T_D) return s < 30 ? ((uint32_t)kDistBase[s] << 16) | ((uint32_t)kDistExtra[s] << 4) : (uint32_t)K_BAD << 8;
+    if (s < 256) return (uint32_t)s << 16;
+    if (s == 256) return (uint32_t)K_EOB << 8;
+    if (s > 285) return (uint32_t)K_BAD << 8;
+    return ((uint32_t)kLenBase[s - 257] << 16) | ((uint32_t)K_LEN << 8) | ((uint32_t)kLenExtra[s - 257] << 4);
+}
+
+// Whole warp: canonical decode structures for n symbols with code lengths L.  Lane 0 counts and sorts, all lanes fill the lookup
+// table (one symbol per lane at a time, every replica of its code).  Returns false for an over-subscribed code.
+template <int KIND>
+__device__ bool build_table(InflMem& M, const uint8_t* L, int n, uint16_t* cnt, uint16_t* sorted, uint32_t* fast, int fastbits) {
+    const int lane = threadIdx.x & 31;
+    int ok = 1, total = 0;
+    if (lane == 0) {
+        for (int i = 0; i < 16; i++) cnt[i] = 0;
+        for (int i = 0; i < n; i++) cnt[L[i]]++;
+        cnt[0] = 0;
+        int left = 1;
+        for (int l = 1; l < 16; l++) { left <<= 1; left -= cnt[l]; if (left < 0) ok = 0; }
+        uint16_t o[16]; o[1] = 0; M.offs[1] = 0; M.fcode[1] = 0;
+        for (int l = 1; l < 15; l++) { o[l + 1] = o[l] + cnt[l]; M.offs[l + 1] = o[l + 1]; M.fcode[l + 1] = (uint16_t)((M.fcode[l] + cnt[l]) << 1); }
+        if (ok) for (int i = 0; i < n; i++) if (L[i]) sorted[o[L[i]]++] = (uint16_t)i;
+        total = o[15] + 0;                    // o[15] was advanced past the 15-bit codes: number of coded symbols
     }
+    ok = __shfl_sync(kFull, ok, 0); total = __shfl_sync(kFull, total, 0);
+    for (int i = lane; i < (1 << fastbits); i += 32) fast[i] = 0;
+    __syncwarp();
+    if (!ok) return false;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int s = sorted[idx], l = L[s];
+        if (l > fastbits) continue;
+        const uint32_t code = (uint32_t)M.fcode[l] + (uint32_t)(idx - M.offs[l]);
+        const uint32_t r = __brev(code) >> (32 - l);                       // the stream is LSB first
+        const uint32_t e = sym_entry<KIND>(s) | (uint32_t)l;
+        for (uint32_t k = r; k < (1u << fastbits); k += 1u << l) fast[k] = e;
+    }
+    __syncwarp();
     return true;
 }
 
-// one symbol (lane 0 only)
-__device__ int decode_sym(BitReader& br, const uint16_t* fast, const uint16_t* cnt, const uint16_t* sorted) {
-    if (br.cnt < 15) br.refill();
-    const uint16_t e = fast[br.peek(kFastBits)];
-    if (e) { br.drop(e & 15); return e >> 4; }
+// one code (lane 0; at least 15 bits buffered): table entry including its length, K_BAD for a code that does not exist
+template <int KIND>
+__device__ __forceinline__ uint32_t decode_entry(BitReader& br, const uint32_t* fast, int fastbits, const uint16_t* cnt, const uint16_t* sorted) {
+    const uint32_t e = fast[br.peek(fastbits)];
+    if (e & 15u) return e;
     int code = 0, first = 0, index = 0;
     unsigned long long b = br.buf;
     for (int l = 1; l <= 15; l++) {
         code |= (int)(b & 1ull); b >>= 1;
         const int c = cnt[l];
-        if (code - c < first) { br.drop(l); return sorted[index + (code - first)]; }
+        if (code - c < first) return sym_entry<KIND>(sorted[index + (code - first)]) | (uint32_t)l;
         index += c; first += c; first <<= 1; code <<= 1;
     }
-    return -1;
+    return ((uint32_t)K_BAD << 8) | 1u;
 }
 
-
-// What a warp does with the tokens it parses.
-//   COUNT: nothing but add up their sizes (k_infl_probe).
-//   BYTES: execute against a byte ring (k_inflate).
-//   SYMS:  execute against a ring of 16-bit symbols; sources in front of the stream become 256 + window index (k_infl_seg).
-enum { COUNT = 0, BYTES = 1, SYMS = 2 };
-
-// Inflates deflate blocks from `br` until the final block (until_final) or until a block ends exactly on the last bit of the
-// reader's range (!until_final).  `abs0` is the position of out[0] in the page's filtered stream (distance check).  All lanes
-// call it; lane 0 parses.  Returns the status; *produced = bytes written (all lanes), *final_seen = the BFINAL block was met.
-template <int MODE, typename T>
-__device__ int inflate_blocks(InflMem& M, T* __restrict__ ring, BitReader& br, const uint8_t* __restrict__ zbase, T* __restrict__ out,
-                              unsigned long long cap, unsigned long long abs0, bool until_final, unsigned long long* produced, bool* final_seen) {
+// Whole warp: the 3 header bits of a block and, for Huffman blocks, its code tables.  Stored blocks: *stored_len / *stored_src are
+// set and the reader is moved behind the raw bytes.  Every lane returns the same status.
+__device__ int block_header(InflMem& M, BitReader& br, uint32_t& filled, int* last, int* btype, int* stored_len, unsigned long long* stored_src) {
     const int lane = threadIdx.x & 31;
-    constexpr uint32_t RM = kWin - 1;
-    unsigned long long pos = 0;
-    int status = INF_OK;
-    int last = 0;
-    bool done = false;
-    uint32_t filled = 0;                      // stream words [.., filled) have been put into M.zbuf (warp-uniform)
-    while (status == INF_OK && !done) {
-        topup(M, br, filled, __shfl_sync(kFull, br.word(), 0));       // a block header is at most ~330 bytes
-        int btype = 0;
-        if (lane == 0) { last = (int)br.bits(1); btype = (int)br.bits(2); if (br.over) status = INF_SHORT; }
-        status = __shfl_sync(kFull, status, 0);
-        if (status != INF_OK) break;
-        last = __shfl_sync(kFull, last, 0); btype = __shfl_sync(kFull, btype, 0);
-        if (btype == 0) {
-            // stored: byte-align, LEN / NLEN, raw copy by the whole warp
-            unsigned long long src = 0; int len = 0;
-            if (lane == 0) {
-                br.drop(br.cnt & 7);
-                const uint32_t l = br.bits(16), nl = br.bits(16);
-                if ((l ^ nl) != 0xFFFFu) status = INF_BAD_BLOCK;
-                len = (int)l;
-                src = br.byte_pos();
-                if (src + len > br.n) status = INF_SHORT; else br.seek(src + len);
-            }
-            status = __shfl_sync(kFull, status, 0); len = __shfl_sync(kFull, len, 0); src = __shfl_sync(kFull, src, 0);
-            if (status == INF_OK && pos + len > cap) status = INF_OVERRUN;
-            if (status != INF_OK) break;
-            if (MODE != COUNT) {
-                const uint8_t* s = zbase + src;
-                for (int k = lane; k < len; k += 32) { const T v = (T)s[k]; ring[(uint32_t)(pos + k) & RM] = v; out[pos + k] = v; }
-            }
-            pos += len;
-            filled = 0;                       // the reader jumped: refill the ring from its new position
-            __syncwarp();
-        } else if (btype == 3) { status = INF_BAD_BLOCK; break; }
-        else {
-            // ---- code tables (lane 0)
-            if (lane == 0) {
-                int nll = 288, nd = 30;
-                if (btype == 1) {
-                    for (int i = 0; i < 144; i++) M.lens[i] = 8;
-                    for (int i = 144; i < 256; i++) M.lens[i] = 9;
-                    for (int i = 256; i < 280; i++) M.lens[i] = 7;
-                    for (int i = 280; i < 288; i++) M.lens[i] = 8;
-                    for (int i = 0; i < 30; i++) M.lens[288 + i] = 5;
-                } else {
-                    nll = (int)br.bits(5) + 257; nd = (int)br.bits(5) + 1;
-                    const int ncl = (int)br.bits(4) + 4;
-                    if (nll > 286 || nd > 30) status = INF_BAD_BLOCK;
-                    uint8_t cl[19];
-                    for (int i = 0; i < 19; i++) cl[i] = 0;
-                    for (int i = 0; i < ncl; i++) cl[kClOrd[i]] = (uint8_t)br.bits(3);
-                    // the code-length code uses the d-table slots as scratch (rebuilt right after)
-                    if (status == INF_OK && !build_table(cl, 19, M.cnt_d, M.sorted_d, M.fast_d)) status = INF_BAD_CODE;
-                    int i = 0;
-                    while (status == INF_OK && i < nll + nd) {
-                        const int s = decode_sym(br, M.fast_d, M.cnt_d, M.sorted_d);
-                        if (s < 0 || br.over) { status = INF_BAD_CODE; break; }
-                        if (s < 16) { M.lens[i++] = (uint8_t)s; continue; }
-                        int rep, v = 0;
-                        if (s == 16) { if (i == 0) { status = INF_BAD_CODE; break; } v = M.lens[i - 1]; rep = 3 + (int)br.bits(2); }
-                        else if (s == 17) rep = 3 + (int)br.bits(3);
-                        else rep = 11 + (int)br.bits(7);
-                        if (i + rep > nll + nd) { status = INF_BAD_CODE; break; }
-                        while (rep--) M.lens[i++] = (uint8_t)v;
-                    }
-                    if (status == INF_OK) {          // move the distance lengths behind a fixed lit/len region of 288
-                        uint8_t tmp[30];
-                        for (int k = 0; k < nd; k++) tmp[k] = M.lens[nll + k];
-                        for (int k = nll; k < 288; k++) M.lens[k] = 0;
-                        for (int k = 0; k < 30; k++) M.lens[288 + k] = k < nd ? tmp[k] : 0;
-                        if (M.lens[256] == 0) status = INF_BAD_CODE;
-                    }
-                }
-                if (status == INF_OK && !build_table(M.lens, 288, M.cnt_ll, M.sorted_ll, M.fast_ll)) status = INF_BAD_CODE;
-                if (status == INF_OK && !build_table(M.lens + 288, 30, M.cnt_d, M.sorted_d, M.fast_d)) status = INF_BAD_CODE;
-            }
-            status = __shfl_sync(kFull, status, 0);
-            __syncwarp();
-            // ---- tokens: lane 0 decodes a batch of up to 32 into shared memory, the warp executes it: sizes are scanned, literals
-            //      are stored together, matches run in order (each copied by the whole warp through the ring)
-            bool eob = false;
-            while (status == INF_OK && !eob) {
-                int ntok = 0;
-                unsigned long long counted = 0;
-                // keep the input ring ahead of the parser: a batch of 32 tokens eats at most 192 bytes, 256 counted ones 1536.
-                // When executing, the next 64 words are requested now and land in the ring after the batch (latency hidden).
-                const uint32_t w0 = __shfl_sync(kFull, br.word(), 0);
-                uint32_t p0 = 0, p1 = 0; bool pf = false;
-                if (MODE == COUNT || filled < w0 + 128) topup(M, br, filled, w0);
-                else if (filled + 64 <= w0 + kZWords) {
-                    pf = true;
-                    p0 = __ldg(br.zw + min(filled + lane, br.maxw)); p1 = __ldg(br.zw + min(filled + 32 + lane, br.maxw));
-                }
-                if (lane == 0) {
-                    const int lim = MODE == COUNT ? 256 : 32;
-                    for (; ntok < lim; ntok++) {
-                        const int s = decode_sym(br, M.fast_ll, M.cnt_ll, M.sorted_ll);
-                        if (s < 0 || br.over) { status = INF_BAD_CODE; break; }
-                        if (s < 256) { if (MODE == COUNT) counted++; else M.tok[ntok] = 0x80000000u | (uint32_t)s; continue; }
-                        if (s == 256) { eob = true; break; }
-                        if (s > 285) { status = INF_BAD_CODE; break; }
-                        const int ls = s - 257;
-                        const int len = kLenBase[ls] + (int)br.bits(kLenExtra[ls]);
-                        const int ds = decode_sym(br, M.fast_d, M.cnt_d, M.sorted_d);
-                        if (ds < 0 || ds > 29) { status = INF_BAD_CODE; break; }
-                        const int dist = kDistBase[ds] + (int)br.bits(kDistExtra[ds]);
-                        if (MODE == COUNT) { counted += (unsigned)len; if (pos + counted > cap) { status = INF_OVERRUN; break; } }
-                        else M.tok[ntok] = ((uint32_t)dist << 9) | (uint32_t)len;
-                    }
-                }
-                status = __shfl_sync(kFull, status, 0); eob = __shfl_sync(kFull, (int)eob, 0) != 0;
-                if (status != INF_OK) break;
-                if (MODE == COUNT) {
-                    counted = __shfl_sync(kFull, counted, 0);
-                    if (pos + counted > cap) { status = INF_OVERRUN; break; }
-                    pos += counted;
-                    continue;
-                }
-                ntok = __shfl_sync(kFull, ntok, 0);
-                __syncwarp();
-                const uint32_t t = lane < ntok ? M.tok[lane] : 0u;
-                const bool lit = (t >> 31) != 0u;
-                const int size = lane < ntok ? (lit ? 1 : (int)(t & 511u)) : 0;
-                int incl = size;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-                const int total = __shfl_sync(kFull, incl, 31);
-                if (pos + total > cap) { status = INF_OVERRUN; break; }
-                const unsigned long long my = pos + (unsigned long long)(incl - size);
-                if (lit) out[my] = (T)(t & 255u);
-                uint32_t mm = __ballot_sync(kFull, lane < ntok && !lit);
-                int prev = -1;
-                // ring slots alias positions 32 KiB apart, so a literal enters the ring only after every match in front of it ran
-                while (mm) {
-                    const int f = __ffs(mm) - 1; mm &= mm - 1;
-                    if (lit && lane > prev && lane < f) ring[(uint32_t)my & RM] = (T)(t & 255u);
-                    prev = f;
-                    const uint32_t tf = __shfl_sync(kFull, t, f);
-                    const unsigned long long at = __shfl_sync(kFull, my, f);
-                    const int len = (int)(tf & 511u), dist = (int)(tf >> 9);
-                    if ((unsigned long long)dist > abs0 + at || (MODE == BYTES && (unsigned long long)dist > at)) { status = INF_BAD_DIST; break; }
-                    __syncwarp();
-                    for (int k0 = 0; k0 < len; k0 += 32) {
-                        const int k = k0 + lane;
-                        T v = 0;
-                        if (k < len) {
-                            // the source is the `dist` elements in front of the match, repeated when it is shorter than the match
-                            const long long q = (long long)at - dist + (dist >= len ? k : k % dist);
-                            v = (MODE == SYMS && q < 0) ? (T)(256 + kWin + q) : ring[(uint32_t)q & RM];
-                        }
-                        __syncwarp();
-                        if (k < len) { ring[(uint32_t)(at + k) & RM] = v; out[at + k] = v; }
-                    }
-                    __syncwarp();
-                }
-                if (status != INF_OK) break;
-                if (lit && lane > prev) ring[(uint32_t)my & RM] = (T)(t & 255u);
-                if (pf) { M.zbuf[(filled + lane) & (kZWords - 1)] = p0; M.zbuf[(filled + 32 + lane) & (kZWords - 1)] = p1; filled += 64; }
-                __syncwarp();
-                pos += total;
-            }
-        }
-        if (status != INF_OK) break;
-        // ---- where did this block end?
-        int stop = 0;
+    topup(M, br, filled, __shfl_sync(kFull, br.word(), 0));       // a block header is at most ~330 bytes
+    int status = INF_OK, bt = 0, la = 0;
+    if (lane == 0) { la = (int)br.bits(1); bt = (int)br.bits(2); if (br.over) status = INF_SHORT; }
+    status = __shfl_sync(kFull, status, 0); la = __shfl_sync(kFull, la, 0); bt = __shfl_sync(kFull, bt, 0);
+    *last = la; *btype = bt;
+    if (status != INF_OK) return status;
+    if (bt == 3) return INF_BAD_BLOCK;
+    if (bt == 0) {
+        unsigned long long src = 0; int len = 0;
         if (lane == 0) {
-            if (last) stop = 1;
-            else if (!until_final) {
-                const unsigned long long used = br.bits_used();
-                if (used == br.n * 8ull) stop = 1;
-                else if (used > br.n * 8ull) status = INF_SEG;
-            }
-            if (br.over) status = INF_SHORT;
+            br.drop(br.cnt & 7);
+            const uint32_t l = br.bits(16), nl = br.bits(16);
+            if ((l ^ nl) != 0xFFFFu) status = INF_BAD_BLOCK;
+            len = (int)l;
+            src = br.byte_pos();
+            if (src + len > br.n) status = INF_SHORT; else br.seek(src + len);
         }
         status = __shfl_sync(kFull, status, 0);
-        done = __shfl_sync(kFull, stop, 0) != 0;
+        *stored_len = __shfl_sync(kFull, len, 0); *stored_src = __shfl_sync(kFull, src, 0);
+        filled = 0;                           // the reader jumped: the ring refills from its new position
+        return status;
     }
-    *produced = pos;
-    *final_seen = last != 0;
-    return status;
+    int nll = 288, nd = 30;
+    if (bt == 1) {
+        for (int i = lane; i < 288; i += 32) M.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+        if (lane < 30) M.lens[288 + lane] = 5;
+        __syncwarp();
+    } else {
+        int ncl = 0;
+        if (lane == 0) {
+            nll = (int)br.bits(5) + 257; nd = (int)br.bits(5) + 1; ncl = (int)br.bits(4) + 4;
+            if (nll > 286 || nd > 30) status = INF_BAD_BLOCK;
+            for (int i = 0; i < 19; i++) M.lens[i] = 0;
+            for (int i = 0; i < ncl; i++) M.lens[kClOrd[i]] = (uint8_t)br.bits(3);
+        }
+        status = __shfl_sync(kFull, status, 0); nll = __shfl_sync(kFull, nll, 0); nd = __shfl_sync(kFull, nd, 0);
+        if (status != INF_OK) return status;
+        __syncwarp();
+        // the code-length code borrows the distance table's slots (rebuilt right after)
+        if (!build_table<T_CL>(M, M.lens, 19, M.cnt_d, M.sorted_d, M.fast_d, 7)) return INF_BAD_CODE;
+        if (lane == 0) {
+            uint8_t* LL = M.lens + 32;        // decoded behind the 19 code-length-code lengths, moved into place below
+            int i = 0;
+            while (status == INF_OK && i < nll + nd) {
+                br.need33();
+                const uint32_t e = decode_entry<T_CL>(br, M.fast_d, 7, M.cnt_d, M.sorted_d);
+                if (((e >> 8) & 3u) == K_BAD || br.over) { status = INF_BAD_CODE; break; }
+                br.drop((int)(e & 15u));
+                const int s = (int)(e >> 16);
+                if (s < 16) { LL[i++] = (uint8_t)s; continue; }
+                int rep, v = 0;
+                if (s == 16) { if (i == 0) { status = INF_BAD_CODE; break; } v = LL[i - 1]; rep = 3 + (int)br.peek(2); br.drop(2); }
+                else if (s == 17) { rep = 3 + (int)br.peek(3); br.drop(3); }
+                else { rep = 11 + (int)br.peek(7); br.drop(7); }
+                if (i + rep > nll + nd) { status = INF_BAD_CODE; break; }
+                while (rep--) LL[i++] = (uint8_t)v;
+            }
+            if (status == INF_OK) {           // lit/len lengths to [0, 288), distance lengths to [288, 318); in-place moves run downwards / via a copy
+                uint8_t tmp[30];
+                for (int k = 0; k < nd; k++) tmp[k] = LL[nll + k];
+                for (int k = 0; k < nll; k++) M.lens[k] = LL[k];
+                for (int k = nll; k < 288; k++) M.lens[k] = 0;
+                for (int k = 0; k < 30; k++) M.lens[288 + k] = k < nd ? tmp[k] : 0;
+                if (M.lens[256] == 0) status = INF_BAD_CODE;
+            }
+        }
+        status = __shfl_sync(kFull, status, 0);
+        if (status != INF_OK) return status;
+        __syncwarp();
+    }
+    if (!build_table<T_LL>(M, M.lens, 288, M.cnt_ll, M.sorted_ll, M.fast_ll, kFastLL)) return INF_BAD_CODE;
+    if (!build_table<T_D>(M, M.lens + 288, 30, M.cnt_d, M.sorted_d, M.fast_d, kFastD)) return INF_BAD_CODE;
+    return INF_OK;
 }
 
-// all lanes: check the two zlib header bytes and move the reader behind them
-__device__ int zlib_header(BitReader& br, const uint8_t* z) {
-    if (br.n < 2) return INF_SHORT;
+// lane 0: one token.  Returns its output size (1 literal, 3..258 match), 0 for end of block, < 0 for an error; *tok in batch form.
+__device__ __forceinline__ int parse_token(InflMem& M, BitReader& br, uint32_t* tok) {
+    br.need33();
+    const uint32_t e = decode_entry<T_LL>(br, M.fast_ll, kFastLL, M.cnt_ll, M.sorted_ll);
+    br.drop((int)(e & 15u));
+    const uint32_t kind = (e >> 8) & 3u;
+    if (kind == K_LIT) { *tok = 0x80000000u | (e >> 16); return 1; }
+    if (kind != K_LEN) return kind == K_EOB ? 0 : INF_BAD_CODE;
+    const int xl = (int)((e >> 4) & 15u);
+    const int len = (int)(e >> 16) + (int)br.peek(xl);
+    br.drop(xl);
+    br.need33();
+    const uint32_t d = decode_entry<T_D>(br, M.fast_d, kFastD, M.cnt_d, M.sorted_d);
+    if (((d >> 8) & 3u) == K_BAD) return INF_BAD_CODE;
+    br.drop((int)(d & 15u));
+    const int xd = (int)((d >> 4) & 15u);
+    const uint32_t dist = (d >> 16) + br.peek(xd);
+    br.drop(xd);
+    *tok = (dist << 9) | (uint32_t)len;
+    return len;
+}
+
+// all lanes: check the two zlib header bytes; the deflate data starts at bit 16
+__device__ int zlib_header(const uint8_t* z, unsigned long long n) {
+    if (n < 2) return INF_SHORT;
     const uint32_t cmf = z[0], flg = z[1];
-    br.seek(2);
     return ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) ? INF_BAD_HEADER : INF_OK;
 }
 
 }  // namespace
 
-// ------------------------------------------------------------------------------------------ serial inflate
-__global__ void __launch_bounds__(32) k_inflate(DecPageD* __restrict__ pages, int n) {
-    __shared__ InflMem M;
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
-    const int lane = threadIdx.x;
-    const int pg = blockIdx.x;
-    if (pg >= n) return;
-    DecPageD& P = pages[pg];
-    if (P.status != 0 || P.mode == 1) return;
-    BitReader br; br.init(P.z, P.zlen, M.zbuf);
-    int status = zlib_header(br, P.z);
-    unsigned long long produced = 0; bool fin = false;
-    if (status == INF_OK) status = inflate_blocks<BYTES, uint8_t>(M, dyn_smem, br, P.z, P.filt, P.filt_len, 0ull, true, &produced, &fin);
-    if (status == INF_OK && produced != P.filt_len) status = INF_SHORT;
-    if (lane == 0) P.status = status;
-}
-
-// ------------------------------------------------------------------------------------------ segment-parallel inflate
-__global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, int nsegs) {
+// ------------------------------------------------------------------------------------------ probe: parse, count, checkpoint
+__global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, DecIvD* __restrict__ slots, int nsegs) {
     __shared__ InflMem mem[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sg = blockIdx.x * 4 + warp;
@@ -378,83 +305,255 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
     DecSegD& S = segs[sg];
     const DecPageD& P = pages[S.page];
     if (P.status != 0) return;
-    const bool first = sg == P.seg0, final_seg = sg == P.seg0 + P.nseg - 1;
-    BitReader br; br.init(P.z + S.zoff, S.zlen, mem[warp].zbuf);
+    InflMem& M = mem[warp];
+    const DecSegD* PS = segs + P.seg0;                  // this page's segments
+    const int s_loc = sg - P.seg0;
+    const uint8_t* z = P.z + S.zoff;
+    BitReader br; br.init(z, P.zlen - S.zoff, M.zbuf);
+    uint32_t filled = 0;
     int status = INF_OK;
-    if (first) status = zlib_header(br, P.z);
-    unsigned long long produced = 0; bool fin = false;
-    if (status == INF_OK)
-        status = inflate_blocks<COUNT, uint8_t>(mem[warp], nullptr, br, P.z + S.zoff, nullptr, P.filt_len, 0ull, false, &produced, &fin);
-    // the stream's final block belongs in the last IDAT and nowhere else; its Adler-32 (4 bytes after byte alignment) ends the IDAT
-    if (status == INF_OK && fin != final_seg) status = INF_SEG;
+    unsigned long long start_bit = 0;
+    if (s_loc == 0) { status = zlib_header(z, br.n); start_bit = 16; }
+    if (status == INF_OK) seek_bit(M, br, filled, start_bit);
+    const unsigned long long cap = P.filt_len;
+    unsigned long long pos = 0;                         // output bytes so far
+    // interval being built (lane 0)
+    unsigned long long iv_hdr = start_bit, iv_start = start_bit, iv_out = 0, next_ck = kCkpt;
+    uint32_t niv = 0;
+    int end_seg = s_loc;                                // the segment whose end the parse has not passed yet
+    int last = 0, next = P.nseg;
+    bool done = false;
+    auto emit = [&](unsigned long long out_now, unsigned long long hdr_bit, unsigned long long bit_now) {   // lane 0: close the interval at a token boundary
+        if (out_now > iv_out) {
+            if (niv < S.iv_cap) { DecIvD& I = slots[S.iv0 + niv]; I.hdr_bit = iv_hdr; I.start_bit = iv_start; I.out = (uint32_t)iv_out; I.len = (uint32_t)(out_now - iv_out); I.seg = (uint32_t)sg; }
+            niv++;
+        }
+        iv_hdr = hdr_bit; iv_start = bit_now; iv_out = out_now;
+        next_ck = (out_now / kCkpt + 1) * kCkpt;
+    };
+    while (status == INF_OK && !done) {
+        unsigned long long hdr_bit = 0;
+        if (lane == 0) hdr_bit = br.bits_used();
+        int btype = 0, slen = 0; unsigned long long ssrc = 0;
+        status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
+        if (status != INF_OK) break;
+        if (btype == 0) {
+            if (pos + slen > cap) { status = INF_OVERRUN; break; }
+            pos += slen;
+        } else {
+            bool eob = false;
+            while (status == INF_OK && !eob) {
+                topup(M, br, filled, __shfl_sync(kFull, br.word(), 0));      // 128 tokens eat at most 768 bytes
+                if (lane == 0) {
+                    uint32_t p = (uint32_t)pos;                               // cap < 2^32, a token adds <= 258: no wrap before the checks
+                    uint32_t ck = (uint32_t)min(next_ck, 0xffffffffull);
+                    for (int t = 0; t < 128; t++) {
+                        uint32_t tok;
+                        const int sz = parse_token(M, br, &tok);
+                        if (sz <= 0) { if (sz == 0) eob = true; else status = sz; break; }
+                        p += (unsigned)sz;
+                        if (p >= ck) {
+                            if (p > cap) { status = INF_OVERRUN; break; }
+                            emit(p, hdr_bit, br.bits_used());
+                            ck = (uint32_t)min(next_ck, 0xffffffffull);
+                        }
+                    }
+                    if (br.over && status == INF_OK) status = INF_SHORT;
+                    if (p > cap && status == INF_OK) status = INF_OVERRUN;
+                    pos = p;
+                }
+                status = __shfl_sync(kFull, status, 0); eob = __shfl_sync(kFull, (int)eob, 0) != 0;
+                pos = __shfl_sync(kFull, pos, 0);
+            }
+            if (status != INF_OK) break;
+        }
+        // ---- where did this block end?  (lane 0 decides)
+        int stop = 0;
+        if (lane == 0) {
+            const unsigned long long used = br.bits_used();
+            if (pos >= next_ck) emit(pos, used, used);                       // after a stored block
+            if (last) stop = 1;
+            else {
+                while (end_seg < P.nseg && ((unsigned long long)PS[end_seg].zoff + PS[end_seg].zlen - S.zoff) * 8ull < used) end_seg++;
+                if (end_seg >= P.nseg) status = INF_SHORT;
+                else if (((unsigned long long)PS[end_seg].zoff + PS[end_seg].zlen - S.zoff) * 8ull == used) { stop = 1; next = end_seg + 1; }
+            }
+            if (br.over && status == INF_OK) status = INF_SHORT;
+        }
+        status = __shfl_sync(kFull, status, 0);
+        done = __shfl_sync(kFull, stop, 0) != 0;
+    }
     if (lane == 0) {
-        if (status == INF_OK && fin) { br.drop(br.cnt & 7); if (br.byte_pos() + 4 != br.n) status = INF_SEG; }
-        S.olen = (uint32_t)produced;
-        S.ok = status == INF_OK ? 1 : 0;
+        if (status == INF_OK) { const unsigned long long used = br.bits_used(); emit(pos, used, used); }
+        if (status == INF_OK && niv > S.iv_cap) status = INF_OVERRUN;
+        S.olen = (uint32_t)pos; S.next = next; S.fin = last; S.niv = niv;
+        S.ok = status == INF_OK ? 1 : status;
     }
 }
 
-__global__ void __launch_bounds__(32) k_infl_plan(DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, int n) {
+// Walk the chain of IDATs whose parse began at a true block boundary; copy their intervals, in stream order, with absolute offsets.
+__global__ void __launch_bounds__(32) k_infl_plan(DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, const DecIvD* __restrict__ slots,
+                                                  DecIvD* __restrict__ ivs, int n) {
     const int pg = blockIdx.x, lane = threadIdx.x;
     if (pg >= n) return;
     DecPageD& P = pages[pg];
-    if (P.status != 0 || P.nseg == 0) return;
+    if (P.status != 0) return;
     DecSegD* S = segs + P.seg0;
-    int ok = 1; unsigned long long sum = 0;
-    for (int i = lane; i < P.nseg; i += 32) { ok &= S[i].ok; sum += S[i].olen; }
-    ok = __all_sync(kFull, ok);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
-    const bool par = ok && sum == P.filt_len;
-    if (par) {
-        unsigned long long base = 0;
-        for (int i0 = 0; i0 < P.nseg; i0 += 32) {
-            const int i = i0 + lane;
-            const unsigned long long v = i < P.nseg ? S[i].olen : 0;
-            unsigned long long incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-            if (i < P.nseg) S[i].opos = (uint32_t)(base + incl - v);
-            base += __shfl_sync(kFull, incl, 31);
+    unsigned long long opos = 0; uint32_t niv = 0;
+    int s = 0, fin = 0, status = INF_OK;
+    for (int guard = 0; s < P.nseg && guard <= P.nseg; guard++) {
+        const int ok = S[s].ok;
+        if (ok != 1) { status = ok < 0 ? ok : INF_SEG; break; }
+        if (niv + S[s].niv > (uint32_t)P.iv_cap || opos + S[s].olen > P.filt_len) { status = INF_OVERRUN; break; }
+        for (uint32_t i = lane; i < S[s].niv; i += 32) {
+            DecIvD I = slots[S[s].iv0 + i];
+            I.out += (uint32_t)opos;
+            ivs[P.iv0 + niv + i] = I;
         }
+        if (lane == 0) S[s].opos = (uint32_t)opos;
+        niv += S[s].niv; opos += S[s].olen; fin = S[s].fin;
+        s = S[s].next;
     }
-    if (lane == 0) P.mode = par ? 1 : 0;
+    if (status == INF_OK && (!fin || opos != P.filt_len)) status = INF_SHORT;
+    if (lane == 0) { P.niv = (int32_t)niv; if (status != INF_OK) P.status = status; }
 }
 
-__global__ void __launch_bounds__(32) k_infl_seg(DecPageD* __restrict__ pages, const DecSegD* __restrict__ segs, int nsegs) {
+// ------------------------------------------------------------------------------------------ exec: one warp per interval
+__global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, const DecSegD* __restrict__ segs, const DecIvD* __restrict__ ivs,
+                                                  int npages, int total_cap) {
     __shared__ InflMem M;
-    extern __shared__ __align__(16) uint8_t dyn_smem[];
     const int lane = threadIdx.x;
-    const int sg = blockIdx.x;
-    if (sg >= nsegs) return;
-    const DecSegD& S = segs[sg];
-    DecPageD& P = pages[S.page];
-    if (P.status != 0 || P.mode != 1) return;
-    BitReader br; br.init(P.z + S.zoff, S.zlen, M.zbuf);
-    int status = INF_OK;
-    if (sg == P.seg0) status = zlib_header(br, P.z);
-    unsigned long long produced = 0; bool fin = false;
-    if (status == INF_OK)
-        status = inflate_blocks<SYMS, uint16_t>(M, reinterpret_cast<uint16_t*>(dyn_smem), br, P.z + S.zoff, P.sym + S.opos,
-                                                (unsigned long long)S.olen, (unsigned long long)S.opos, false, &produced, &fin);
-    if (status == INF_OK && produced != S.olen) status = INF_SHORT;
+    const int g = blockIdx.x;
+    if (g >= total_cap) return;
+    int lo = 0, hi = npages - 1;                          // page of slot g: last page with iv0 <= g
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pages[mid].iv0 <= g) lo = mid; else hi = mid - 1; }
+    DecPageD& P = pages[lo];
+    const int li = g - P.iv0;
+    if (P.status != 0 || li >= P.niv) return;
+    const DecIvD I = ivs[g];
+    const DecSegD& S = segs[I.seg];
+    BitReader br; br.init(P.z + S.zoff, P.zlen - S.zoff, M.zbuf);
+    uint32_t filled = 0;
+    seek_bit(M, br, filled, I.hdr_bit);
+    uint16_t* __restrict__ out = P.sym + I.out;
+    const unsigned long long abs0 = I.out;
+    const uint32_t target = I.len;
+    uint32_t pos = 0;
+    int status = INF_OK, last = 0;
+    bool first = true;
+    while (status == INF_OK && pos < target) {
+        int btype = 0, slen = 0; unsigned long long ssrc = 0;
+        status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
+        if (status != INF_OK) break;
+        if (first) {
+            first = false;
+            const unsigned long long used = __shfl_sync(kFull, br.bits_used(), 0);
+            if (I.start_bit > used) {
+                if (btype == 0) { status = INF_SEG; break; }                  // checkpoints never fall inside a stored block
+                seek_bit(M, br, filled, I.start_bit);
+            }
+        }
+        if (btype == 0) {
+            if (pos + (uint32_t)slen > target) { status = INF_SEG; break; }
+            const uint8_t* s = P.z + S.zoff + ssrc;
+            for (int k = lane; k < slen; k += 32) out[pos + k] = (uint16_t)s[k];
+            pos += (uint32_t)slen;
+            __syncwarp();
+            if (last && pos < target) status = INF_SHORT;
+            continue;
+        }
+        bool eob = false;
+        while (status == INF_OK && !eob && pos < target) {
+            // keep the input ring ahead of the parser: a batch of 32 tokens eats at most 192 bytes; the next 64 words are requested
+            // now and land in the ring after the batch (latency hidden behind the parse)
+            const uint32_t w0 = __shfl_sync(kFull, br.word(), 0);
+            uint32_t p0 = 0, p1 = 0; bool pf = false;
+            if (filled < w0 + 96) topup(M, br, filled, w0);
+            else if (filled + 64 <= w0 + kZWords) {
+                pf = true;
+                p0 = __ldg(br.zw + min(filled + lane, br.maxw)); p1 = __ldg(br.zw + min(filled + 32 + lane, br.maxw));
+            }
+            int ntok = 0;
+            if (lane == 0) {
+                uint32_t room = target - pos;
+                for (; ntok < 32 && room > 0; ntok++) {
+                    uint32_t tok;
+                    const int sz = parse_token(M, br, &tok);
+                    if (sz <= 0) { if (sz == 0) eob = true; else status = sz; break; }
+                    if ((uint32_t)sz > room) { status = INF_SEG; break; }    // the probe cut at a token boundary: must land exactly
+                    room -= (uint32_t)sz;
+                    M.tok[ntok] = tok;
+                }
+                if (br.over && status == INF_OK) status = INF_SHORT;
+            }
+            status = __shfl_sync(kFull, status, 0); eob = __shfl_sync(kFull, (int)eob, 0) != 0; ntok = __shfl_sync(kFull, ntok, 0);
+            if (status != INF_OK) break;
+            __syncwarp();
+            const uint32_t t = lane < ntok ? M.tok[lane] : 0u;
+            const bool lit = (t >> 31) != 0u;
+            const int size = lane < ntok ? (lit ? 1 : (int)(t & 511u)) : 0;
+            int incl = size;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(kFull, incl, 31);
+            const uint32_t my = pos + (uint32_t)(incl - size);
+            if (lit) out[my] = (uint16_t)(t & 255u);
+            uint32_t mm = __ballot_sync(kFull, lane < ntok && !lit);
+            __syncwarp();
+            while (mm) {
+                const int f = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t tf = __shfl_sync(kFull, t, f);
+                const uint32_t at = __shfl_sync(kFull, my, f);
+                const int len = (int)(tf & 511u), dist = (int)(tf >> 9);
+                if ((unsigned long long)dist > abs0 + at) { status = INF_BAD_DIST; break; }
+                for (int k0 = 0; k0 < len; k0 += 32) {
+                    const int k = k0 + lane;
+                    if (k < len) {
+                        // the source is the `dist` symbols in front of the match, repeated when it is shorter than the match;
+                        // in front of the interval it is a symbol of its own: 256 + index into the 32 KiB window
+                        const int q = (int)at - dist + (dist >= len ? k : k % dist);
+                        out[at + k] = q < 0 ? (uint16_t)(256 + kWin + q) : out[q];
+                    }
+                }
+                __syncwarp();
+            }
+            if (status != INF_OK) break;
+            if (pf) { M.zbuf[(filled + lane) & (kZWords - 1)] = p0; M.zbuf[(filled + 32 + lane) & (kZWords - 1)] = p1; filled += 64; }
+            __syncwarp();
+            pos += (uint32_t)total;
+        }
+        if (status == INF_OK && eob && last && pos < target) status = INF_SHORT;
+    }
     if (lane == 0 && status != INF_OK) atomicMin(&P.status, status);
 }
 
-// The last 32 KiB of every IDAT, in stream order: symbol -> byte through the (already concrete) 32 KiB in front of the IDAT.
-__global__ void __launch_bounds__(1024) k_infl_window(const DecPageD* __restrict__ pages, const DecSegD* __restrict__ segs, int n) {
+// The last 32 KiB of every interval, in stream order: symbol -> byte through the (already concrete) 32 KiB in front of the interval.
+__global__ void __launch_bounds__(1024) k_infl_window(const DecPageD* __restrict__ pages, const DecIvD* __restrict__ ivs, int n) {
     const int pg = blockIdx.x;
     if (pg >= n) return;
     const DecPageD& P = pages[pg];
-    if (P.status != 0 || P.mode != 1) return;
-    for (int s = 0; s < P.nseg; s++) {
-        const DecSegD& S = segs[P.seg0 + s];
-        const unsigned long long end = (unsigned long long)S.opos + S.olen;
-        const unsigned long long lo = S.olen > (uint32_t)kWin ? end - kWin : S.opos;
-        for (unsigned long long p = lo + threadIdx.x; p < end; p += 1024) {
-            const uint32_t v = P.sym[p];
-            P.filt[p] = v < 256u ? (uint8_t)v : __ldcg(P.filt + ((unsigned long long)S.opos - kWin + (v - 256u)));
+    if (P.status != 0) return;
+    const DecIvD* __restrict__ IV = ivs + P.iv0;
+    const uint16_t* __restrict__ sym = P.sym;           // local copies: a store through P.filt could alias the descriptor otherwise
+    uint8_t* filt = P.filt;
+    const int niv = P.niv;
+    for (int s = 0; s < niv; s++) {
+        const unsigned long long a = IV[s].out, end = a + IV[s].len;
+        const unsigned long long lo = IV[s].len > (uint32_t)kWin ? end - kWin : a;
+        // <= 32 elements per thread, all loads of a stage in flight together (this loop is the one serial chain of the page)
+        const unsigned long long p0 = lo + threadIdx.x;
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) { const unsigned long long p = p0 + 1024ull * i; v[i] = p < end ? sym[p] : 0u; }
+#pragma unroll
+        for (int i = 0; i < 32; i++) {        // unconditional loads (a byte symbol re-reads its own slot): nothing to branch around
+            const unsigned long long p = p0 + 1024ull * i;
+            const bool ref = v[i] >= 256u;
+            const uint32_t g = __ldcg(filt + (ref ? a - kWin + (v[i] - 256u) : (p < end ? p : lo)));
+            v[i] = ref ? g : v[i];
         }
+#pragma unroll
+        for (int i = 0; i < 32; i++) { const unsigned long long p = p0 + 1024ull * i; if (p < end) filt[p] = (uint8_t)v[i]; }
         __syncthreads();
     }
 }
@@ -462,63 +561,56 @@ __global__ void __launch_bounds__(1024) k_infl_window(const DecPageD* __restrict
 __global__ void __launch_bounds__(256) k_infl_resolve(const DecBatchD b) {
     const int ck = blockIdx.x;
     const DecPageD& P = b.pages[b.chunk_page[ck]];
-    if (P.status != 0 || P.mode != 1) return;
-    const DecSegD* __restrict__ S = b.segs + P.seg0;
-    const unsigned long long c0 = b.chunk_pos[ck];
+    if (P.status != 0) return;
+    const DecIvD* __restrict__ S = b.ivs + P.iv0;
+    const int nseg = P.niv;
+    const unsigned long long c0 = b.chunk_pos[ck], flen = P.filt_len;
+    const uint16_t* __restrict__ sym = P.sym;
+    uint8_t* filt = P.filt;
     for (int it = 0; it < kResolveChunk / (256 * 8); it++) {
         const unsigned long long p0 = c0 + (unsigned long long)(it * 256 + threadIdx.x) * 8ull;
-        if (p0 >= P.filt_len) break;
-        // segment of p0: last s with opos <= p0
-        int lo = 0, hi = P.nseg - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((unsigned long long)S[mid].opos <= p0) lo = mid; else hi = mid - 1; }
+        if (p0 >= flen) break;
+        // interval of p0: last s with out <= p0
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((unsigned long long)S[mid].out <= p0) lo = mid; else hi = mid - 1; }
         int s = lo;
-        unsigned long long s_end = (unsigned long long)S[s].opos + S[s].olen;
-        const int cnt = (int)min(8ull, P.filt_len - p0);
+        unsigned long long s_end = (unsigned long long)S[s].out + S[s].len;
+        const int cnt = (int)min(8ull, flen - p0);
         uint16_t v8[8];
-        if (cnt == 8) { const uint4 q = *reinterpret_cast<const uint4*>(P.sym + p0); memcpy(v8, &q, 16); }
-        else for (int k = 0; k < cnt; k++) v8[k] = P.sym[p0 + k];
+        if (cnt == 8) { const uint4 q = *reinterpret_cast<const uint4*>(sym + p0); memcpy(v8, &q, 16); }
+        else for (int k = 0; k < cnt; k++) v8[k] = sym[p0 + k];
         uint8_t o8[8]; bool all = cnt == 8;
         for (int k = 0; k < cnt; k++) {
             const unsigned long long p = p0 + k;
-            while (p >= s_end && s + 1 < P.nseg) { s++; s_end = (unsigned long long)S[s].opos + S[s].olen; }
+            while (p >= s_end && s + 1 < nseg) { s++; s_end = (unsigned long long)S[s].out + S[s].len; }
             const bool tail = p + kWin >= s_end;         // concrete already (k_infl_window)
             const uint32_t v = v8[k];
             uint8_t o = (uint8_t)v;
-            if (!tail && v >= 256u) o = P.filt[(unsigned long long)S[s].opos - kWin + (v - 256u)];
+            if (!tail && v >= 256u) o = __ldg(filt + (unsigned long long)S[s].out - kWin + (v - 256u));
             if (tail) all = false;
             o8[k] = o;
             v8[k] = tail ? 1 : 0;
         }
-        if (all) { uint2 w; memcpy(&w, o8, 8); *reinterpret_cast<uint2*>(P.filt + p0) = w; }
-        else for (int k = 0; k < cnt; k++) if (!v8[k]) P.filt[p0 + k] = o8[k];
+        if (all) { uint2 w; memcpy(&w, o8, 8); *reinterpret_cast<uint2*>(filt + p0) = w; }
+        else for (int k = 0; k < cnt; k++) if (!v8[k]) filt[p0 + k] = o8[k];
     }
 }
 
-int decode_kernel_setup() {
-    cudaError_t e = cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, kWin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_infl_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, kWin * 2);
-    return e == cudaSuccess ? 0 : -1;
-}
+int decode_kernel_setup() { return 0; }
 
 int launch_inflate(const DecBatchD& b, cudaStream_t st) {
-    if (b.npages == 0) return 0;
-    int launches = 0;
-    if (b.nsegs) {
-        k_infl_probe<<<(b.nsegs + 3) / 4, 128, 0, st>>>(b.pages, b.segs, b.nsegs);
-        k_infl_plan<<<b.npages, 32, 0, st>>>(b.pages, b.segs, b.npages);
-        k_infl_seg<<<b.nsegs, 32, kWin * 2, st>>>(b.pages, b.segs, b.nsegs);
-        k_infl_window<<<b.npages, 1024, 0, st>>>(b.pages, b.segs, b.npages);
-        if (b.nchunks) k_infl_resolve<<<b.nchunks, 256, 0, st>>>(b);
-        launches += 4 + (b.nchunks ? 1 : 0);
-    }
-    k_inflate<<<b.npages, 32, kWin, st>>>(b.pages, b.npages);
-    return launches + 1;
+    if (b.npages == 0 || b.nsegs == 0) return 0;
+    k_infl_probe<<<(b.nsegs + 3) / 4, 128, 0, st>>>(b.pages, b.segs, b.slots, b.nsegs);
+    k_infl_plan<<<b.npages, 32, 0, st>>>(b.pages, b.segs, b.slots, b.ivs, b.npages);
+    k_infl_exec<<<b.iv_total, 32, 0, st>>>(b.pages, b.segs, b.ivs, b.npages, b.iv_total);
+    k_infl_window<<<b.npages, 1024, 0, st>>>(b.pages, b.ivs, b.npages);
+    if (b.nchunks) k_infl_resolve<<<b.nchunks, 256, 0, st>>>(b);
+    return 4 + (b.nchunks ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------ un-filter
 namespace {
 
-constexpr int kUfWarps = 4;
 constexpr int kUfPitch = 136;             // bytes per staged row: up to 3 + 32 pixels x 4 channels, as 34 words (bank = 2 * lane + const)
 
 struct UfMem {                            // views of one warp's staging buffers (separate __shared__ arrays: loads of `in` may pass stores to `out`)
@@ -636,25 +728,24 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
 
 }  // namespace
 
-__global__ void __launch_bounds__(kUfWarps * 32) k_unfilter(const DecBatchD b) {
-    __shared__ uint32_t s_in[kUfWarps][32][kUfPitch / 4];
-    __shared__ uint8_t s_out[kUfWarps][32][kUfPitch];
-    __shared__ uint32_t s_up[kUfWarps][kUfPitch / 4];
-    __shared__ uint32_t ticket;
-    if (threadIdx.x == 0) ticket = atomicAdd(b.counters, 1u);
-    __syncthreads();
-    const int warp = threadIdx.x >> 5;
-    const UfMem mem_w{s_in[warp], s_out[warp], s_up[warp]};
-    const int g = (int)ticket * kUfWarps + warp;          // global band number, in launch order
-    if (g >= b.nbands) return;
-    int lo = 0, hi = b.npages - 1;                        // page of band g: last page with band0 <= g (pages without bands repeat band0)
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.pages[mid].band0 <= g) lo = mid; else hi = mid - 1; }
-    DecPageD& P = b.pages[lo];
-    const int band = g - P.band0;
+__global__ void __launch_bounds__(32) k_unfilter(const DecBatchD b) {
+    __shared__ uint32_t s_in[32][kUfPitch / 4];
+    __shared__ uint8_t s_out[32][kUfPitch];
+    __shared__ uint32_t s_up[kUfPitch / 4];
+    // One band per CTA (a finished band frees its slot at once).  Bands are handed out by ticket, band-major over the pages of
+    // the batch (band 0 of every page, then band 1, ...): a band only waits on one that holds an earlier ticket, and the resident
+    // CTAs are the pipeline fronts of all pages rather than all bands of a few.
+    uint32_t t = 0;
+    if (threadIdx.x == 0) t = atomicAdd(b.counters, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if ((int)t >= b.nbands) return;
+    const UfMem mem_w{s_in, s_out, s_up};
+    DecPageD& P = b.pages[b.band_page[t]];
+    const int band = (int)b.band_idx[t];
     uint32_t* flags = b.band_flag + P.band0;
     int bad = 0;
     if (P.status != 0) {                                  // a skipped band still releases the bands waiting on it
-        if ((threadIdx.x & 31) == 0) *(volatile uint32_t*)(flags + band) = 0xffffffffu;
+        if (threadIdx.x == 0) *(volatile uint32_t*)(flags + band) = 0xffffffffu;
     } else {
         switch (P.c) {
             case 1: unfilter_band<1>(mem_w, P, band, flags, &bad, b.dbg_nowait != 0); break;
@@ -663,12 +754,12 @@ __global__ void __launch_bounds__(kUfWarps * 32) k_unfilter(const DecBatchD b) {
             default: unfilter_band<4>(mem_w, P, band, flags, &bad, b.dbg_nowait != 0); break;
         }
     }
-    if (__any_sync(kFull, bad) && (threadIdx.x & 31) == 0) atomicMin(&P.status, (int)INF_BAD_FILTER);
+    if (__any_sync(kFull, bad) && threadIdx.x == 0) atomicMin(&P.status, (int)INF_BAD_FILTER);
 }
 
 int launch_unfilter(const DecBatchD& b, cudaStream_t st) {
     if (b.nbands == 0) return 0;
-    k_unfilter<<<(b.nbands + kUfWarps - 1) / kUfWarps, kUfWarps * 32, 0, st>>>(b);
+    k_unfilter<<<b.nbands, 32, 0, st>>>(b);
     return 1;
 }
 

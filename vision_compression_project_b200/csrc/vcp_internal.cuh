@@ -101,27 +101,42 @@ struct DecPageD {
     const uint8_t* z; unsigned long long zlen;      // concatenated IDAT payloads (one zlib stream)
     uint8_t* filt; unsigned long long filt_len;     // h * (1 + w*c)
     uint8_t* pix;                                   // w*h*c
-    uint16_t* sym;                                  // filt_len symbolic bytes (segment-parallel inflate), nullptr when nseg == 0
+    uint16_t* sym;                                  // filt_len symbolic bytes (see k_infl_exec)
     int32_t w, h, c;
     int32_t status;                                 // 0 or a negative inflate / un-filter error
-    int32_t seg0, nseg;                             // IDAT segments of this page in the DecSegD array (nseg == 0: serial inflate only)
-    int32_t mode;                                   // written by k_infl_plan: 1 = every IDAT is a run of whole deflate blocks -> segment-parallel
+    int32_t seg0, nseg;                             // IDAT segments of this page in the DecSegD array
+    int32_t iv0, iv_cap, niv;                       // its intervals in the DecIvD array (niv written by k_infl_plan)
     int32_t band0;                                  // first 32-row band of this page in the un-filter's band numbering
 };
 
-// One IDAT chunk of a PNG being decoded: a candidate for independent inflation.
+// One IDAT chunk of a PNG being decoded: a place where a parse may begin (k_infl_probe).
 struct DecSegD {
     uint32_t page;
     uint32_t zoff, zlen;     // byte range inside the page's zlib stream
-    uint32_t olen, opos;     // bytes it inflates to (k_infl_probe) and where they start in the filtered stream (k_infl_plan)
-    int32_t ok;              // 1 = the range is a whole number of deflate blocks (and ends the stream iff it is the last one)
+    uint32_t olen, opos;     // bytes its parse produced (k_infl_probe) and where they start in the filtered stream (k_infl_plan)
+    int32_t ok;              // 1 = the parse ended on a block boundary that is an IDAT boundary (or the end of the stream); < 0 error
+    int32_t next;            // the IDAT (index within the page) in front of which it ended
+    int32_t fin;             // it met the final block
+    uint32_t niv;            // intervals it wrote
+    uint32_t iv0, iv_cap;    // its private range of checkpoint slots
+};
+
+// A stretch of tokens between two checkpoints of a parse: the unit of k_infl_exec.
+struct DecIvD {
+    unsigned long long hdr_bit;    // bit position (relative to the segment's first byte) of the header of the deflate block it starts in
+    unsigned long long start_bit;  // bit position of its first token
+    uint32_t out, len;             // output range (relative to the segment in the probe's slots, absolute after k_infl_plan)
+    uint32_t seg, pad;
 };
 
 struct DecBatchD {
     DecPageD* pages; int32_t npages;
     DecSegD* segs; int32_t nsegs;
+    DecIvD* slots;                                                            // checkpoint slots, one private range per segment
+    DecIvD* ivs; int32_t iv_total;                                            // intervals in stream order, one range per page
     const uint32_t* chunk_page; const uint32_t* chunk_pos; int32_t nchunks;   // resolve work list: 32 Ki positions each
     uint32_t* band_flag; int32_t nbands;                                      // un-filter progress per band (zeroed per launch)
+    const uint32_t* band_page; const uint32_t* band_idx;                      // un-filter work list in ticket order (band-major over pages)
     uint32_t* counters;                                                       // [0] un-filter CTA ticket (zeroed per launch)
     int32_t dbg_nowait;                                                       // timing experiments only: bands do not wait (wrong pixels)
 };
