@@ -540,20 +540,24 @@ __global__ void __launch_bounds__(1024) k_infl_window(const DecPageD* __restrict
     for (int s = 0; s < niv; s++) {
         const unsigned long long a = IV[s].out, end = a + IV[s].len;
         const unsigned long long lo = IV[s].len > (uint32_t)kWin ? end - kWin : a;
-        // <= 32 elements per thread, all loads of a stage in flight together (this loop is the one serial chain of the page)
-        const unsigned long long p0 = lo + threadIdx.x;
-        uint32_t v[32];
+        // <= 32 elements per thread in two rounds of 16, all loads of a stage in flight together (this loop is the one serial
+        // chain of the page; 16 keeps the round in registers at 1024 threads)
+        for (int h = 0; h < 2; h++) {
+            const unsigned long long p0 = lo + threadIdx.x + 16384ull * h;
+            if (p0 >= end) break;
+            uint32_t v[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) { const unsigned long long p = p0 + 1024ull * i; v[i] = p < end ? sym[p] : 0u; }
+            for (int i = 0; i < 16; i++) { const unsigned long long p = p0 + 1024ull * i; v[i] = p < end ? sym[p] : 0u; }
 #pragma unroll
-        for (int i = 0; i < 32; i++) {        // unconditional loads (a byte symbol re-reads its own slot): nothing to branch around
-            const unsigned long long p = p0 + 1024ull * i;
-            const bool ref = v[i] >= 256u;
-            const uint32_t g = __ldcg(filt + (ref ? a - kWin + (v[i] - 256u) : (p < end ? p : lo)));
-            v[i] = ref ? g : v[i];
+            for (int i = 0; i < 16; i++) {    // unconditional loads (a byte symbol re-reads its own slot): nothing to branch around
+                const unsigned long long p = p0 + 1024ull * i;
+                const bool ref = v[i] >= 256u;
+                const uint32_t g = __ldcg(filt + (ref ? a - kWin + (v[i] - 256u) : (p < end ? p : lo)));
+                v[i] = ref ? g : v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i++) { const unsigned long long p = p0 + 1024ull * i; if (p < end) filt[p] = (uint8_t)v[i]; }
         }
-#pragma unroll
-        for (int i = 0; i < 32; i++) { const unsigned long long p = p0 + 1024ull * i; if (p < end) filt[p] = (uint8_t)v[i]; }
         __syncthreads();
     }
 }
