@@ -265,26 +265,57 @@ __device__ int block_header(InflMem& M, BitReader& br, uint32_t& filled, int* la
     return INF_OK;
 }
 
-// lane 0: one token.  Returns its output size (1 literal, 3..258 match), 0 for end of block, < 0 for an error; *tok in batch form.
-__device__ __forceinline__ int parse_token(InflMem& M, BitReader& br, uint32_t* tok) {
-    br.need33();
-    const uint32_t e = decode_entry<T_LL>(br, M.fast_ll, kFastLL, M.cnt_ll, M.sorted_ll);
-    br.drop((int)(e & 15u));
-    const uint32_t kind = (e >> 8) & 3u;
-    if (kind == K_LIT) { *tok = 0x80000000u | (e >> 16); return 1; }
-    if (kind != K_LEN) return kind == K_EOB ? 0 : INF_BAD_CODE;
-    const int xl = (int)((e >> 4) & 15u);
-    const int len = (int)(e >> 16) + (int)br.peek(xl);
-    br.drop(xl);
-    br.need33();
-    const uint32_t d = decode_entry<T_D>(br, M.fast_d, kFastD, M.cnt_d, M.sorted_d);
-    if (((d >> 8) & 3u) == K_BAD) return INF_BAD_CODE;
-    br.drop((int)(d & 15u));
-    const int xd = (int)((d >> 4) & 15u);
-    const uint32_t dist = (d >> 16) + br.peek(xd);
-    br.drop(xd);
-    *tok = (dist << 9) | (uint32_t)len;
-    return len;
+
+// ---- warp-parallel token parse.  Where a token starts is only known once the one in front of it has been decoded, but *what* a
+// token would be if it started at a given bit can be looked up for 32 consecutive bits at once: lane l decodes a whole token
+// (literal, or length + distance with their extra bits) as if it began at bit B + l.  The true tokens are then found by following
+// the chain 0 -> tb(0) -> ... with one shuffle per token, instead of a dependent table lookup, shifts and branches per token.
+enum { SP_EOB = 1 << 15, SP_BAD = 1 << 16, SP_SLOW = 1 << 17 };    // info = bits | size << 6 | flags
+
+template <bool ALLOW_SLOW>
+__device__ __forceinline__ void spec_decode(const InflMem& M, uint32_t w0, uint32_t w1, uint32_t* info, uint32_t* tok) {
+    uint32_t e = M.fast_ll[w0 & ((1u << kFastLL) - 1u)];
+    if ((e & 15u) == 0u) {
+        if (!ALLOW_SLOW) { *info = SP_SLOW; return; }
+        int code = 0, first = 0, index = 0; uint32_t b = w0; e = ((uint32_t)K_BAD << 8) | 1u;
+        for (int l = 1; l <= 15; l++) {
+            code |= (int)(b & 1u); b >>= 1;
+            const int c = M.cnt_ll[l];
+            if (code - c < first) { e = sym_entry<T_LL>(M.sorted_ll[index + (code - first)]) | (uint32_t)l; break; }
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+    }
+    const uint32_t nb = e & 15u, kind = (e >> 8) & 3u, val = e >> 16;
+    if (kind == K_LIT) { *info = nb | (1u << 6); *tok = 0x80000000u | val; return; }
+    if (kind != K_LEN) { *info = nb | (kind == K_EOB ? SP_EOB : SP_BAD); return; }
+    const uint32_t xl = (e >> 4) & 15u;
+    const uint32_t len = val + ((w0 >> nb) & ((1u << xl) - 1u));
+    const uint32_t c1 = nb + xl;                                             // <= 20
+    const uint32_t w2 = __funnelshift_r(w0, w1, c1);
+    uint32_t d = M.fast_d[w2 & ((1u << kFastD) - 1u)];
+    if ((d & 15u) == 0u) {
+        if (!ALLOW_SLOW) { *info = SP_SLOW; return; }
+        int code = 0, first = 0, index = 0; uint32_t b = w2; d = ((uint32_t)K_BAD << 8) | 1u;
+        for (int l = 1; l <= 15; l++) {
+            code |= (int)(b & 1u); b >>= 1;
+            const int c = M.cnt_d[l];
+            if (code - c < first) { d = sym_entry<T_D>(M.sorted_d[index + (code - first)]) | (uint32_t)l; break; }
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+    }
+    if (((d >> 8) & 3u) == K_BAD) { *info = SP_BAD; return; }
+    const uint32_t nbd = d & 15u, xd = (d >> 4) & 15u;
+    const uint32_t dist = (d >> 16) + ((w2 >> nbd) & ((1u << xd) - 1u));     // nbd + xd <= 28
+    *info = (c1 + nbd + xd) | (len << 6);
+    *tok = (dist << 9) | len;
+}
+
+// the 64 stream bits that start at bit position `bit` (relative to the first byte of the stream), from the shared-memory ring
+__device__ __forceinline__ void ring_window(const InflMem& M, const BitReader& br, unsigned long long bit, uint32_t* w0, uint32_t* w1) {
+    const unsigned long long a = bit + 8ull * (unsigned)br.mis;
+    const uint32_t i = (uint32_t)(a >> 5); const int sh = (int)(a & 31);
+    const uint32_t x0 = M.zbuf[i & (kZWords - 1)], x1 = M.zbuf[(i + 1) & (kZWords - 1)], x2 = M.zbuf[(i + 2) & (kZWords - 1)];
+    *w0 = __funnelshift_r(x0, x1, sh); *w1 = __funnelshift_r(x1, x2, sh);
 }
 
 // all lanes: check the two zlib header bytes; the deflate data starts at bit 16
@@ -342,29 +373,39 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
             pos += slen;
         } else {
             bool eob = false;
+            unsigned long long B = __shfl_sync(kFull, br.bits_used(), 0);      // bit position of the next token
+            uint32_t p = (uint32_t)pos;                                       // cap < 2^32, a token adds <= 258: no wrap before the checks
+            uint32_t ck = (uint32_t)min(__shfl_sync(kFull, next_ck, 0), 0xffffffffull);
             while (status == INF_OK && !eob) {
-                topup(M, br, filled, __shfl_sync(kFull, br.word(), 0));      // 128 tokens eat at most 768 bytes
-                if (lane == 0) {
-                    uint32_t p = (uint32_t)pos;                               // cap < 2^32, a token adds <= 258: no wrap before the checks
-                    uint32_t ck = (uint32_t)min(next_ck, 0xffffffffull);
-                    for (int t = 0; t < 128; t++) {
-                        uint32_t tok;
-                        const int sz = parse_token(M, br, &tok);
-                        if (sz <= 0) { if (sz == 0) eob = true; else status = sz; break; }
-                        p += (unsigned)sz;
+                if (B > br.n * 8ull + 64ull) { status = INF_SHORT; break; }
+                topup(M, br, filled, (uint32_t)((B + 8ull * (unsigned)br.mis) >> 5));
+                for (int r = 0; r < 48 && !eob && status == INF_OK; r++) {    // 48 rounds eat at most 48 * 79 bits = 119 words
+                    uint32_t w0, w1, info = 0, tok = 0;
+                    ring_window(M, br, B + lane, &w0, &w1);
+                    spec_decode<false>(M, w0, w1, &info, &tok);
+                    int o = 0;
+                    while (o < 32) {
+                        uint32_t inf = __shfl_sync(kFull, info, o);
+                        if (inf & SP_SLOW) {
+                            if (lane == o) spec_decode<true>(M, w0, w1, &info, &tok);
+                            inf = __shfl_sync(kFull, info, o);
+                        }
+                        if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
+                        o += (int)(inf & 63u);
+                        if (inf & SP_EOB) { eob = true; break; }
+                        p += (inf >> 6) & 511u;
                         if (p >= ck) {
                             if (p > cap) { status = INF_OVERRUN; break; }
-                            emit(p, hdr_bit, br.bits_used());
-                            ck = (uint32_t)min(next_ck, 0xffffffffull);
+                            if (lane == 0) emit(p, hdr_bit, B + o);
+                            ck = (uint32_t)min(((unsigned long long)p / kCkpt + 1) * kCkpt, 0xffffffffull);
                         }
                     }
-                    if (br.over && status == INF_OK) status = INF_SHORT;
-                    if (p > cap && status == INF_OK) status = INF_OVERRUN;
-                    pos = p;
+                    B += o;
                 }
-                status = __shfl_sync(kFull, status, 0); eob = __shfl_sync(kFull, (int)eob, 0) != 0;
-                pos = __shfl_sync(kFull, pos, 0);
             }
+            if (status == INF_OK && p > cap) status = INF_OVERRUN;
+            pos = p;
+            if (status == INF_OK) seek_bit(M, br, filled, B);                 // the header reader continues behind the end-of-block code
             if (status != INF_OK) break;
         }
         // ---- where did this block end?  (lane 0 decides)
@@ -445,12 +486,12 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
         int btype = 0, slen = 0; unsigned long long ssrc = 0;
         status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
         if (status != INF_OK) break;
+        unsigned long long B = __shfl_sync(kFull, br.bits_used(), 0);         // bit position of the next token
         if (first) {
             first = false;
-            const unsigned long long used = __shfl_sync(kFull, br.bits_used(), 0);
-            if (I.start_bit > used) {
+            if (I.start_bit > B) {
                 if (btype == 0) { status = INF_SEG; break; }                  // checkpoints never fall inside a stored block
-                seek_bit(M, br, filled, I.start_bit);
+                B = I.start_bit;
             }
         }
         if (btype == 0) {
@@ -466,7 +507,8 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
         while (status == INF_OK && !eob && pos < target) {
             // keep the input ring ahead of the parser: a batch of 32 tokens eats at most 192 bytes; the next 64 words are requested
             // now and land in the ring after the batch (latency hidden behind the parse)
-            const uint32_t w0 = __shfl_sync(kFull, br.word(), 0);
+            if (B > br.n * 8ull + 64ull) { status = INF_SHORT; break; }
+            const uint32_t w0 = (uint32_t)((B + 8ull * (unsigned)br.mis) >> 5);
             uint32_t p0 = 0, p1 = 0; bool pf = false;
             if (filled < w0 + 96) topup(M, br, filled, w0);
             else if (filled + 64 <= w0 + kZWords) {
@@ -474,19 +516,27 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
                 p0 = __ldg(br.zw + min(filled + lane, br.maxw)); p1 = __ldg(br.zw + min(filled + 32 + lane, br.maxw));
             }
             int ntok = 0;
-            if (lane == 0) {
-                uint32_t room = target - pos;
-                for (; ntok < 32 && room > 0; ntok++) {
-                    uint32_t tok;
-                    const int sz = parse_token(M, br, &tok);
-                    if (sz <= 0) { if (sz == 0) eob = true; else status = sz; break; }
-                    if ((uint32_t)sz > room) { status = INF_SEG; break; }    // the probe cut at a token boundary: must land exactly
-                    room -= (uint32_t)sz;
-                    M.tok[ntok] = tok;
+            uint32_t room = target - pos;
+            while (ntok < 32 && room > 0 && !eob && status == INF_OK) {
+                uint32_t x0, x1, info = 0, tok = 0;
+                ring_window(M, br, B + lane, &x0, &x1);
+                spec_decode<false>(M, x0, x1, &info, &tok);
+                int o = 0;
+                while (o < 32 && ntok < 32 && room > 0) {
+                    uint32_t inf = __shfl_sync(kFull, info, o);
+                    if (inf & SP_SLOW) {
+                        if (lane == o) spec_decode<true>(M, x0, x1, &info, &tok);
+                        inf = __shfl_sync(kFull, info, o);
+                    }
+                    if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
+                    if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
+                    const uint32_t sz = (inf >> 6) & 511u;
+                    if (sz > room) { status = INF_SEG; break; }               // the probe cut at a token boundary: must land exactly
+                    if (lane == o) M.tok[ntok] = tok;
+                    ntok++; room -= sz; o += (int)(inf & 63u);
                 }
-                if (br.over && status == INF_OK) status = INF_SHORT;
+                B += o;
             }
-            status = __shfl_sync(kFull, status, 0); eob = __shfl_sync(kFull, (int)eob, 0) != 0; ntok = __shfl_sync(kFull, ntok, 0);
             if (status != INF_OK) break;
             __syncwarp();
             const uint32_t t = lane < ntok ? M.tok[lane] : 0u;
@@ -523,6 +573,7 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
             pos += (uint32_t)total;
         }
         if (status == INF_OK && eob && last && pos < target) status = INF_SHORT;
+        if (status == INF_OK && pos < target) seek_bit(M, br, filled, B);     // the header reader continues behind the end-of-block code
     }
     if (lane == 0 && status != INF_OK) atomicMin(&P.status, status);
 }
