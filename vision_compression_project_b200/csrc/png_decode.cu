@@ -556,6 +556,19 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
                 const uint32_t at = __shfl_sync(kFull, my, f);
                 const int len = (int)(tf & 511u), dist = (int)(tf >> 9);
                 if ((unsigned long long)dist > abs0 + at) { status = INF_BAD_DIST; break; }
+                if (dist == 1) {
+                    // a run (most bytes of a page sit in 258-long ones): one symbol, stored four at a time
+                    const uint32_t v = at == 0 ? (uint32_t)(256 + kWin - 1) : (uint32_t)out[at - 1];
+                    uint16_t* d = out + at;
+                    const int head = min(len, (int)((4u - (uint32_t)(((uintptr_t)d >> 1) & 3u)) & 3u));
+                    const int body = (len - head) >> 2, tail0 = head + 4 * body;
+                    if (lane < head) d[lane] = (uint16_t)v;
+                    const uint2 vv = make_uint2(v | (v << 16), v | (v << 16));
+                    for (int i = lane; i < body; i += 32) reinterpret_cast<uint2*>(d + head)[i] = vv;
+                    if (lane < len - tail0) d[tail0 + lane] = (uint16_t)v;
+                    __syncwarp();
+                    continue;
+                }
                 for (int k0 = 0; k0 < len; k0 += 32) {
                     const int k = k0 + lane;
                     if (k < len) {
