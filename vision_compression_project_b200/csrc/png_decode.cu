@@ -32,6 +32,9 @@
 //                  range from a ticket, so a band only ever waits on bands that are already running.
 // Every loop is bounded by the stream / output length: malformed input ends in a status, never in a hang.
 #include "vcp_internal.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace vcp {
 
@@ -592,37 +595,42 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
 }
 
 // The last 32 KiB of every interval, in stream order: symbol -> byte through the (already concrete) 32 KiB in front of the interval.
-__global__ void __launch_bounds__(1024) k_infl_window(const DecPageD* __restrict__ pages, const DecIvD* __restrict__ ivs, int n) {
-    const int pg = blockIdx.x;
+// This is the one serial chain of a page (one step per interval), so a step is spread over a cluster of 8 CTAs (8 SMs) that meet at
+// the hardware cluster barrier: 4 elements per thread, three dependent L2 round trips and one barrier per step.
+constexpr int kWinCluster = 8;
+__global__ void __cluster_dims__(kWinCluster, 1, 1) __launch_bounds__(1024) k_infl_window(const DecPageD* __restrict__ pages, const DecIvD* __restrict__ ivs, int n) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int pg = blockIdx.x / kWinCluster;
+    const unsigned rank = cluster.block_rank();
     if (pg >= n) return;
     const DecPageD& P = pages[pg];
-    if (P.status != 0) return;
+    if (P.status != 0) return;                          // the same for every CTA of the cluster
     const DecIvD* __restrict__ IV = ivs + P.iv0;
     const uint16_t* __restrict__ sym = P.sym;           // local copies: a store through P.filt could alias the descriptor otherwise
     uint8_t* filt = P.filt;
     const int niv = P.niv;
+    constexpr int E = kWin / (kWinCluster * 1024);      // elements per thread per step
+    unsigned long long a = niv ? IV[0].out : 0; uint32_t len = niv ? IV[0].len : 0;
     for (int s = 0; s < niv; s++) {
-        const unsigned long long a = IV[s].out, end = a + IV[s].len;
-        const unsigned long long lo = IV[s].len > (uint32_t)kWin ? end - kWin : a;
-        // <= 32 elements per thread in two rounds of 16, all loads of a stage in flight together (this loop is the one serial
-        // chain of the page; 16 keeps the round in registers at 1024 threads)
-        for (int h = 0; h < 2; h++) {
-            const unsigned long long p0 = lo + threadIdx.x + 16384ull * h;
-            if (p0 >= end) break;
-            uint32_t v[16];
+        const unsigned long long end = a + len;
+        const unsigned long long lo = len > (uint32_t)kWin ? end - kWin : a;
+        const unsigned long long p0 = lo + rank * 1024u + threadIdx.x;
+        unsigned long long a_next = 0; uint32_t len_next = 0;
+        if (s + 1 < niv) { a_next = IV[s + 1].out; len_next = IV[s + 1].len; }      // in flight with this step's loads
+        uint32_t v[E];
 #pragma unroll
-            for (int i = 0; i < 16; i++) { const unsigned long long p = p0 + 1024ull * i; v[i] = p < end ? sym[p] : 0u; }
+        for (int i = 0; i < E; i++) { const unsigned long long p = p0 + (unsigned long long)(kWinCluster * 1024) * i; v[i] = p < end ? sym[p] : 0u; }
 #pragma unroll
-            for (int i = 0; i < 16; i++) {    // unconditional loads (a byte symbol re-reads its own slot): nothing to branch around
-                const unsigned long long p = p0 + 1024ull * i;
-                const bool ref = v[i] >= 256u;
-                const uint32_t g = __ldcg(filt + (ref ? a - kWin + (v[i] - 256u) : (p < end ? p : lo)));
-                v[i] = ref ? g : v[i];
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) { const unsigned long long p = p0 + 1024ull * i; if (p < end) filt[p] = (uint8_t)v[i]; }
+        for (int i = 0; i < E; i++) {         // unconditional loads (a byte symbol re-reads its own slot): nothing to branch around
+            const unsigned long long p = p0 + (unsigned long long)(kWinCluster * 1024) * i;
+            const bool ref = v[i] >= 256u;
+            const uint32_t g = __ldcg(filt + (ref ? a - kWin + (v[i] - 256u) : (p < end ? p : lo)));
+            v[i] = ref ? g : v[i];
         }
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < E; i++) { const unsigned long long p = p0 + (unsigned long long)(kWinCluster * 1024) * i; if (p < end) filt[p] = (uint8_t)v[i]; }
+        cluster.sync();                       // release / acquire at cluster scope: the next step reads these bytes through L2
+        a = a_next; len = len_next;
     }
 }
 
@@ -671,7 +679,7 @@ int launch_inflate(const DecBatchD& b, cudaStream_t st) {
     k_infl_probe<<<(b.nsegs + 3) / 4, 128, 0, st>>>(b.pages, b.segs, b.slots, b.nsegs);
     k_infl_plan<<<b.npages, 32, 0, st>>>(b.pages, b.segs, b.slots, b.ivs, b.npages);
     k_infl_exec<<<b.iv_total, 32, 0, st>>>(b.pages, b.segs, b.ivs, b.npages, b.iv_total);
-    k_infl_window<<<b.npages, 1024, 0, st>>>(b.pages, b.ivs, b.npages);
+    k_infl_window<<<b.npages * kWinCluster, 1024, 0, st>>>(b.pages, b.ivs, b.npages);
     if (b.nchunks) k_infl_resolve<<<b.nchunks, 256, 0, st>>>(b);
     return 4 + (b.nchunks ? 1 : 0);
 }
