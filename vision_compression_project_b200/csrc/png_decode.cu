@@ -389,13 +389,15 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
                     int o = 0;
                     while (o < 32) {
                         uint32_t inf = __shfl_sync(kFull, info, o);
-                        if (inf & SP_SLOW) {
-                            if (lane == o) spec_decode<true>(M, w0, w1, &info, &tok);
-                            inf = __shfl_sync(kFull, info, o);
+                        if (inf & (SP_SLOW | SP_BAD | SP_EOB)) {              // the common token pays one test for all three
+                            if (inf & SP_SLOW) {
+                                if (lane == o) spec_decode<true>(M, w0, w1, &info, &tok);
+                                inf = __shfl_sync(kFull, info, o);
+                            }
+                            if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
+                            if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
                         }
-                        if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
                         o += (int)(inf & 63u);
-                        if (inf & SP_EOB) { eob = true; break; }
                         p += (inf >> 6) & 511u;
                         if (p >= ck) {
                             if (p > cap) { status = INF_OVERRUN; break; }
@@ -527,12 +529,14 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
                 int o = 0;
                 while (o < 32 && ntok < 32 && room > 0) {
                     uint32_t inf = __shfl_sync(kFull, info, o);
-                    if (inf & SP_SLOW) {
-                        if (lane == o) spec_decode<true>(M, x0, x1, &info, &tok);
-                        inf = __shfl_sync(kFull, info, o);
+                    if (inf & (SP_SLOW | SP_BAD | SP_EOB)) {
+                        if (inf & SP_SLOW) {
+                            if (lane == o) spec_decode<true>(M, x0, x1, &info, &tok);
+                            inf = __shfl_sync(kFull, info, o);
+                        }
+                        if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
+                        if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
                     }
-                    if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
-                    if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
                     const uint32_t sz = (inf >> 6) & 511u;
                     if (sz > room) { status = INF_SEG; break; }               // the probe cut at a token boundary: must land exactly
                     if (lane == o) M.tok[ntok] = tok;
@@ -753,6 +757,7 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
     stage();
     uint32_t cur = 0, bprev = 0;              // packed channels: my pixel x-1, the pixel above x-1
     const int ka = ft == 1 ? -1 : 0, kb = ft == 2 ? -1 : 0, kavg = ft == 3 ? -1 : 0, kp = ft == 4 ? -1 : 0;
+    const bool simple = __all_sync(kFull, ft <= 2);
     for (int j = 0; j < nchunks; j++) {
         if (j + 1 < nchunks) fetch(j + 1);
         const uint8_t* inb = reinterpret_cast<const uint8_t*>(M.in[lane]) +
@@ -765,6 +770,24 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
             for (int ch = 0; ch < BPP; ch++) upv |= (uint32_t)upb[lane * BPP + ch] << (8 * ch);
         }
         uint8_t* outb = M.out[lane];
+        if (simple) {
+            // no Avg / Paeth row in the band (blank paper is all Up): the predictor is a or b, four channels at a time
+            const uint32_t ma = (uint32_t)ka, mb = (uint32_t)kb;
+#pragma unroll 8
+            for (int s = 0; s < 32; s++) {
+                const int x = 32 * j + s - lane;
+                const uint32_t bs = __shfl_up_sync(kFull, cur, 1), b0 = __shfl_sync(kFull, upv, s);
+                const uint32_t b = lane == 0 ? b0 : bs;
+                uint32_t r = 0;
+#pragma unroll
+                for (int ch = 0; ch < BPP; ch++) r |= (uint32_t)inb[s * BPP + ch] << (8 * ch);
+                const uint32_t o = __vadd4(r, (cur & ma) | (b & mb));
+#pragma unroll
+                for (int ch = 0; ch < BPP; ch++) outb[s * BPP + ch] = (uint8_t)(o >> (8 * ch));
+                cur = x < 0 ? 0u : o;
+                bprev = x < 0 ? 0u : b;
+            }
+        } else
 #pragma unroll 8
         for (int s = 0; s < 32; s++) {
             const int x = 32 * j + s - lane;
