@@ -722,14 +722,18 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
     constexpr int NW = (3 + 32 * BPP + 3) / 4;                                    // words per staged row (<= 33)
     const long long rstep = (long long)nb + 1 - BPP;                              // row r starts r pixels behind row r - 1
     uint32_t pre[32], pre_x = 0, pre_u = 0, pre_ux = 0;                           // the next chunk, in flight while this one computes
+    uint32_t seen = 0;                                                            // lane 0: last value read from the flag of the band above
 
     auto fetch = [&](int j) {
         if (band > 0) {                       // the band above must have finished the pixels lane 0 will read in chunk j
             const uint32_t need = (uint32_t)min(j + 2, nchunks);
-            if (lane == 0) {
-                const volatile uint32_t* f = flags + band - 1;
-                while (!nowait && *f < need) __nanosleep(32);
-                __threadfence();
+            if (lane == 0 && seen < need) {       // acquire load: what the band above stored before its release is visible after it
+                const uint32_t* f = flags + band - 1;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                    if (seen >= need || nowait) break;
+                    __nanosleep(100);
+                } while (true);
             }
             __syncwarp();
             const uint8_t* u = X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP;
@@ -820,7 +824,7 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
             }
         }
         __syncwarp();
-        if (lane == 0) { __threadfence(); *(volatile uint32_t*)(flags + band) = (uint32_t)(j + 1); }
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + band), "r"((uint32_t)(j + 1)) : "memory");
         if (j + 1 < nchunks) stage();
     }
 }
