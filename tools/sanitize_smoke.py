@@ -16,4 +16,14 @@ res = V.prepare_pages(ims + [np.zeros((3, 5, 4), np.uint8), rng.integers(0, 256,
 assert all(x.error is None for x in res)
 d = rng.integers(0, 256, 100003, dtype=np.uint8).tobytes()
 S.crc32(d); S.adler32(d); S.base64(d); S.deflate(d); S.deflate(bytes(70000)); S.lz_tokens(b"abc" * 20000)
+# decode: this library's PNGs (segment chain), Pillow's (serial chain), a multi-IDAT page, odd sizes / modes, a corrupt one
+import io
+from PIL import Image
+big = synth.make_page(4, size=(900, 1300))
+pngs = [x.png for x in res] + [V.prepare_page(big).png]
+for im in ims + [big]:
+    b = io.BytesIO(); im.save(b, format="PNG"); pngs.append(b.getvalue())
+bad = bytearray(pngs[-1]); bad[len(bad) // 2:len(bad) // 2 + 32] = bytes(32); pngs.append(bytes(bad))
+dec = V.decode_pages(pngs)
+assert np.array_equal(dec[len(res)], np.asarray(big))
 print("sanitize smoke done")

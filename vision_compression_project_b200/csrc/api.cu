@@ -782,7 +782,6 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     if (!h || n < 0 || (n > 0 && (!pngs || !png_lens || !results || !out_pixels))) return fail(VCP_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> lock(h->mu);
     CU(cudaSetDevice(h->device));
-    Lane& L = h->lane[0];
     struct Idat { const uint8_t* p; size_t n; };
     std::vector<std::vector<Idat>> idats(n);
     std::vector<DecPageD> dp(n);
@@ -824,120 +823,158 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         results[i].status = st;
         D.status = st;
     }
-    // ---- arena + bounce buffer
-    Bump bump; size_t zoff_total = 0;
-    std::vector<size_t> o_z(n, kNone), o_f(n, kNone), o_p(n, kNone), o_s(n, kNone), s_z(n, 0);
-    std::vector<DecSegD> segs;
-    std::vector<uint32_t> chunk_page, chunk_pos;
+    // ---- the batch runs as up to two groups of consecutive pages on two lanes (streams): the latency-bound kernels of one group
+    //      (probe, window chain, un-filter pipeline) overlap the throughput-bound ones of the other (exec, resolve)
     constexpr unsigned long long kResolveChunk = 32768, kCkpt = 65536;      // keep in step with png_decode.cu
-    uint64_t pix_total = 0;
-    int nbands = 0;
-    size_t nslots = 0, iv_total = 0;
-    for (int i = 0; i < n; i++) {
-        dp[i].band0 = nbands; dp[i].iv0 = (int32_t)iv_total; dp[i].seg0 = (int32_t)segs.size();
-        if (dp[i].status) continue;
-        size_t zl = 0; for (auto& c : idats[i]) zl += c.n;
-        if (zl >= (1ull << 32) || idats[i].size() > (1u << 20)) { results[i].status = dp[i].status = fail(VCP_EINVAL, "PNG %d: too large", i); continue; }
-        dp[i].zlen = zl;
-        s_z[i] = zoff_total; zoff_total += align_up(zl + 64, 256);
-        o_f[i] = bump.take((size_t)dp[i].filt_len + 16);
-        o_s[i] = bump.take(((size_t)dp[i].filt_len + 16) * 2);
-        nbands += (dp[i].h + 31) / 32;
-        // one segment per IDAT: each is a place a parse may begin.  A parse that begins at IDAT s can produce at most the whole
-        // page, and at most 1032 bytes per byte of input that is left: that bounds the checkpoint slots it may need.
-        dp[i].nseg = (int32_t)idats[i].size();
-        const unsigned long long page_iv = dp[i].filt_len / kCkpt + 2;
-        size_t o = 0;
-        for (auto& c : idats[i]) {
-            DecSegD S; memset(&S, 0, sizeof S);
-            S.page = (uint32_t)i; S.zoff = (uint32_t)o; S.zlen = (uint32_t)c.n;
-            S.iv0 = (uint32_t)nslots; S.iv_cap = (uint32_t)std::min<unsigned long long>(page_iv, (unsigned long long)(zl - o) * 1032ull / kCkpt + 2);
-            nslots += S.iv_cap;
-            segs.push_back(S); o += c.n;
+    struct Group { int i0 = 0, i1 = 0; uint64_t pix_base = 0, pix_bytes = 0; DecPageD* hd = nullptr; Lane* L = nullptr; };
+    auto enqueue = [&](Group& G) -> int {
+        Lane& L = *G.L;
+        const int i0 = G.i0, m = G.i1 - G.i0;
+        Bump bump; size_t zoff_total = 0;
+        std::vector<size_t> o_f(m, kNone), o_p(m, kNone), o_s(m, kNone), s_z(m, 0);
+        std::vector<DecSegD> segs;
+        std::vector<uint32_t> chunk_page, chunk_pos;
+        uint64_t pix_total = 0;
+        int nbands = 0;
+        size_t nslots = 0, iv_total = 0;
+        for (int j = 0; j < m; j++) {
+            DecPageD& D = dp[i0 + j];
+            D.band0 = nbands; D.iv0 = (int32_t)iv_total; D.seg0 = (int32_t)segs.size();
+            if (D.status) continue;
+            size_t zl = 0; for (auto& c : idats[i0 + j]) zl += c.n;
+            if (zl >= (1ull << 32) || idats[i0 + j].size() > (1u << 20)) { results[i0 + j].status = D.status = fail(VCP_EINVAL, "PNG %d: too large", i0 + j); continue; }
+            D.zlen = zl;
+            s_z[j] = zoff_total; zoff_total += align_up(zl + 64, 256);
+            o_f[j] = bump.take((size_t)D.filt_len + 16);
+            o_s[j] = bump.take(((size_t)D.filt_len + 16) * 2);
+            nbands += (D.h + 31) / 32;
+            // one segment per IDAT: each is a place a parse may begin.  A parse that begins at IDAT s can produce at most the whole
+            // page, and at most 1032 bytes per byte of input that is left: that bounds the checkpoint slots it may need.
+            D.nseg = (int32_t)idats[i0 + j].size();
+            const unsigned long long page_iv = D.filt_len / kCkpt + 2;
+            size_t o = 0;
+            for (auto& c : idats[i0 + j]) {
+                DecSegD S; memset(&S, 0, sizeof S);
+                S.page = (uint32_t)j; S.zoff = (uint32_t)o; S.zlen = (uint32_t)c.n;
+                S.iv0 = (uint32_t)nslots; S.iv_cap = (uint32_t)std::min<unsigned long long>(page_iv, (unsigned long long)(zl - o) * 1032ull / kCkpt + 2);
+                nslots += S.iv_cap;
+                segs.push_back(S); o += c.n;
+            }
+            D.iv_cap = (int32_t)(page_iv + idats[i0 + j].size());
+            iv_total += (size_t)D.iv_cap;
+            for (unsigned long long p = 0; p < D.filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)j); chunk_pos.push_back((uint32_t)p); }
         }
-        dp[i].iv_cap = (int32_t)(page_iv + idats[i].size());
-        iv_total += (size_t)dp[i].iv_cap;
-        for (unsigned long long p = 0; p < dp[i].filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)i); chunk_pos.push_back((uint32_t)p); }
+        if (nslots >= (1ull << 31) || iv_total >= (1ull << 31)) return fail(VCP_ESIZE, "PNG batch too large");
+        const size_t o_zreg = bump.take(zoff_total + 256);
+        const size_t o_preg = bump.take(0);
+        for (int j = 0; j < m; j++) {
+            DecPageD& D = dp[i0 + j];
+            if (D.status) continue;
+            const size_t pl = (size_t)D.w * D.h * D.c;
+            o_p[j] = bump.take(pl);
+            vcp_decode_result& R = results[i0 + j];
+            R.pix_off = G.pix_base + (o_p[j] - o_preg); R.pix_len = pl;
+            R.width = D.w; R.height = D.h; R.channels = D.c;
+            pix_total = (o_p[j] - o_preg) + pl;
+        }
+        G.pix_bytes = align_up(pix_total, 256);
+        // un-filter work list: band b of every page that has one, for b = 0, 1, ...
+        std::vector<uint32_t> band_page, band_idx;
+        band_page.reserve(nbands); band_idx.reserve(nbands);
+        {
+            int maxb = 0;
+            for (int j = 0; j < m; j++) if (!dp[i0 + j].status) maxb = std::max(maxb, (dp[i0 + j].h + 31) / 32);
+            for (int bnd = 0; bnd < maxb; bnd++)
+                for (int j = 0; j < m; j++) if (!dp[i0 + j].status && bnd < (dp[i0 + j].h + 31) / 32) { band_page.push_back((uint32_t)j); band_idx.push_back((uint32_t)bnd); }
+        }
+        const size_t desc_bytes = align_up((size_t)m * sizeof(DecPageD), 256), seg_bytes = align_up(segs.size() * sizeof(DecSegD), 256),
+                     chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256), band_bytes = align_up(band_page.size() * sizeof(uint32_t), 256);
+        const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes;
+        const size_t o_desc = bump.take(meta_bytes + 16);
+        const size_t flag_bytes = align_up(((size_t)nbands + 64) * sizeof(uint32_t), 256);
+        const size_t o_flag = bump.take(flag_bytes);
+        const size_t o_slots = bump.take((nslots + 1) * sizeof(DecIvD)), o_ivs = bump.take((iv_total + 1) * sizeof(DecIvD));
+        if (G.pix_base + pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)(G.pix_base + pix_total));
+        int rc = ensure_arena(L, bump.off + 256); if (rc) return rc;
+        rc = ensure_stage(L, zoff_total + meta_bytes + 512); if (rc) return rc;
+        uint8_t* A = L.arena;
+        std::vector<CopyJob> jobs;
+        for (int j = 0; j < m; j++) {
+            DecPageD& D = dp[i0 + j];
+            if (D.status) continue;
+            size_t o = s_z[j];
+            for (auto& c : idats[i0 + j]) { jobs.push_back({L.stage + o, c.p, c.n}); o += c.n; }
+            D.z = A + o_zreg + s_z[j]; D.filt = A + o_f[j]; D.pix = A + o_p[j];
+            D.sym = reinterpret_cast<uint16_t*>(A + o_s[j]);
+        }
+        parallel_copy(jobs, h->copy_threads);
+        uint8_t* hm = L.stage + align_up(zoff_total, 256);
+        G.hd = reinterpret_cast<DecPageD*>(hm);
+        memcpy(G.hd, dp.data() + i0, (size_t)m * sizeof(DecPageD));
+        if (!segs.empty()) memcpy(hm + desc_bytes, segs.data(), segs.size() * sizeof(DecSegD));
+        if (!chunk_page.empty()) {
+            memcpy(hm + desc_bytes + seg_bytes, chunk_page.data(), chunk_page.size() * sizeof(uint32_t));
+            memcpy(hm + desc_bytes + seg_bytes + chunk_bytes, chunk_pos.data(), chunk_pos.size() * sizeof(uint32_t));
+        }
+        if (!band_page.empty()) {
+            memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes, band_page.data(), band_page.size() * sizeof(uint32_t));
+            memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes, band_idx.data(), band_idx.size() * sizeof(uint32_t));
+        }
+        cudaStream_t st = L.stream;
+        if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(A + o_desc, hm, meta_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(A + o_flag, 0, flag_bytes, st));
+        DecBatchD B; memset(&B, 0, sizeof B);
+        B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = m;
+        B.segs = reinterpret_cast<DecSegD*>(A + o_desc + desc_bytes); B.nsegs = (int32_t)segs.size();
+        B.slots = reinterpret_cast<DecIvD*>(A + o_slots);
+        B.ivs = reinterpret_cast<DecIvD*>(A + o_ivs); B.iv_total = (int32_t)iv_total;
+        B.chunk_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes);
+        B.chunk_pos = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + chunk_bytes);
+        B.nchunks = (int32_t)chunk_page.size();
+        B.counters = reinterpret_cast<uint32_t*>(A + o_flag);
+        B.band_flag = B.counters + 64; B.nbands = nbands;
+        B.band_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes);
+        B.band_idx = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes);
+        if (const char* g = getenv("VCP_DBG_UF_NOWAIT")) B.dbg_nowait = atoi(g);
+        launch_inflate(B, st);
+        launch_unfilter(B, st);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(G.hd, B.pages, (size_t)m * sizeof(DecPageD), cudaMemcpyDeviceToHost, st));
+        if (pix_total) CU(cudaMemcpyAsync((uint8_t*)out_pixels + G.pix_base, A + o_preg, pix_total, dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    // split where half of the filtered bytes have gone by.  Measured on B200: +5 % at 256 letter pages, a loss at 64 (two half-sized
+    // latency-bound pipelines instead of one), so small batches stay whole
+    unsigned long long total_f = 0; int n_ok = 0;
+    for (int i = 0; i < n; i++) if (!dp[i].status) { total_f += dp[i].filt_len; n_ok++; }
+    int split = n;
+    if (n_ok >= 128 && !getenv("VCP_DECODE_ONE_GROUP")) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < n; i++) { if (!dp[i].status) acc += dp[i].filt_len; if (acc * 2 >= total_f) { split = i + 1; break; } }
+        if (split >= n) split = n;
     }
-    if (nslots >= (1ull << 31) || iv_total >= (1ull << 31)) return fail(VCP_ESIZE, "PNG batch too large");
-    const size_t o_zreg = bump.take(zoff_total + 256);
-    const size_t o_preg = bump.take(0);
-    for (int i = 0; i < n; i++) {
-        if (dp[i].status) continue;
-        const size_t pl = (size_t)dp[i].w * dp[i].h * dp[i].c;
-        o_p[i] = bump.take(pl);
-        results[i].pix_off = (o_p[i] - o_preg); results[i].pix_len = pl;
-        results[i].width = dp[i].w; results[i].height = dp[i].h; results[i].channels = dp[i].c;
-        pix_total = (o_p[i] - o_preg) + pl;
+    Group G[2];
+    G[0].i0 = 0; G[0].i1 = split; G[0].L = &h->lane[0];
+    G[1].i0 = split; G[1].i1 = n; G[1].L = &h->lane[1];
+    int rc = 0;
+    for (int g = 0; g < 2 && rc == 0; g++) {
+        if (G[g].i1 <= G[g].i0) continue;
+        if (g == 1) G[1].pix_base = G[0].pix_base + G[0].pix_bytes;
+        rc = enqueue(G[g]);
     }
-    const size_t desc_bytes = align_up((size_t)n * sizeof(DecPageD), 256), seg_bytes = align_up(segs.size() * sizeof(DecSegD), 256),
-                 chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256);
-    // un-filter work list: band b of every page that has one, for b = 0, 1, ...
-    std::vector<uint32_t> band_page, band_idx;
-    band_page.reserve(nbands); band_idx.reserve(nbands);
-    {
-        int maxb = 0;
-        for (int i = 0; i < n; i++) if (!dp[i].status) maxb = std::max(maxb, (dp[i].h + 31) / 32);
-        for (int bnd = 0; bnd < maxb; bnd++)
-            for (int i = 0; i < n; i++) if (!dp[i].status && bnd < (dp[i].h + 31) / 32) { band_page.push_back((uint32_t)i); band_idx.push_back((uint32_t)bnd); }
+    for (int g = 0; g < 2; g++) {
+        if (G[g].i1 <= G[g].i0) continue;
+        cudaError_t e = cudaStreamSynchronize(G[g].L->stream);
+        if (e != cudaSuccess && rc == 0) rc = fail(VCP_ECUDA, "CUDA: %s", cudaGetErrorString(e));
     }
-    const size_t band_bytes = align_up(band_page.size() * sizeof(uint32_t), 256);
-    const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes;
-    const size_t o_desc = bump.take(meta_bytes + 16);
-    const size_t flag_bytes = align_up(((size_t)nbands + 64) * sizeof(uint32_t), 256);
-    const size_t o_flag = bump.take(flag_bytes);
-    const size_t o_slots = bump.take((nslots + 1) * sizeof(DecIvD)), o_ivs = bump.take((iv_total + 1) * sizeof(DecIvD));
-    if (pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)pix_total);
-    int rc = ensure_arena(L, bump.off + 256); if (rc) return rc;
-    rc = ensure_stage(L, zoff_total + meta_bytes + 512); if (rc) return rc;
-    uint8_t* A = L.arena;
-    std::vector<CopyJob> jobs;
-    for (int i = 0; i < n; i++) {
-        if (dp[i].status) continue;
-        size_t o = s_z[i];
-        for (auto& c : idats[i]) { jobs.push_back({L.stage + o, c.p, c.n}); o += c.n; }
-        dp[i].z = A + o_zreg + s_z[i]; dp[i].filt = A + o_f[i]; dp[i].pix = A + o_p[i];
-        dp[i].sym = reinterpret_cast<uint16_t*>(A + o_s[i]);
-    }
-    parallel_copy(jobs, h->copy_threads);
-    uint8_t* hm = L.stage + align_up(zoff_total, 256);
-    DecPageD* hd = reinterpret_cast<DecPageD*>(hm);
-    memcpy(hd, dp.data(), (size_t)n * sizeof(DecPageD));
-    if (!segs.empty()) memcpy(hm + desc_bytes, segs.data(), segs.size() * sizeof(DecSegD));
-    if (!chunk_page.empty()) {
-        memcpy(hm + desc_bytes + seg_bytes, chunk_page.data(), chunk_page.size() * sizeof(uint32_t));
-        memcpy(hm + desc_bytes + seg_bytes + chunk_bytes, chunk_pos.data(), chunk_pos.size() * sizeof(uint32_t));
-    }
-    if (!band_page.empty()) {
-        memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes, band_page.data(), band_page.size() * sizeof(uint32_t));
-        memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes, band_idx.data(), band_idx.size() * sizeof(uint32_t));
-    }
-    cudaStream_t st = L.stream;
-    if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(A + o_desc, hm, meta_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(A + o_flag, 0, flag_bytes, st));
-    DecBatchD B; memset(&B, 0, sizeof B);
-    B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = n;
-    B.segs = reinterpret_cast<DecSegD*>(A + o_desc + desc_bytes); B.nsegs = (int32_t)segs.size();
-    B.slots = reinterpret_cast<DecIvD*>(A + o_slots);
-    B.ivs = reinterpret_cast<DecIvD*>(A + o_ivs); B.iv_total = (int32_t)iv_total;
-    B.chunk_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes);
-    B.chunk_pos = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + chunk_bytes);
-    B.nchunks = (int32_t)chunk_page.size();
-    B.counters = reinterpret_cast<uint32_t*>(A + o_flag);
-    B.band_flag = B.counters + 64; B.nbands = nbands;
-    B.band_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes);
-    B.band_idx = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes);
-    if (const char* g = getenv("VCP_DBG_UF_NOWAIT")) B.dbg_nowait = atoi(g);
-    DecPageD* dd = B.pages;
-    launch_inflate(B, st);
-    launch_unfilter(B, st);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(hd, dd, (size_t)n * sizeof(DecPageD), cudaMemcpyDeviceToHost, st));
-    if (pix_total) CU(cudaMemcpyAsync(out_pixels, A + o_preg, pix_total, dst_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int i = 0; i < n; i++)
-        if (!results[i].status && hd[i].status) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: corrupt zlib stream or filter byte (code %d)", i, hd[i].status); }
+    if (rc) return rc;
+    for (int g = 0; g < 2; g++)
+        for (int i = G[g].i0; i < G[g].i1; i++) {
+            if (!G[g].hd) continue;
+            const int st_dev = G[g].hd[i - G[g].i0].status;
+            if (!results[i].status && st_dev) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: corrupt zlib stream or filter byte (code %d)", i, st_dev); }
+        }
     return 0;
 }
 
