@@ -159,3 +159,24 @@ def test_decode_large_batch_mixed_and_corrupt_segment(V):
             continue
         assert not isinstance(d, Exception), k
         assert np.array_equal(d.cpu().numpy(), _px(pages[k % len(pages) if k < 2 * len(pages) else k - 2 * len(pages) - 1])), k
+
+
+def test_decode_two_groups_keep_page_order(V):
+    """>= 128 decodable pages run as two page groups on two streams: results stay in input order, a bad page stays in its slot."""
+    rng = np.random.default_rng(21)
+    ims = []
+    for t in range(150):
+        h, w = int(rng.integers(20, 120)), int(rng.integers(20, 160))
+        mode = ["L", "RGB", "RGBA"][t % 3]
+        c = {"L": 1, "RGB": 3, "RGBA": 4}[mode]
+        px = (rng.integers(0, 3, (h, w, c)) * 90 + t).astype(np.uint8)
+        ims.append(Image.fromarray(px[:, :, 0] if c == 1 else px, mode))
+    ours = [r.png for r in V.prepare_pages(ims[:75], mode=None, want_base64=False)]
+    pngs = ours + [U.pillow_png(im) for im in ims[75:]]
+    pngs.insert(40, b"\x89PNG\r\n\x1a\n" + bytes(40))
+    dec = V.decode_pages(pngs)
+    assert isinstance(dec[40], ValueError)
+    del dec[40]
+    for k, (d, im) in enumerate(zip(dec, ims)):
+        assert not isinstance(d, Exception), k
+        assert np.array_equal(d, _px(im)), k

@@ -548,7 +548,7 @@ int vcp_init(int device, vcp_handle** out) {
         const unsigned hc = std::thread::hardware_concurrency();
         int lw = 1;
         if (const char* g = getenv("LOCAL_WORLD_SIZE")) lw = std::max(1, atoi(g));
-        h->copy_threads = std::max(2, std::min(8, (int)(hc ? hc : 8) / lw));
+        h->copy_threads = std::max(2, std::min(16, (int)(hc ? hc : 8) / lw));   // B200 box, 16 vCPUs: 8 -> 16 threads = +7 % pages/s with PIL inputs
         if (const char* g = getenv("VCP_COPY_THREADS")) h->copy_threads = std::max(1, atoi(g));
     }
     if (const char* g = getenv("VCP_PIPE_BYTES")) { const long long v = atoll(g); if (v >= (1 << 20)) h->pipe_bytes = (size_t)v; }
