@@ -647,19 +647,40 @@ __global__ void __launch_bounds__(256) k_infl_resolve(const DecBatchD b) {
     const unsigned long long c0 = b.chunk_pos[ck], flen = P.filt_len;
     const uint16_t* __restrict__ sym = P.sym;
     uint8_t* filt = P.filt;
+    // interval of the chunk's first position (last s with out <= c0), searched once per CTA; threads walk on from there
+    __shared__ int s_first;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((unsigned long long)S[mid].out <= c0) lo = mid; else hi = mid - 1; }
+        s_first = lo;
+    }
+    __syncthreads();
+    int s = s_first;
+    unsigned long long s_end = (unsigned long long)S[s].out + S[s].len;
     for (int it = 0; it < kResolveChunk / (256 * 8); it++) {
         const unsigned long long p0 = c0 + (unsigned long long)(it * 256 + threadIdx.x) * 8ull;
         if (p0 >= flen) break;
-        // interval of p0: last s with out <= p0
-        int lo = 0, hi = nseg - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((unsigned long long)S[mid].out <= p0) lo = mid; else hi = mid - 1; }
-        int s = lo;
-        unsigned long long s_end = (unsigned long long)S[s].out + S[s].len;
+        while (p0 >= s_end && s + 1 < nseg) { s++; s_end = (unsigned long long)S[s].out + S[s].len; }
         const int cnt = (int)min(8ull, flen - p0);
         uint16_t v8[8];
         if (cnt == 8) { const uint4 q = *reinterpret_cast<const uint4*>(sym + p0); memcpy(v8, &q, 16); }
         else for (int k = 0; k < cnt; k++) v8[k] = sym[p0 + k];
         uint8_t o8[8]; bool all = cnt == 8;
+        if (cnt == 8 && p0 + 8 + kWin <= s_end) {
+            // the usual group: one interval, nothing in its (already concrete) tail.  Loads are issued together; a symbol equal to
+            // its left neighbour (runs are most of a page) reuses the neighbour's byte
+            const uint8_t* base = filt + (unsigned long long)S[s].out - kWin - 256;
+            uint32_t g[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) g[k] = (v8[k] >= 256u && (k == 0 || v8[k] != v8[k - 1])) ? (uint32_t)__ldg(base + v8[k]) : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t v = v8[k];
+                o8[k] = v < 256u ? (uint8_t)v : (k && v == v8[k - 1]) ? o8[k - 1] : (uint8_t)g[k];
+            }
+            uint2 w; memcpy(&w, o8, 8); *reinterpret_cast<uint2*>(filt + p0) = w;
+            continue;
+        }
         for (int k = 0; k < cnt; k++) {
             const unsigned long long p = p0 + k;
             while (p >= s_end && s + 1 < nseg) { s++; s_end = (unsigned long long)S[s].out + S[s].len; }
