@@ -180,3 +180,40 @@ def test_decode_two_groups_keep_page_order(V):
     for k, (d, im) in enumerate(zip(dec, ims)):
         assert not isinstance(d, Exception), k
         assert np.array_equal(d, _px(im)), k
+
+
+@pytest.mark.timeout(180)
+def test_decode_corrupted_streams_end_in_a_status(V):
+    """Random damage anywhere in the file (container, zlib header, Huffman tables, tokens, Adler): every PNG of the batch comes back
+    as an error or as some array of the right shape, the intact neighbours stay exact, nothing hangs."""
+    from vision_compression_project_b200 import synth
+    rng = np.random.default_rng(99)
+    page = synth.make_page(7, size=(700, 900), photo=True)
+    good = [V.prepare_pages([page], want_base64=False)[0].png, U.pillow_png(page)]
+    batch, kind = [], []
+    for t in range(48):
+        b = bytearray(good[t % 2])
+        mode = t % 4
+        if mode == 0:
+            for _ in range(3):
+                b[int(rng.integers(33, len(b)))] ^= int(rng.integers(1, 256))           # behind IHDR: the geometry stays
+        elif mode == 1:
+            o = int(rng.integers(60, len(b) - 200)); b[o:o + 64] = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
+        elif mode == 2:
+            del b[int(rng.integers(100, len(b) - 100)):]
+        else:
+            o = int(rng.integers(41, 120)); b[o] ^= 0xFF                      # inside the first block header
+        batch.append(bytes(b)); kind.append(mode)
+        if t % 8 == 7:
+            batch.append(good[(t // 8) % 2]); kind.append(-1)
+    dec = V.decode_pages(batch)
+    exp = _px(page)
+    n_err = 0
+    for d, k in zip(dec, kind):
+        if k == -1:
+            assert not isinstance(d, Exception) and np.array_equal(d, exp)
+        elif isinstance(d, Exception):
+            n_err += 1
+        else:
+            assert d.shape == exp.shape
+    assert n_err >= 24                                                         # most damage is detected (chunk CRCs are not checked)
