@@ -825,46 +825,53 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     }
     // ---- the batch runs as up to two groups of consecutive pages on two lanes (streams): the latency-bound kernels of one group
     //      (probe, window chain, un-filter pipeline) overlap the throughput-bound ones of the other (exec, resolve)
-    constexpr unsigned long long kResolveChunk = 32768, kCkpt = 65536;      // keep in step with png_decode.cu
+    constexpr unsigned long long kResolveChunk = 32768, kCkpt = 65536, kScanBits = 8192;      // keep in step with png_decode.cu
+    constexpr int kMaxCand = 1024;                                                              // scanned block headers per page
     struct Group { int i0 = 0, i1 = 0; uint64_t pix_base = 0, pix_bytes = 0; DecPageD* hd = nullptr; Lane* L = nullptr; };
     auto enqueue = [&](Group& G) -> int {
         Lane& L = *G.L;
         const int i0 = G.i0, m = G.i1 - G.i0;
         Bump bump; size_t zoff_total = 0;
         std::vector<size_t> o_f(m, kNone), o_p(m, kNone), o_s(m, kNone), s_z(m, 0);
-        std::vector<DecSegD> segs;
-        std::vector<uint32_t> chunk_page, chunk_pos;
+        std::vector<unsigned long long> cand;            // candidate start bits: per page seg_cap entries, the IDAT starts filled in
+        std::vector<uint32_t> chunk_page, chunk_pos, scan_page, scan_bit;
         uint64_t pix_total = 0;
         int nbands = 0;
-        size_t nslots = 0, iv_total = 0;
+        size_t nslots = 0, iv_total = 0, seg_total = 0, surv_total = 0;
         for (int j = 0; j < m; j++) {
             DecPageD& D = dp[i0 + j];
-            D.band0 = nbands; D.iv0 = (int32_t)iv_total; D.seg0 = (int32_t)segs.size();
+            D.band0 = nbands; D.iv0 = (int32_t)iv_total; D.seg0 = D.cand0 = (int32_t)seg_total; D.surv0 = (int32_t)surv_total; D.slot0 = (int32_t)nslots;
             if (D.status) continue;
             size_t zl = 0; for (auto& c : idats[i0 + j]) zl += c.n;
-            if (zl >= (1ull << 32) || idats[i0 + j].size() > (1u << 20)) { results[i0 + j].status = D.status = fail(VCP_EINVAL, "PNG %d: too large", i0 + j); continue; }
+            if (zl >= (1ull << 28) || idats[i0 + j].size() > (1u << 20)) { results[i0 + j].status = D.status = fail(VCP_EINVAL, "PNG %d: too large", i0 + j); continue; }
             D.zlen = zl;
             s_z[j] = zoff_total; zoff_total += align_up(zl + 64, 256);
             o_f[j] = bump.take((size_t)D.filt_len + 16);
             o_s[j] = bump.take(((size_t)D.filt_len + 16) * 2);
             nbands += (D.h + 31) / 32;
-            // one segment per IDAT: each is a place a parse may begin.  A parse that begins at IDAT s can produce at most the whole
-            // page, and at most 1032 bytes per byte of input that is left: that bounds the checkpoint slots it may need.
-            D.nseg = (int32_t)idats[i0 + j].size();
+            // parse units: every IDAT start, plus up to kMaxCand block headers the scan finds on the device.  A parse can produce at
+            // most the whole page: page_iv checkpoint slots each.
             const unsigned long long page_iv = D.filt_len / kCkpt + 2;
-            size_t o = 0;
+            D.page_iv = (int32_t)page_iv;
+            int n_idat = 0; size_t o = 0;
             for (auto& c : idats[i0 + j]) {
-                DecSegD S; memset(&S, 0, sizeof S);
-                S.page = (uint32_t)j; S.zoff = (uint32_t)o; S.zlen = (uint32_t)c.n;
-                S.iv0 = (uint32_t)nslots; S.iv_cap = (uint32_t)std::min<unsigned long long>(page_iv, (unsigned long long)(zl - o) * 1032ull / kCkpt + 2);
-                nslots += S.iv_cap;
-                segs.push_back(S); o += c.n;
+                const unsigned long long sb = o == 0 ? 16ull : 8ull * o;         // the deflate data starts behind the 2-byte zlib header
+                if (n_idat == 0 || sb > cand.back()) { cand.push_back(sb); n_idat++; }
+                o += c.n;
             }
-            D.iv_cap = (int32_t)(page_iv + idats[i0 + j].size());
+            D.n_idat = n_idat; D.ncand = (uint32_t)n_idat; D.nsurv = 0;
+            D.seg_cap = n_idat + kMaxCand;
+            cand.resize(seg_total + (size_t)D.seg_cap, 0ull);
+            seg_total += (size_t)D.seg_cap;
+            nslots += (size_t)D.seg_cap * page_iv;
+            D.surv_cap = (int32_t)(zl * 8 / 32 + 256);
+            surv_total += (size_t)D.surv_cap;
+            for (unsigned long long bb = 0; bb < zl * 8ull; bb += kScanBits) { scan_page.push_back((uint32_t)j); scan_bit.push_back((uint32_t)bb); }
+            D.iv_cap = (int32_t)(page_iv + (unsigned long long)D.seg_cap);
             iv_total += (size_t)D.iv_cap;
             for (unsigned long long p = 0; p < D.filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)j); chunk_pos.push_back((uint32_t)p); }
         }
-        if (nslots >= (1ull << 31) || iv_total >= (1ull << 31)) return fail(VCP_ESIZE, "PNG batch too large");
+        if (nslots >= (1ull << 31) || iv_total >= (1ull << 31) || surv_total >= (1ull << 31)) return fail(VCP_ESIZE, "PNG batch too large");
         const size_t o_zreg = bump.take(zoff_total + 256);
         const size_t o_preg = bump.take(0);
         for (int j = 0; j < m; j++) {
@@ -887,13 +894,15 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             for (int bnd = 0; bnd < maxb; bnd++)
                 for (int j = 0; j < m; j++) if (!dp[i0 + j].status && bnd < (dp[i0 + j].h + 31) / 32) { band_page.push_back((uint32_t)j); band_idx.push_back((uint32_t)bnd); }
         }
-        const size_t desc_bytes = align_up((size_t)m * sizeof(DecPageD), 256), seg_bytes = align_up(segs.size() * sizeof(DecSegD), 256),
-                     chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256), band_bytes = align_up(band_page.size() * sizeof(uint32_t), 256);
-        const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes;
+        const size_t desc_bytes = align_up((size_t)m * sizeof(DecPageD), 256), seg_bytes = align_up(cand.size() * sizeof(unsigned long long), 256),
+                     chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256), band_bytes = align_up(band_page.size() * sizeof(uint32_t), 256),
+                     scan_bytes = align_up(scan_page.size() * sizeof(uint32_t), 256);
+        const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes + 2 * scan_bytes;
         const size_t o_desc = bump.take(meta_bytes + 16);
         const size_t flag_bytes = align_up(((size_t)nbands + 64) * sizeof(uint32_t), 256);
         const size_t o_flag = bump.take(flag_bytes);
         const size_t o_slots = bump.take((nslots + 1) * sizeof(DecIvD)), o_ivs = bump.take((iv_total + 1) * sizeof(DecIvD));
+        const size_t o_segs = bump.take((seg_total + 1) * sizeof(DecSegD)), o_surv = bump.take((surv_total + 1) * sizeof(uint32_t));
         if (G.pix_base + pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)(G.pix_base + pix_total));
         int rc = ensure_arena(L, bump.off + 256); if (rc) return rc;
         rc = ensure_stage(L, zoff_total + meta_bytes + 512); if (rc) return rc;
@@ -911,7 +920,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         uint8_t* hm = L.stage + align_up(zoff_total, 256);
         G.hd = reinterpret_cast<DecPageD*>(hm);
         memcpy(G.hd, dp.data() + i0, (size_t)m * sizeof(DecPageD));
-        if (!segs.empty()) memcpy(hm + desc_bytes, segs.data(), segs.size() * sizeof(DecSegD));
+        if (!cand.empty()) memcpy(hm + desc_bytes, cand.data(), cand.size() * sizeof(unsigned long long));
         if (!chunk_page.empty()) {
             memcpy(hm + desc_bytes + seg_bytes, chunk_page.data(), chunk_page.size() * sizeof(uint32_t));
             memcpy(hm + desc_bytes + seg_bytes + chunk_bytes, chunk_pos.data(), chunk_pos.size() * sizeof(uint32_t));
@@ -920,13 +929,24 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes, band_page.data(), band_page.size() * sizeof(uint32_t));
             memcpy(hm + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes, band_idx.data(), band_idx.size() * sizeof(uint32_t));
         }
+        const size_t scan_off = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes;
+        if (!scan_page.empty()) {
+            memcpy(hm + scan_off, scan_page.data(), scan_page.size() * sizeof(uint32_t));
+            memcpy(hm + scan_off + scan_bytes, scan_bit.data(), scan_bit.size() * sizeof(uint32_t));
+        }
         cudaStream_t st = L.stream;
         if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(A + o_desc, hm, meta_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(A + o_flag, 0, flag_bytes, st));
         DecBatchD B; memset(&B, 0, sizeof B);
         B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = m;
-        B.segs = reinterpret_cast<DecSegD*>(A + o_desc + desc_bytes); B.nsegs = (int32_t)segs.size();
+        B.segs = reinterpret_cast<DecSegD*>(A + o_segs); B.seg_total = (int32_t)seg_total;
+        B.cand_bits = reinterpret_cast<unsigned long long*>(A + o_desc + desc_bytes);
+        B.surv = reinterpret_cast<uint32_t*>(A + o_surv); B.surv_total = (int32_t)surv_total;
+        B.scan_page = reinterpret_cast<const uint32_t*>(A + o_desc + scan_off);
+        B.scan_bit = reinterpret_cast<const uint32_t*>(A + o_desc + scan_off + scan_bytes);
+        B.nscan = (int32_t)scan_page.size();
+        if (getenv("VCP_DECODE_NO_SCAN")) B.no_scan = 1;
         B.slots = reinterpret_cast<DecIvD*>(A + o_slots);
         B.ivs = reinterpret_cast<DecIvD*>(A + o_ivs); B.iv_total = (int32_t)iv_total;
         B.chunk_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes);

@@ -321,40 +321,171 @@ __device__ __forceinline__ void ring_window(const InflMem& M, const BitReader& b
     *w0 = __funnelshift_r(x0, x1, sh); *w1 = __funnelshift_r(x1, x2, sh);
 }
 
-// all lanes: check the two zlib header bytes; the deflate data starts at bit 16
-__device__ int zlib_header(const uint8_t* z, unsigned long long n) {
-    if (n < 2) return INF_SHORT;
-    const uint32_t cmf = z[0], flg = z[1];
-    return ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) ? INF_BAD_HEADER : INF_OK;
-}
-
 }  // namespace
 
+// ------------------------------------------------------------------------------------------ scan: where do deflate blocks start?
+// A parse can begin wherever a deflate block begins, and the header of a dynamic-Huffman block (the only kind an encoder emits for
+// page-sized data) is recognisable: 3 + 14 fixed bits, a code-length code that must be complete, and ~300 run-length coded code
+// lengths that must form a complete literal/length code containing the end-of-block symbol and a complete (or one-symbol)
+// distance code.  Random bits pass that with probability ~0, so every bit position of the stream is simply tried:
+//   k_infl_scan1   thread per bit position: the fixed fields and the Kraft sum of the code-length code (cheap, ~0.4 % pass)
+//   k_infl_scan2   thread per survivor: decode the code lengths, tracking the two Kraft sums (leaves at the first overflow)
+//   k_infl_sort    CTA per page: the IDAT starts (from the host) and the found headers, sorted, become the page's parse units
+// A false positive only costs a wasted parse (no chain reaches it); a missed block (stored / fixed Huffman) is parsed by the warp of
+// the block in front of it.
+constexpr int kScanBits = 8192;           // bit positions per CTA of k_infl_scan1 (keep in step with api.cu)
+
+// 32 stream bits starting at bit `bit` of the byte stream z (z has >= 64 bytes of slack behind its n bytes)
+__device__ __forceinline__ uint32_t bits_at(const uint8_t* __restrict__ z, unsigned long long bit) {
+    const uintptr_t a = (uintptr_t)z + (uintptr_t)(bit >> 3);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const int sh = (int)((a & 3) * 8 + (bit & 7));                             // 0..31
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
+}
+
+__global__ void __launch_bounds__(256) k_infl_scan1(const DecBatchD b) {
+    const int ck = blockIdx.x;
+    DecPageD& P = b.pages[b.scan_page[ck]];
+    if (P.status != 0) return;
+    const uint8_t* __restrict__ z = P.z;
+    const unsigned long long nbits = P.zlen * 8ull;
+    const unsigned long long b0 = b.scan_bit[ck];
+    for (int i = 0; i < kScanBits / 256; i++) {
+        const unsigned long long bit = b0 + (unsigned long long)i * 256 + threadIdx.x;
+        if (bit < 17 || bit + 60 > nbits) continue;                            // bit 16 is a parse unit anyway; a header needs room
+        const uint32_t h = bits_at(z, bit);
+        if (((h >> 1) & 3u) != 2u) continue;                                   // BTYPE = dynamic
+        if (((h >> 3) & 31u) > 29u || ((h >> 8) & 31u) > 29u) continue;        // HLIT, HDIST
+        const int ncl = (int)((h >> 13) & 15u) + 4;
+        // code-length code: ncl 3-bit lengths from bit 17; complete iff the Kraft sum is exactly 1 (128 / 128)
+        const uint32_t c0 = bits_at(z, bit + 17), c1 = bits_at(z, bit + 17 + 30);
+        uint32_t kraft = 0;
+#pragma unroll
+        for (int k = 0; k < 19; k++) {
+            const uint32_t len = k < 10 ? (c0 >> (3 * k)) & 7u : (c1 >> (3 * (k - 10))) & 7u;
+            if (k < ncl && len) kraft += 128u >> len;
+        }
+        if (kraft != 128u) continue;
+        const uint32_t idx = atomicAdd(&P.nsurv, 1u);
+        if (idx < (uint32_t)P.surv_cap) b.surv[P.surv0 + idx] = (uint32_t)bit;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_infl_scan2(const DecBatchD b) {
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= b.surv_total) return;
+    int lo = 0, hi = b.npages - 1;                        // page of survivor slot g: last page with surv0 <= g
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.pages[mid].surv0 <= g) lo = mid; else hi = mid - 1; }
+    DecPageD& P = b.pages[lo];
+    if (P.status != 0 || (uint32_t)(g - P.surv0) >= min(P.nsurv, (uint32_t)P.surv_cap)) return;
+    const uint8_t* __restrict__ z = P.z;
+    const unsigned long long nbits = P.zlen * 8ull;
+    const unsigned long long bit0 = b.surv[g];
+    const uint32_t h = bits_at(z, bit0);
+    const int nll = (int)((h >> 3) & 31u) + 257, nd = (int)((h >> 8) & 31u) + 1, ncl = (int)((h >> 13) & 15u) + 4;
+    // the code-length code (<= 7 bits, complete): direct lookup, entry = symbol << 3 | length
+    uint8_t cl[19], tab[128];
+    {
+        const uint32_t c0 = bits_at(z, bit0 + 17), c1 = bits_at(z, bit0 + 17 + 30);
+#pragma unroll
+        for (int k = 0; k < 19; k++) {
+            const uint32_t len = k < 10 ? (c0 >> (3 * k)) & 7u : (c1 >> (3 * (k - 10))) & 7u;
+            cl[kClOrd[k]] = k < ncl ? (uint8_t)len : (uint8_t)0;
+        }
+        uint32_t code = 0;
+        for (int l = 1; l <= 7; l++) {
+            for (int s = 0; s < 19; s++) {
+                if (cl[s] != l) continue;
+                const uint32_t r = __brev(code) >> (32 - l);
+                for (uint32_t e = r; e < 128u; e += 1u << l) tab[e] = (uint8_t)((s << 3) | l);
+                code++;
+            }
+            code <<= 1;
+        }
+    }
+    unsigned long long bit = bit0 + 17 + 3ull * ncl;
+    uint32_t kr_ll = 0, kr_d = 0;                         // Kraft sums in units of 2^-15
+    int i = 0, prev = 0, n_d = 0; bool has_eob = false, ok = true;
+    while (i < nll + nd) {
+        if (bit + 14 > nbits) { ok = false; break; }
+        const uint32_t w = bits_at(z, bit);
+        const uint32_t e = tab[w & 127u];
+        const int l = (int)(e & 7u), s = (int)(e >> 3);
+        int rep = 1, v = s;
+        if (s < 16) bit += l;
+        else if (s == 16) { if (i == 0) { ok = false; break; } v = prev; rep = 3 + (int)((w >> l) & 3u); bit += l + 2; }
+        else if (s == 17) { v = 0; rep = 3 + (int)((w >> l) & 7u); bit += l + 3; }
+        else { v = 0; rep = 11 + (int)((w >> l) & 127u); bit += l + 7; }
+        if (i + rep > nll + nd) { ok = false; break; }
+        if (v) {
+            for (int r = 0; r < rep; r++) {
+                if (i + r < nll) { kr_ll += 32768u >> v; if (i + r == 256) has_eob = true; }
+                else { kr_d += 32768u >> v; n_d++; }
+            }
+            if (kr_ll > 32768u || kr_d > 32768u) { ok = false; break; }
+        }
+        prev = v; i += rep;
+    }
+    if (!ok || !has_eob || kr_ll != 32768u || !(kr_d == 32768u || n_d <= 1)) return;
+    // an IDAT start is a parse unit already
+    {
+        const unsigned long long* I = b.cand_bits + P.cand0;
+        int a = 0, c = P.n_idat - 1;
+        while (a < c) { const int mid = (a + c + 1) >> 1; if (I[mid] <= bit0) a = mid; else c = mid - 1; }
+        if (I[a] == bit0) return;
+    }
+    const uint32_t idx = atomicAdd(&P.ncand, 1u);
+    if (idx < (uint32_t)P.seg_cap) b.cand_bits[P.cand0 + idx] = bit0;
+}
+
+// The page's parse units in stream order (rank sort: the candidates are distinct).
+__global__ void __launch_bounds__(256) k_infl_sort(const DecBatchD b) {
+    DecPageD& P = b.pages[blockIdx.x];
+    if (P.status != 0) return;
+    if (threadIdx.x == 0) {
+        if (P.zlen < 6) P.status = INF_SHORT;
+        else { const uint32_t cmf = P.z[0], flg = P.z[1]; if ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) P.status = INF_BAD_HEADER; }
+    }
+    const int K = (int)min(P.ncand, (uint32_t)P.seg_cap);
+    const unsigned long long* C = b.cand_bits + P.cand0;
+    for (int i = threadIdx.x; i < K; i += 256) {
+        const unsigned long long v = C[i];
+        int rank = 0;
+        for (int j = 0; j < K; j++) rank += C[j] < v ? 1 : 0;
+        DecSegD S; memset(&S, 0, sizeof S);
+        S.page = blockIdx.x; S.start_bit = v;
+        S.iv0 = (uint32_t)P.slot0 + (uint32_t)rank * (uint32_t)P.page_iv; S.iv_cap = (uint32_t)P.page_iv;
+        b.segs[P.seg0 + rank] = S;
+    }
+    if (threadIdx.x == 0) P.nseg = K;
+}
+
 // ------------------------------------------------------------------------------------------ probe: parse, count, checkpoint
-__global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, DecIvD* __restrict__ slots, int nsegs) {
+__global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, DecIvD* __restrict__ slots,
+                                                    int npages, int seg_total) {
     __shared__ InflMem mem[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sg = blockIdx.x * 4 + warp;
-    if (sg >= nsegs) return;
-    DecSegD& S = segs[sg];
-    const DecPageD& P = pages[S.page];
-    if (P.status != 0) return;
-    InflMem& M = mem[warp];
-    const DecSegD* PS = segs + P.seg0;                  // this page's segments
+    if (sg >= seg_total) return;
+    int plo = 0, phi = npages - 1;                      // page of parse-unit slot sg: last page with seg0 <= sg
+    while (plo < phi) { const int mid = (plo + phi + 1) >> 1; if (pages[mid].seg0 <= sg) plo = mid; else phi = mid - 1; }
+    const DecPageD& P = pages[plo];
     const int s_loc = sg - P.seg0;
-    const uint8_t* z = P.z + S.zoff;
-    BitReader br; br.init(z, P.zlen - S.zoff, M.zbuf);
+    if (P.status != 0 || s_loc >= P.nseg) return;
+    DecSegD& S = segs[sg];
+    InflMem& M = mem[warp];
+    const DecSegD* PS = segs + P.seg0;                  // this page's parse units, sorted by start bit
+    BitReader br; br.init(P.z, P.zlen, M.zbuf);
     uint32_t filled = 0;
     int status = INF_OK;
-    unsigned long long start_bit = 0;
-    if (s_loc == 0) { status = zlib_header(z, br.n); start_bit = 16; }
-    if (status == INF_OK) seek_bit(M, br, filled, start_bit);
+    const unsigned long long start_bit = S.start_bit;
+    seek_bit(M, br, filled, start_bit);
     const unsigned long long cap = P.filt_len;
     unsigned long long pos = 0;                         // output bytes so far
     // interval being built (lane 0)
     unsigned long long iv_hdr = start_bit, iv_start = start_bit, iv_out = 0, next_ck = kCkpt;
     uint32_t niv = 0;
-    int end_seg = s_loc;                                // the segment whose end the parse has not passed yet
+    int end_seg = s_loc + 1;                            // the first parse unit whose start the parse has not passed yet
     int last = 0, next = P.nseg;
     bool done = false;
     auto emit = [&](unsigned long long out_now, unsigned long long hdr_bit, unsigned long long bit_now) {   // lane 0: close the interval at a token boundary
@@ -420,9 +551,12 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
             if (pos >= next_ck) emit(pos, used, used);                       // after a stored block
             if (last) stop = 1;
             else {
-                while (end_seg < P.nseg && ((unsigned long long)PS[end_seg].zoff + PS[end_seg].zlen - S.zoff) * 8ull < used) end_seg++;
-                if (end_seg >= P.nseg) status = INF_SHORT;
-                else if (((unsigned long long)PS[end_seg].zoff + PS[end_seg].zlen - S.zoff) * 8ull == used) { stop = 1; next = end_seg + 1; }
+                // units are sorted: gallop, then bisect to the first one that starts at or behind this block's end
+                int step = 1, hi2 = end_seg;
+                while (hi2 < P.nseg && PS[hi2].start_bit < used) { end_seg = hi2 + 1; hi2 += step; step <<= 1; }
+                hi2 = min(hi2, P.nseg);
+                while (end_seg < hi2) { const int mid = (end_seg + hi2) >> 1; if (PS[mid].start_bit < used) end_seg = mid + 1; else hi2 = mid; }
+                if (end_seg < P.nseg && PS[end_seg].start_bit == used) { stop = 1; next = end_seg; }
             }
             if (br.over && status == INF_OK) status = INF_SHORT;
         }
@@ -477,8 +611,7 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
     const int li = g - P.iv0;
     if (P.status != 0 || li >= P.niv) return;
     const DecIvD I = ivs[g];
-    const DecSegD& S = segs[I.seg];
-    BitReader br; br.init(P.z + S.zoff, P.zlen - S.zoff, M.zbuf);
+    BitReader br; br.init(P.z, P.zlen, M.zbuf);
     uint32_t filled = 0;
     seek_bit(M, br, filled, I.hdr_bit);
     uint16_t* __restrict__ out = P.sym + I.out;
@@ -501,7 +634,7 @@ __global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, 
         }
         if (btype == 0) {
             if (pos + (uint32_t)slen > target) { status = INF_SEG; break; }
-            const uint8_t* s = P.z + S.zoff + ssrc;
+            const uint8_t* s = P.z + ssrc;
             for (int k = lane; k < slen; k += 32) out[pos + k] = (uint16_t)s[k];
             pos += (uint32_t)slen;
             __syncwarp();
@@ -700,13 +833,18 @@ __global__ void __launch_bounds__(256) k_infl_resolve(const DecBatchD b) {
 int decode_kernel_setup() { return 0; }
 
 int launch_inflate(const DecBatchD& b, cudaStream_t st) {
-    if (b.npages == 0 || b.nsegs == 0) return 0;
-    k_infl_probe<<<(b.nsegs + 3) / 4, 128, 0, st>>>(b.pages, b.segs, b.slots, b.nsegs);
+    if (b.npages == 0 || b.seg_total == 0) return 0;
+    if (b.nscan && !b.no_scan) {
+        k_infl_scan1<<<b.nscan, 256, 0, st>>>(b);
+        k_infl_scan2<<<(b.surv_total + 127) / 128, 128, 0, st>>>(b);
+    }
+    k_infl_sort<<<b.npages, 256, 0, st>>>(b);
+    k_infl_probe<<<(b.seg_total + 3) / 4, 128, 0, st>>>(b.pages, b.segs, b.slots, b.npages, b.seg_total);
     k_infl_plan<<<b.npages, 32, 0, st>>>(b.pages, b.segs, b.slots, b.ivs, b.npages);
     k_infl_exec<<<b.iv_total, 32, 0, st>>>(b.pages, b.segs, b.ivs, b.npages, b.iv_total);
     k_infl_window<<<b.npages * kWinCluster, 1024, 0, st>>>(b.pages, b.ivs, b.npages);
     if (b.nchunks) k_infl_resolve<<<b.nchunks, 256, 0, st>>>(b);
-    return 4 + (b.nchunks ? 1 : 0);
+    return 7 + (b.nchunks ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------ un-filter

@@ -104,18 +104,22 @@ struct DecPageD {
     uint16_t* sym;                                  // filt_len symbolic bytes (see k_infl_exec)
     int32_t w, h, c;
     int32_t status;                                 // 0 or a negative inflate / un-filter error
-    int32_t seg0, nseg;                             // IDAT segments of this page in the DecSegD array
+    int32_t seg0, seg_cap, nseg;                    // its parse units in the DecSegD array (nseg written by k_infl_sort)
+    int32_t cand0, n_idat;                          // its range of candidate start bits; the first n_idat are the IDAT starts (host)
+    int32_t surv0, surv_cap;                        // its range of k_infl_scan1 survivors
+    uint32_t nsurv, ncand;                          // device counters (ncand starts at n_idat)
+    int32_t slot0, page_iv;                         // first checkpoint slot; slots per parse unit (filt_len / 64 Ki + 2)
     int32_t iv0, iv_cap, niv;                       // its intervals in the DecIvD array (niv written by k_infl_plan)
     int32_t band0;                                  // first 32-row band of this page in the un-filter's band numbering
 };
 
-// One IDAT chunk of a PNG being decoded: a place where a parse may begin (k_infl_probe).
+// A place where a parse of a page's deflate stream may begin: an IDAT start or a block header found by the scan (k_infl_probe).
 struct DecSegD {
-    uint32_t page;
-    uint32_t zoff, zlen;     // byte range inside the page's zlib stream
+    uint32_t page, pad;
+    unsigned long long start_bit;   // bit position inside the page's zlib stream
     uint32_t olen, opos;     // bytes its parse produced (k_infl_probe) and where they start in the filtered stream (k_infl_plan)
-    int32_t ok;              // 1 = the parse ended on a block boundary that is an IDAT boundary (or the end of the stream); < 0 error
-    int32_t next;            // the IDAT (index within the page) in front of which it ended
+    int32_t ok;              // 1 = the parse ended on a block boundary that is another parse unit's start (or the end of the stream); < 0 error
+    int32_t next;            // the parse unit (index within the page) in front of which it ended
     int32_t fin;             // it met the final block
     uint32_t niv;            // intervals it wrote
     uint32_t iv0, iv_cap;    // its private range of checkpoint slots
@@ -123,22 +127,26 @@ struct DecSegD {
 
 // A stretch of tokens between two checkpoints of a parse: the unit of k_infl_exec.
 struct DecIvD {
-    unsigned long long hdr_bit;    // bit position (relative to the segment's first byte) of the header of the deflate block it starts in
+    unsigned long long hdr_bit;    // bit position (in the page's zlib stream) of the header of the deflate block it starts in
     unsigned long long start_bit;  // bit position of its first token
-    uint32_t out, len;             // output range (relative to the segment in the probe's slots, absolute after k_infl_plan)
+    uint32_t out, len;             // output range (relative to the parse unit in the probe's slots, absolute after k_infl_plan)
     uint32_t seg, pad;
 };
 
 struct DecBatchD {
     DecPageD* pages; int32_t npages;
-    DecSegD* segs; int32_t nsegs;
-    DecIvD* slots;                                                            // checkpoint slots, one private range per segment
+    DecSegD* segs; int32_t seg_total;                                         // parse units, one range of seg_cap per page
+    unsigned long long* cand_bits;                                            // candidate start bits, same ranges
+    uint32_t* surv; int32_t surv_total;                                       // k_infl_scan1 survivors, one range per page
+    const uint32_t* scan_page; const uint32_t* scan_bit; int32_t nscan;       // scan work list: 8 Ki bit positions each
+    DecIvD* slots;                                                            // checkpoint slots, one private range per parse unit
     DecIvD* ivs; int32_t iv_total;                                            // intervals in stream order, one range per page
     const uint32_t* chunk_page; const uint32_t* chunk_pos; int32_t nchunks;   // resolve work list: 32 Ki positions each
     uint32_t* band_flag; int32_t nbands;                                      // un-filter progress per band (zeroed per launch)
     const uint32_t* band_page; const uint32_t* band_idx;                      // un-filter work list in ticket order (band-major over pages)
     uint32_t* counters;                                                       // [0] un-filter CTA ticket (zeroed per launch)
     int32_t dbg_nowait;                                                       // timing experiments only: bands do not wait (wrong pixels)
+    int32_t no_scan;                                                          // VCP_DECODE_NO_SCAN: parse units are the IDAT starts only
 };
 
 // ---- launchers (each returns the number of kernels it launched) ----
