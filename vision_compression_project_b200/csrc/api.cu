@@ -866,7 +866,15 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             nslots += (size_t)D.seg_cap * page_iv;
             D.surv_cap = (int32_t)(zl * 8 / 32 + 256);
             surv_total += (size_t)D.surv_cap;
-            for (unsigned long long bb = 0; bb < zl * 8ull; bb += kScanBits) { scan_page.push_back((uint32_t)j); scan_bit.push_back((uint32_t)bb); }
+            // An encoder that ends every IDAT on a block boundary by an empty stored block (this library: 00 00 FF FF closes every IDAT but
+            // the last) has its block starts at the IDAT starts already; the chain check in k_infl_plan still decides, the scan is skipped.
+            bool synced = idats[i0 + j].size() >= 2;
+            for (size_t q = 0; synced && q + 1 < idats[i0 + j].size(); q++) {
+                const Idat& c = idats[i0 + j][q];
+                synced = c.n >= 4 && c.p[c.n - 4] == 0 && c.p[c.n - 3] == 0 && c.p[c.n - 2] == 0xFF && c.p[c.n - 1] == 0xFF;
+            }
+            if (!synced || getenv("VCP_DECODE_SCAN_ALL"))
+                for (unsigned long long bb = 0; bb < zl * 8ull; bb += kScanBits) { scan_page.push_back((uint32_t)j); scan_bit.push_back((uint32_t)bb); }
             D.iv_cap = (int32_t)(page_iv + (unsigned long long)D.seg_cap);
             iv_total += (size_t)D.iv_cap;
             for (unsigned long long p = 0; p < D.filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)j); chunk_pos.push_back((uint32_t)p); }

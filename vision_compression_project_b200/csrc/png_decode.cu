@@ -347,28 +347,61 @@ __global__ void __launch_bounds__(256) k_infl_scan1(const DecBatchD b) {
     const int ck = blockIdx.x;
     DecPageD& P = b.pages[b.scan_page[ck]];
     if (P.status != 0) return;
-    const uint8_t* __restrict__ z = P.z;
     const unsigned long long nbits = P.zlen * 8ull;
-    const unsigned long long b0 = b.scan_bit[ck];
-    for (int i = 0; i < kScanBits / 256; i++) {
-        const unsigned long long bit = b0 + (unsigned long long)i * 256 + threadIdx.x;
-        if (bit < 17 || bit + 60 > nbits) continue;                            // bit 16 is a parse unit anyway; a header needs room
-        const uint32_t h = bits_at(z, bit);
-        if (((h >> 1) & 3u) != 2u) continue;                                   // BTYPE = dynamic
-        if (((h >> 3) & 31u) > 29u || ((h >> 8) & 31u) > 29u) continue;        // HLIT, HDIST
-        const int ncl = (int)((h >> 13) & 15u) + 4;
-        // code-length code: ncl 3-bit lengths from bit 17; complete iff the Kraft sum is exactly 1 (128 / 128)
-        const uint32_t c0 = bits_at(z, bit + 17), c1 = bits_at(z, bit + 17 + 30);
-        uint32_t kraft = 0;
-#pragma unroll
-        for (int k = 0; k < 19; k++) {
-            const uint32_t len = k < 10 ? (c0 >> (3 * k)) & 7u : (c1 >> (3 * (k - 10))) & 7u;
-            if (k < ncl && len) kraft += 128u >> len;
-        }
-        if (kraft != 128u) continue;
-        const uint32_t idx = atomicAdd(&P.nsurv, 1u);
-        if (idx < (uint32_t)P.surv_cap) b.surv[P.surv0 + idx] = (uint32_t)bit;
+    __shared__ uint32_t s_n, s_base, s_list[512];                              // survivors of this CTA: one global atomic for all of them
+    __shared__ uint8_t s_kraft[512];                                           // Kraft sum (in 1/128) of three 3-bit code lengths
+    for (int i = threadIdx.x; i < 512; i += 256) {
+        uint32_t k = 0;
+        for (int f = 0; f < 3; f++) { const uint32_t len = (i >> (3 * f)) & 7u; if (len) k += 128u >> len; }
+        s_kraft[i] = (uint8_t)k;
     }
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // a thread tries 32 consecutive bit positions out of one 128-bit window held in registers: first the fixed fields of all 32
+    // (a bit mask), then the code-length code of those that passed — lanes loop over their set bits, not over all positions
+    const unsigned long long t0 = (unsigned long long)b.scan_bit[ck] + 32ull * threadIdx.x;
+    if (t0 < nbits) {
+        const uintptr_t a = (uintptr_t)P.z + (uintptr_t)(t0 >> 3);              // t0 is a multiple of 32: (t0 & 7) == 0
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const int sh0 = (int)(a & 3) * 8;
+        uint32_t x[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) x[i] = __ldg(wp + i);
+        uint32_t w[4];                                                         // stream bits [t0 + 32 i, t0 + 32 i + 32)
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = __funnelshift_r(x[i], x[i + 1], sh0);
+        uint32_t pass = 0;
+#pragma unroll
+        for (int o = 0; o < 32; o++) {
+            const uint32_t h = __funnelshift_r(w[0], w[1], o);
+            const bool ok = ((h >> 1) & 3u) == 2u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;   // BTYPE = dynamic, HLIT, HDIST
+            pass |= (ok ? 1u : 0u) << o;
+        }
+        while (pass) {
+            const int o = __ffs(pass) - 1; pass &= pass - 1;
+            const unsigned long long bit = t0 + o;
+            if (bit < 17 || bit + 60 > nbits) continue;                        // bit 16 is a parse unit anyway; a header needs room
+            const uint32_t h = __funnelshift_r(w[0], w[1], o);
+            const int nb = 3 * ((int)((h >> 13) & 15u) + 4);                   // bits of code-length-code lengths: 12..57, from bit 17
+            const int p0 = o + 17, p1 = o + 47;
+            uint32_t c0 = p0 < 32 ? __funnelshift_r(w[0], w[1], p0) : __funnelshift_r(w[1], w[2], p0 - 32);
+            uint32_t c1 = p1 < 64 ? __funnelshift_r(w[1], w[2], p1 - 32) : __funnelshift_r(w[2], w[3], p1 - 64);
+            c0 &= nb >= 30 ? 0x3FFFFFFFu : (1u << nb) - 1u;
+            c1 &= nb > 30 ? (1u << (nb - 30)) - 1u : 0u;
+            // complete iff the Kraft sum is exactly 1 (128 / 128)
+            const uint32_t kraft = s_kraft[c0 & 511u] + s_kraft[(c0 >> 9) & 511u] + s_kraft[(c0 >> 18) & 511u] + s_kraft[c0 >> 27] +
+                                   s_kraft[c1 & 511u] + s_kraft[(c1 >> 9) & 511u] + s_kraft[(c1 >> 18) & 511u];
+            if (kraft != 128u) continue;
+            const uint32_t q = atomicAdd(&s_n, 1u);
+            if (q < 512u) s_list[q] = (uint32_t)bit;
+            else { const uint32_t idx = atomicAdd(&P.nsurv, 1u); if (idx < (uint32_t)P.surv_cap) b.surv[P.surv0 + idx] = (uint32_t)bit; }
+        }
+    }
+    __syncthreads();
+    const uint32_t n = min(s_n, 512u);
+    if (threadIdx.x == 0 && n) s_base = atomicAdd(&P.nsurv, n);
+    __syncthreads();
+    for (uint32_t q = threadIdx.x; q < n; q += 256) { const uint32_t idx = s_base + q; if (idx < (uint32_t)P.surv_cap) b.surv[P.surv0 + idx] = s_list[q]; }
 }
 
 __global__ void __launch_bounds__(128) k_infl_scan2(const DecBatchD b) {
