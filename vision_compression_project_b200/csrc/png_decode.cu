@@ -6,15 +6,19 @@
 // oracle/restate.py:png_unfilter and Python's zlib.
 //
 // Inflate.  Parsing a deflate stream is serial (a code starts where the last one ended); *executing* its tokens is not, once it is
-// known where in the output each stretch of tokens lands.  So the stream is parsed twice:
-//   k_infl_probe   one warp per IDAT chunk, parse only.  The warp treats its IDAT as the start of a deflate block and counts output
-//                  bytes until a block ends exactly on the last bit of an IDAT (its own or a later one) or the final block ends.
-//                  Every 64 KiB of output it writes a checkpoint: bit position, bit position of the enclosing block header,
-//                  output offset.  IDAT 0 really does begin a block, so its result is true, and so is the result of the IDAT
-//                  its parse stopped in front of, and so on: a chain of true results (k_infl_plan walks it).  An encoder that
-//                  ends every IDAT on a block boundary (this library) gives a chain through all IDATs, each parsed by its own
-//                  warp; Pillow's 64 KiB cuts fall mid-block, the chain is IDAT 0's warp alone, the parse is serial — but still
-//                  a parse only.  Warps that began mid-block produce garbage that no chain reaches.
+// known where in the output each stretch of tokens lands.  So the stream is parsed twice, and the first parse is itself split
+// wherever a deflate block can be shown to begin:
+//   k_infl_scan1/2 every bit position of the stream is tried as a dynamic-Huffman block header (complete code-length code, complete
+//                  literal/length code with an end-of-block symbol, complete or one-symbol distance code: random bits do not pass).
+//   k_infl_sort    the found headers and the IDAT starts (known to the host) are a page's *parse units*, sorted by bit position.
+//   k_infl_probe   one warp per parse unit, parse only.  The warp counts output bytes until a block ends exactly on the first bit of
+//                  another parse unit, or the final block ends.  Every 64 KiB of output it writes a checkpoint: bit position, bit
+//                  position of the enclosing block header, output offset.  The first unit (bit 16 of the zlib stream) really does
+//                  begin a block, so its result is true, and so is the result of the unit its parse stopped in front of, and so on: a
+//                  chain of true results (k_infl_plan walks it).  zlib starts a block every 32 Ki symbols, this library one per IDAT:
+//                  either way a page is parsed by many warps.  A unit that is not a block start (a false positive of the scan, an IDAT
+//                  that Pillow cut mid-block) produces garbage that no chain reaches; a block the scan cannot see (stored, fixed
+//                  Huffman) is parsed by the warp of the block in front of it.
 //   k_infl_plan    one warp per page: walk the chain, give every interval between checkpoints its output offset, in order.
 //   k_infl_exec    one warp per interval: rebuild the block's code tables, seek to the checkpoint, parse again and execute the tokens.
 //                  A match may reach up to 32 KiB in front of the interval, into output another warp is still producing, so the
