@@ -20,6 +20,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <tuple>
 #include <vector>
@@ -682,17 +683,25 @@ int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* 
         return 0;
     };
     int rc = 0;
+    const bool trace = getenv("VCP_TRACE") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
     for (int g = 0; g < G && !rc; g++) {
         // lane g % kLanes was last used by group g-kLanes: its payload copy must have left the arena before it is overwritten
         if (g >= kLanes) {
             Lane& L = h->lane[g % kLanes];
+            const double ta = now_ms();
             CU(cudaStreamSynchronize(L.stream));
+            if (trace) fprintf(stderr, "[vcp] g%d lane sync %.2f..%.2f\n", g, ta, now_ms());
             float ms = 0; cudaEventElapsedTime(&ms, L.ev[EV_B64], L.ev[EV_D2H]); h->stats.ms_d2h += ms;
         }
+        const double tb = now_ms();
         rc = issue(g);
+        const double tc = now_ms();
         if (!rc && g >= kLanes - 1) rc = collect(g - (kLanes - 1));
+        if (trace) fprintf(stderr, "[vcp] g%d (%d pages) issue %.2f..%.2f collect(g%d) ..%.2f\n", g, (int)groups[g].size(), tb, tc, g - (kLanes - 1), now_ms());
     }
-    for (int g = std::max(0, G - (kLanes - 1)); g < G && !rc; g++) rc = collect(g);
+    for (int g = std::max(0, G - (kLanes - 1)); g < G && !rc; g++) { rc = collect(g); if (trace) fprintf(stderr, "[vcp] tail collect(g%d) ..%.2f\n", g, now_ms()); }
     for (int l = 0; l < kLanes; l++) {             // drain both lanes even on error
         Lane& L = h->lane[l];
         cudaStreamSynchronize(L.stream);
