@@ -217,3 +217,14 @@ def test_decode_corrupted_streams_end_in_a_status(V):
         else:
             assert d.shape == exp.shape
     assert n_err >= 24                                                         # most damage is detected (chunk CRCs are not checked)
+
+
+def test_decode_png_cut_into_thousands_of_idats(V):
+    """IDAT starts are optional parse units: a stream cut into 5000 tiny IDATs decodes like any other."""
+    rng = np.random.default_rng(5)
+    px = (rng.integers(0, 5, (300, 400, 3)) * 50).astype(np.uint8)
+    z = zlib.compress(_filtered(px), 6)
+    step = max(1, len(z) // 5000)
+    png = _png_from_idats(400, 300, 3, [z[i:i + step] for i in range(0, len(z), step)])
+    d = V.decode_pages([png])[0]
+    assert not isinstance(d, Exception) and np.array_equal(d, px)

@@ -862,11 +862,12 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             // most the whole page: page_iv checkpoint slots each.
             const unsigned long long page_iv = D.filt_len / kCkpt + 2;
             D.page_iv = (int32_t)page_iv;
-            int n_idat = 0; size_t o = 0;
+            int n_idat = 0; size_t o = 0, q = 0;
+            const size_t keep_every = (idats[i0 + j].size() + 2047) / 2048;       // parse units are optional: a PNG cut into very many IDATs offers a subset
             for (auto& c : idats[i0 + j]) {
                 const unsigned long long sb = o == 0 ? 16ull : 8ull * o;         // the deflate data starts behind the 2-byte zlib header
-                if (n_idat == 0 || sb > cand.back()) { cand.push_back(sb); n_idat++; }
-                o += c.n;
+                if ((n_idat == 0 || sb > cand.back()) && q % keep_every == 0) { cand.push_back(sb); n_idat++; }
+                o += c.n; q++;
             }
             D.n_idat = n_idat; D.ncand = (uint32_t)n_idat; D.nsurv = 0;
             D.seg_cap = n_idat + kMaxCand;
