@@ -298,7 +298,7 @@ class PagePrep:
         res = (N.DecodeResult * n)()
         N.check(self.lib.vcp_png_decode_batch(self.handle, ptrs, lens, n, out.data_ptr(), out.numel(), int(to_device), res))
         result = []
-        host = None if to_device else out.numpy()
+        good = []
         for r in res:
             if r.status != 0:
                 result.append(ValueError("PNG rejected by libvcprep (unsupported or corrupt)"))
@@ -307,7 +307,14 @@ class PagePrep:
             if to_device:
                 result.append(out[r.pix_off:r.pix_off + r.pix_len].view(shape))
             else:
-                result.append(host[r.pix_off:r.pix_off + r.pix_len].reshape(shape).copy())
+                a = np.empty(shape, np.uint8)
+                result.append(a); good.append((r, a))
+        if good:                                             # pinned staging -> the caller's arrays, on several host threads (GIL released)
+            m = len(good)
+            offs = (C.c_uint64 * m)(*[r.pix_off for r, _ in good])
+            lns = (C.c_uint64 * m)(*[r.pix_len for r, _ in good])
+            dsts = (C.c_void_p * m)(*[a.ctypes.data for _, a in good])
+            N.check(self.lib.vcp_host_scatter(out.data_ptr(), offs, lns, dsts, m, self.copy_threads))
         return result
 
     # ------------------------------------------------------------------ planning
