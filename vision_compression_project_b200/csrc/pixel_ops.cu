@@ -127,7 +127,33 @@ __device__ __forceinline__ void resample_h_tile(const PageD& P, uint32_t* sm) {
     const int mis = (int)(((uintptr_t)row0 + lo_b) & 3);
     const int span_words = (int)((mis + (hi_b - lo_b) + 3) >> 2);
     if (!rows_aligned || span_words * 4 > kHSpanMax) {              // direct path (block-uniform decision)
-        if (xx < w) for (int r = 0; r < rows; r++) resample_h_direct<C>(P, y0 + r, xx);
+        if (xx >= w) return;
+        if (rows == kHRows) {
+            // all 8 rows at once: a coefficient is loaded once per 8 rows, the pixel bytes come through L1 (rows of unaligned
+            // stride, e.g. 2550 RGB pixels = 7650 bytes, cannot share one staged alignment)
+            const int xmin = __ldg(P.hb + 2 * xx), n = __ldg(P.hb + 2 * xx + 1);
+            const uint8_t* __restrict__ p = row0 + (int64_t)xmin * C;
+            int acc[kHRows][C];
+#pragma unroll
+            for (int r = 0; r < kHRows; r++)
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) acc[r][ch] = 1 << 21;
+            for (int k = 0; k < n; k++) {
+                const int kv = __ldg(P.hk + (int64_t)k * w + xx);
+#pragma unroll
+                for (int r = 0; r < kHRows; r++)
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) acc[r][ch] += (int)__ldg(p + (int64_t)r * P.hin_stride + C * k + ch) * kv;
+            }
+#pragma unroll
+            for (int r = 0; r < kHRows; r++) {
+                uint8_t* out = P.tmp + (int64_t)(y0 + r) * P.tmp_stride + (int64_t)xx * C;
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) out[ch] = clip8(acc[r][ch]);
+            }
+            return;
+        }
+        for (int r = 0; r < rows; r++) resample_h_direct<C>(P, y0 + r, xx);
         return;
     }
     for (int r = 0; r < rows; r++) {
