@@ -537,7 +537,6 @@ int vcp_init(int device, vcp_handle** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(VCP_ECUDA, "libvcprep is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
-    if (decode_kernel_setup()) return fail(VCP_ECUDA, "cudaFuncSetAttribute (decode kernels): %s", cudaGetErrorString(cudaGetLastError()));
     vcp_handle* h = new vcp_handle();
     h->device = device;
     for (Lane& L : h->lane) {

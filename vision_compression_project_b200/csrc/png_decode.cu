@@ -867,8 +867,6 @@ __global__ void __launch_bounds__(256) k_infl_resolve(const DecBatchD b) {
     }
 }
 
-int decode_kernel_setup() { return 0; }
-
 int launch_inflate(const DecBatchD& b, cudaStream_t st) {
     if (b.npages == 0 || b.seg_total == 0) return 0;
     if (b.nscan && !b.no_scan) {

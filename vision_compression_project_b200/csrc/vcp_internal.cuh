@@ -152,7 +152,6 @@ struct DecBatchD {
 // ---- launchers (each returns the number of kernels it launched) ----
 int launch_inflate(const DecBatchD& b, cudaStream_t st);
 int launch_unfilter(const DecBatchD& b, cudaStream_t st);
-int decode_kernel_setup();
 int launch_convert(const PageD* d_pages, int npages, int max_rows, int max_w, cudaStream_t st);
 int launch_reduce(const PageD* d_pages, int npages, int max_rh, int max_rw, cudaStream_t st);
 int launch_resample_h(const PageD* d_pages, int npages, int max_rh, int max_w, cudaStream_t st);
