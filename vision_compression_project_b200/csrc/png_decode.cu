@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(32) k_infl_plan(DecPageD* __restrict__ pages, 
 }
 
 // ------------------------------------------------------------------------------------------ exec: one warp per interval
-__global__ void __launch_bounds__(32) k_infl_exec(DecPageD* __restrict__ pages, const DecSegD* __restrict__ segs, const DecIvD* __restrict__ ivs,
+__global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pages, const DecSegD* __restrict__ segs, const DecIvD* __restrict__ ivs,
                                                   int npages, int total_cap) {
     __shared__ InflMem M;
     const int lane = threadIdx.x;
