@@ -488,6 +488,24 @@ def prepare_pages(images: Sequence[Any], *, device: int = 0, **kw) -> List[Prepa
         _pool.give_back(eng)
 
 
+def prepare_stream(batches, *, depth: int = 2, device: int = 0, **kw):
+    """A long document as a sequence of page batches: yields `prepare_pages(batch)` for every batch, in order, keeping `depth`
+    batches in flight on as many engines (one host thread each, GIL released inside the library).  A single call ends with its
+    pipeline draining (the last pages' LZ / Huffman / D2H after the last H2D copy, ~3 ms); with the next batch already copying,
+    the PCIe link stays busy.  The reference's analogue is its page thread pool (pdf_extract.py:313-350)."""
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    depth = max(1, int(depth))
+    with ThreadPoolExecutor(depth) as ex:
+        pending = deque()
+        for b in batches:
+            pending.append(ex.submit(prepare_pages, b, device=device, **kw))
+            if len(pending) >= depth:
+                yield pending.popleft().result()
+        while pending:
+            yield pending.popleft().result()
+
+
 def decode_pages(pngs: Sequence[bytes], *, device: int = 0, to_device: bool = False) -> list:
     """GPU PNG decode of a batch (see PagePrep.decode_pages)."""
     eng = _pool.borrow(device)
