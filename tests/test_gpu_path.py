@@ -290,3 +290,18 @@ def test_all_gpus_in_one_process(V, synth):
     if torch.cuda.device_count() >= 2:
         got2 = V.prepare_pages_all_gpus(pages, devices=[1, 0])
         assert [r.png for r in got2] == [r.png for r in ref]
+
+
+def test_prepare_stream_keeps_batch_order_and_bytes(V, synth):
+    """Batches of a long document in flight on several engines: results come back per batch, in order, byte-identical to
+    prepare_pages on the same batch; an empty batch and a batch with a bad page pass through."""
+    batches = [[synth.make_page(10 * b + i, size=(300 + 40 * b, 400)) for i in range(3 + b)] for b in range(5)]
+    batches.insert(2, [])
+    batches[4] = batches[4] + [np.zeros((0, 5, 3), np.uint8)]
+    want = [V.prepare_pages(b, max_side=256) for b in batches]
+    for depth in (1, 3):
+        got = list(V.prepare_stream(iter(batches), depth=depth, max_side=256))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert [(x.png, x.b64, x.error is None) for x in g] == [(x.png, x.b64, x.error is None) for x in w]
+    assert want[4][-1].error is not None
