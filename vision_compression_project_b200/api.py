@@ -47,6 +47,24 @@ class PreparedPage:
     error: Optional[str] = None
     stats: dict = field(default_factory=dict)
 
+    def inline_data(self, base64_text: bool = False) -> dict:
+        """The image part for `model.generate_content([prompt, part])` (pdf_extract.py:55): handing the SDK finished PNG bytes
+        instead of the PIL image skips the second full image encode it would do per page.
+        base64_text=True gives the REST `inline_data` form (base64 string instead of raw bytes)."""
+        if self.png is None:
+            raise ValueError(self.error or "page was not prepared")
+        if base64_text:
+            if self.b64 is None:
+                raise ValueError("prepared without base64 (want_base64=False)")
+            return {"mime_type": "image/png", "data": self.b64.decode("ascii")}
+        return {"mime_type": "image/png", "data": self.png}
+
+    def blob(self) -> Tuple[str, bytes]:
+        """(mime type, bytes) — the pair SDK blob constructors take."""
+        if self.png is None:
+            raise ValueError(self.error or "page was not prepared")
+        return "image/png", self.png
+
 
 def thumbnail_size(src: Tuple[int, int], box: Tuple[int, int]) -> Tuple[int, int]:
     """Aspect-preserving target size of Image.thumbnail (PIL/Image.py:2876-2898): never enlarges."""
@@ -340,9 +358,13 @@ class PagePrep:
 
     def prepare_pages(self, images: Sequence[Any], *, size=None, max_side=None, mode: Optional[str] = "RGB",
                       resample: int = LANCZOS, reducing_gap: Optional[float] = None, compress_level: int = 6,
-                      optimize: bool = False, want_base64: bool = True, raw_shape=None) -> List[PreparedPage]:
+                      optimize: bool = False, filter_mode: str = "pillow", want_base64: bool = True,
+                      raw_shape=None) -> List[PreparedPage]:
         if mode not in ("RGB", "L", None):
             raise ValueError(f"unsupported output mode {mode!r} (RGB, L or None = keep)")
+        if filter_mode not in ("pillow", "all5"):
+            raise ValueError("filter_mode must be 'pillow' (ZipEncode.c rule: Avg only with optimize) or 'all5' (all five candidates)")
+        optimize = bool(optimize) or filter_mode == "all5"
         if compress_level == -1:
             compress_level = 6
         if not 0 <= compress_level <= 9:

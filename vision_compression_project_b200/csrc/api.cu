@@ -18,6 +18,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <chrono>
@@ -60,6 +61,7 @@ struct Lane {
     cudaEvent_t ev[EV_COUNT] = {};
 };
 constexpr int kLanes = 4;
+constexpr int kMaxGroupPages = 65535;                    // the page index is grid.y / grid.z of the row kernels
 
 struct BatchJob {                  // a streaming batch (vcp_batch_begin .. vcp_batch_end)
     struct Ready { int first, last; cudaEvent_t ev; };
@@ -75,7 +77,7 @@ struct vcp_handle {
     std::mutex mu;
     BatchJob* job = nullptr;
     Lane lane[kLanes];
-    std::map<CoeffKey, Coeffs> coeff_cache;
+    std::map<CoeffKey, std::shared_ptr<const Coeffs>> coeff_cache;   // plans hold shared_ptrs: eviction never frees tables a group still uses
     vcp_stats stats = {};
     size_t group_bytes = (size_t)2 << 30;                  // max filtered bytes per launch set
     size_t pipe_bytes = (size_t)96 << 20;                  // host inputs: source bytes per pipelined group
@@ -83,6 +85,18 @@ struct vcp_handle {
 };
 
 namespace {
+
+// Entry points serialise on the handle's mutex.  While a streaming batch (vcp_batch_begin .. vcp_batch_end) is in flight the
+// handle belongs to its worker thread: every other call is refused with VCP_EINVAL instead of blocking (the mutex is not held
+// across begin .. end, so a second call from the same thread cannot deadlock).
+struct HandleGuard {
+    vcp_handle* h; bool ok;
+    explicit HandleGuard(vcp_handle* h_) : h(h_) { h->mu.lock(); ok = h->job == nullptr; if (!ok) h->mu.unlock(); }
+    ~HandleGuard() { if (ok) h->mu.unlock(); }
+    HandleGuard(const HandleGuard&) = delete;
+};
+#define LOCK_HANDLE(h) HandleGuard guard_(h); \
+    if (!guard_.ok) return fail(VCP_EINVAL, "a streaming batch is in flight on this handle (finish it with vcp_batch_end first)")
 
 int ensure_arena(Lane& L, size_t need) {
     if (need <= L.arena_cap) return 0;
@@ -133,20 +147,22 @@ void parallel_copy(const std::vector<CopyJob>& jobs, int T) {
     for (auto& th : pool) th.join();
 }
 
-const Coeffs* get_coeffs(vcp_handle* h, int in_size, int out_size, int filter, float b0, float b1) {
+typedef std::shared_ptr<const Coeffs> CoeffRef;
+
+CoeffRef get_coeffs(vcp_handle* h, int in_size, int out_size, int filter, float b0, float b1) {
     CoeffKey key(in_size, out_size, filter, b0, b1);
     auto it = h->coeff_cache.find(key);
-    if (it != h->coeff_cache.end()) return &it->second;
-    if (h->coeff_cache.size() > 256) h->coeff_cache.clear();
-    Coeffs c;
-    if (resample_coeffs_host(in_size, out_size, filter, b0, b1, nullptr, nullptr, &c.ksize) != 0) return nullptr;
-    std::vector<int32_t> kk((size_t)out_size * c.ksize);
-    c.bounds.resize((size_t)out_size * 2);
-    if (resample_coeffs_host(in_size, out_size, filter, b0, b1, c.bounds.data(), kk.data(), &c.ksize) != 0) return nullptr;
-    c.kt.resize(kk.size());
+    if (it != h->coeff_cache.end()) return it->second;
+    if (h->coeff_cache.size() > 256) h->coeff_cache.clear();     // page plans of the group being planned keep their own references
+    auto c = std::make_shared<Coeffs>();
+    if (resample_coeffs_host(in_size, out_size, filter, b0, b1, nullptr, nullptr, &c->ksize) != 0) return nullptr;
+    std::vector<int32_t> kk((size_t)out_size * c->ksize);
+    c->bounds.resize((size_t)out_size * 2);
+    if (resample_coeffs_host(in_size, out_size, filter, b0, b1, c->bounds.data(), kk.data(), &c->ksize) != 0) return nullptr;
+    c->kt.resize(kk.size());
     for (int x = 0; x < out_size; x++)
-        for (int k = 0; k < c.ksize; k++) c.kt[(size_t)k * out_size + x] = kk[(size_t)x * c.ksize + k];
-    return &(h->coeff_cache[key] = std::move(c));
+        for (int k = 0; k < c->ksize; k++) c->kt[(size_t)k * out_size + x] = kk[(size_t)x * c->ksize + k];
+    return h->coeff_cache[key] = c;
 }
 
 struct Bump {
@@ -165,7 +181,7 @@ struct PagePlan {
     float box[4] = {0, 0, 0, 0};
     size_t o_raw = kNone, o_conv = kNone, o_red = kNone, o_tmp = kNone, o_vout = kNone, o_filt = kNone;
     size_t o_hb = kNone, o_hk = kNone, o_vb = kNone, o_vk = kNone;
-    const Coeffs* ch = nullptr; const Coeffs* cv = nullptr;
+    CoeffRef ch, cv;
     int64_t filt_len = 0;
     int nblk = 0, nsub = 0;
     uint64_t png_bound = 0;
@@ -246,7 +262,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     uint64_t png_cap = 0, b64_cap = 0;
     std::vector<int32_t> coeff_blob;
     auto put_coeff = [&](const std::vector<int32_t>& v) { const size_t o2 = coeff_blob.size(); coeff_blob.insert(coeff_blob.end(), v.begin(), v.end()); return o2; };
-    std::map<const Coeffs*, std::pair<size_t, size_t>> coeff_at;   // -> (bounds idx, kt idx) in coeff_blob
+    std::map<const Coeffs*, std::pair<size_t, size_t>> coeff_at;   // -> (bounds idx, kt idx) in coeff_blob; the plans' references keep the keys alive
     for (auto& P : plans) {
         if (!stream_in) {
             if (!o.src_device) P.o_raw = bump.take((size_t)P.sw * P.sc * P.sh + 16);
@@ -257,12 +273,12 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
             if (P.need_h) {
                 P.ch = get_coeffs(h, P.rw, P.w, o.resample, P.box[0], P.box[2]);
                 if (!P.ch) return fail(VCP_EINVAL, "bad resample parameters");
-                if (!coeff_at.count(P.ch)) { const size_t a = put_coeff(P.ch->bounds); const size_t b = put_coeff(P.ch->kt); coeff_at[P.ch] = {a, b}; }
+                if (!coeff_at.count(P.ch.get())) { const size_t a = put_coeff(P.ch->bounds); const size_t b = put_coeff(P.ch->kt); coeff_at[P.ch.get()] = {a, b}; }
             }
             if (P.need_v) {
                 P.cv = get_coeffs(h, P.rh, P.h, o.resample, P.box[1], P.box[3]);
                 if (!P.cv) return fail(VCP_EINVAL, "bad resample parameters");
-                if (!coeff_at.count(P.cv)) { const size_t a = put_coeff(P.cv->bounds); const size_t b = put_coeff(P.cv->kt); coeff_at[P.cv] = {a, b}; }
+                if (!coeff_at.count(P.cv.get())) { const size_t a = put_coeff(P.cv->bounds); const size_t b = put_coeff(P.cv->kt); coeff_at[P.cv.get()] = {a, b}; }
             }
         }
         nblocks += P.nblk; nsub += P.nsub; nrows += P.h;
@@ -342,12 +358,12 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
             D.hin = cur; D.hin_stride = cur_stride;
             if (P.need_h) {
                 D.tmp = A + P.o_tmp; D.tmp_stride = (int64_t)align_up((size_t)P.w * P.pc, 16); cur = D.tmp; cur_stride = D.tmp_stride; any_h = true;
-                D.hb = d_coeff + coeff_at[P.ch].first; D.hk = d_coeff + coeff_at[P.ch].second; D.hks = P.ch->ksize;
+                D.hb = d_coeff + coeff_at[P.ch.get()].first; D.hk = d_coeff + coeff_at[P.ch.get()].second; D.hks = P.ch->ksize;
             }
             D.vin = cur; D.vin_stride = cur_stride;
             if (P.need_v) {
                 D.vout = A + P.o_vout; D.vout_stride = (int64_t)align_up((size_t)P.w * P.pc, 16); cur = D.vout; cur_stride = D.vout_stride; any_v = true;
-                D.vb = d_coeff + coeff_at[P.cv].first; D.vk = d_coeff + coeff_at[P.cv].second; D.vks = P.cv->ksize;
+                D.vb = d_coeff + coeff_at[P.cv.get()].first; D.vk = d_coeff + coeff_at[P.cv.get()].second; D.vks = P.cv->ksize;
             }
             D.pix = cur; D.pix_stride = cur_stride;
             max_sh = std::max(max_sh, P.sh); max_sw = std::max(max_sw, P.sw);
@@ -634,7 +650,7 @@ int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* 
         for (int i = 0; i < n; i++) {
             if (all[i].status) continue;
             const size_t fb = cost(i);
-            if (groups.empty() || (bytes + fb > lim && !groups.back().empty())) {
+            if (groups.empty() || (bytes + fb > lim && !groups.back().empty()) || (int)groups.back().size() >= kMaxGroupPages) {
                 groups.emplace_back(); bytes = 0;
                 lim = limit;
                 if (!opts->src_device) {
@@ -720,7 +736,7 @@ int vcp_prepare_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vc
                       void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results) {
     int rc = check_batch_args(h, pages, n, opts, out_png, out_b64, results);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     return run_batch(h, pages, n, opts, out_png, png_cap, out_b64, b64_cap, results, [](int, int, Lane*) {});
 }
 
@@ -729,25 +745,35 @@ int vcp_batch_begin(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_
                     void* out_png, uint64_t png_cap, void* out_b64, uint64_t b64_cap, vcp_page_result* results) {
     int rc = check_batch_args(h, pages, n, opts, out_png, out_b64, results);
     if (rc) return rc;
-    h->mu.lock();                                   // released by vcp_batch_end (same calling thread)
     BatchJob* J = new BatchJob();
-    h->job = J;
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        if (h->job) { delete J; return fail(VCP_EINVAL, "a streaming batch is already in flight on this handle"); }
+        h->job = J;                                 // from here to vcp_batch_end the handle belongs to the worker (see HandleGuard)
+    }
     J->pages.assign(pages, pages + n); J->opts = *opts;
-    J->th = std::thread([=]() {
-        const int r = run_batch(h, J->pages.data(), n, &J->opts, out_png, png_cap, out_b64, b64_cap, results,
-                                [J](int first, int last, Lane* L) {
-                                    cudaEvent_t ev = nullptr;
-                                    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-                                    cudaEventRecord(ev, L->stream);
-                                    std::lock_guard<std::mutex> g(J->m);
-                                    J->ready.push_back({first, last, ev});
-                                    J->cv.notify_all();
-                                });
-        std::lock_guard<std::mutex> g(J->m);
-        J->rc = r; if (r) J->err = g_err;
-        J->done = true;
-        J->cv.notify_all();
-    });
+    try {
+        J->th = std::thread([=]() {
+            const int r = run_batch(h, J->pages.data(), n, &J->opts, out_png, png_cap, out_b64, b64_cap, results,
+                                    [J](int first, int last, Lane* L) {
+                                        cudaEvent_t ev = nullptr;
+                                        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                                        cudaEventRecord(ev, L->stream);
+                                        std::lock_guard<std::mutex> g(J->m);
+                                        J->ready.push_back({first, last, ev});
+                                        J->cv.notify_all();
+                                    });
+            std::lock_guard<std::mutex> g(J->m);
+            J->rc = r; if (r) J->err = g_err;
+            J->done = true;
+            J->cv.notify_all();
+        });
+    } catch (...) {                                 // no worker: give the handle back
+        std::lock_guard<std::mutex> lock(h->mu);
+        h->job = nullptr;
+        delete J;
+        return fail(VCP_ENOMEM, "could not start the batch worker thread");
+    }
     return 0;
 }
 
@@ -779,8 +805,10 @@ int vcp_batch_end(vcp_handle* h) {
     const int rc = J->rc;
     if (rc) g_err = J->err;
     delete J;
-    h->job = nullptr;
-    h->mu.unlock();
+    {
+        std::lock_guard<std::mutex> lock(h->mu);
+        h->job = nullptr;
+    }
     return rc;
 }
 
@@ -788,7 +816,7 @@ int vcp_batch_end(vcp_handle* h) {
 int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t* png_lens, int n,
                          void* out_pixels, uint64_t out_cap, int dst_device, vcp_decode_result* results) {
     if (!h || n < 0 || (n > 0 && (!pngs || !png_lens || !results || !out_pixels))) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     struct Idat { const uint8_t* p; size_t n; };
     std::vector<std::vector<Idat>> idats(n);
@@ -1020,7 +1048,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
 
 int vcp_get_stats(vcp_handle* h, vcp_stats* out) {
     if (!h || !out) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     *out = h->stats;
     return 0;
 }
@@ -1071,7 +1099,7 @@ int vcp_convert(vcp_handle* h, const void* d_src, int width, int height, int src
                 void* d_dst, int dst_channels) {
     if (!h || !d_src || !d_dst || width <= 0 || height <= 0) return fail(VCP_EINVAL, "bad arguments");
     if (src_channels < 1 || src_channels > 4 || (dst_channels != 1 && dst_channels != 3)) return fail(VCP_EINVAL, "unsupported conversion %d -> %d channels", src_channels, dst_channels);
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     PageD D = {};
@@ -1091,7 +1119,7 @@ int vcp_resample_coeffs(int in_size, int out_size, int filter, float box0, float
 
 int vcp_reduce(vcp_handle* h, const void* d_src, int width, int height, int channels, void* d_dst, int fx, int fy) {
     if (!h || !d_src || !d_dst || width <= 0 || height <= 0 || channels < 1 || channels > 4 || fx < 1 || fy < 1) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     PageD D = {};
@@ -1110,7 +1138,7 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
     if (!h || !d_src || !d_dst || width <= 0 || height <= 0 || out_width <= 0 || out_height <= 0) return fail(VCP_EINVAL, "bad arguments");
     if (channels != 1 && channels != 3) return fail(VCP_EINVAL, "resample supports L and RGB");
     if (filter < VCP_LANCZOS || filter > VCP_HAMMING) return fail(VCP_EINVAL, "unsupported resample filter %d", filter);
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     const bool need_h = out_width != width, need_v = out_height != height;
@@ -1119,8 +1147,8 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
         CU(cudaStreamSynchronize(L.stream));
         return 0;
     }
-    const Coeffs* ch = need_h ? get_coeffs(h, width, out_width, filter, 0.f, (float)width) : nullptr;
-    const Coeffs* cv = need_v ? get_coeffs(h, height, out_height, filter, 0.f, (float)height) : nullptr;
+    const CoeffRef ch = need_h ? get_coeffs(h, width, out_width, filter, 0.f, (float)width) : nullptr;
+    const CoeffRef cv = need_v ? get_coeffs(h, height, out_height, filter, 0.f, (float)height) : nullptr;
     if ((need_h && !ch) || (need_v && !cv)) return fail(VCP_EINVAL, "bad resample parameters");
     std::vector<int32_t> blob;
     size_t ihb = 0, ihk = 0, ivb = 0, ivk = 0;
@@ -1155,7 +1183,7 @@ int vcp_resample(vcp_handle* h, const void* d_src, int width, int height, int ch
 int vcp_png_filter(vcp_handle* h, const void* d_pix, int width, int height, int channels, int optimize,
                    void* d_dst, uint32_t* adler32_out) {
     if (!h || !d_pix || !d_dst || width <= 0 || height <= 0 || channels < 1 || channels > 4) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     vcp_page_desc d = {}; d.src = d_pix; d.width = width; d.height = height; d.channels = channels;
@@ -1187,7 +1215,7 @@ static int stream_plan(const void* d_stream, uint64_t len, int bpp, PagePlan& P)
 
 int vcp_deflate(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, int level, void* d_out, uint64_t cap, uint64_t* out_len) {
     if (!h || !d_out || !out_len) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     std::vector<PagePlan> g(1);
@@ -1204,7 +1232,7 @@ int vcp_deflate(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, int 
 
 int vcp_lz_tokens(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, uint32_t* d_tokens, uint32_t* sub_ntok_host, uint32_t* sub_hist_host) {
     if (!h || !d_tokens || !sub_ntok_host) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     std::vector<PagePlan> g(1);
@@ -1222,7 +1250,7 @@ int vcp_lz_tokens(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, ui
 
 int vcp_adler32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) {
     if (!h || !out || (len && !d_data)) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     const size_t nseg = (size_t)((len + 4095) / 4096);
@@ -1239,7 +1267,7 @@ int vcp_adler32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) 
 
 int vcp_crc32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) {
     if (!h || !out || (len && !d_data)) return fail(VCP_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     int rc = ensure_arena(L, 4096); if (rc) return rc;
@@ -1256,7 +1284,7 @@ int vcp_crc32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out) {
 int vcp_base64(vcp_handle* h, const void* d_src, uint64_t len, void* d_dst) {
     if (!h || (len && (!d_src || !d_dst))) return fail(VCP_EINVAL, "bad arguments");
     if (((uintptr_t)d_src & 3) || ((uintptr_t)d_dst & 15)) return fail(VCP_EINVAL, "vcp_base64 needs a 4-byte aligned source and a 16-byte aligned destination");
-    std::lock_guard<std::mutex> lock(h->mu);
+    LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     Lane& L = h->lane[0]; (void)L;
     launch_base64_flat((const uint8_t*)d_src, len, (uint8_t*)d_dst, L.stream);

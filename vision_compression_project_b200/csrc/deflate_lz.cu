@@ -27,6 +27,7 @@
 // Integer-issue / latency bound, not HBM bound: the stream is read ~once from L2/HBM; see DESIGN.md §4.
 #include "vcp_internal.cuh"
 #include <algorithm>
+#include <atomic>
 
 namespace vcp {
 
@@ -601,14 +602,20 @@ int launch_lz_order(const BatchD& b, cudaStream_t st) {
 template <class Cfg>
 static int launch_lz_cfg(const BatchD& b, cudaStream_t st) {
     const size_t smem = sizeof(WarpMem<Cfg>) * kLzWarps;
-    static int resident = 0;                                  // CTAs the device can hold at once (persistent grid)
-    if (!resident) {
+    // CTAs the device can hold at once (persistent grid).  The dynamic shared-memory limit is a per-device function attribute:
+    // one process may drive several GPUs (prepare_pages_all_gpus), so the cache is keyed by device ordinal.
+    static std::atomic<int> resident_by_dev[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = std::min(std::max(dev, 0), kMaxDevices - 1);
+    int resident = resident_by_dev[slot].load(std::memory_order_acquire);
+    if (!resident || dev >= kMaxDevices) {
         cudaFuncSetAttribute(k_lz<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int per_sm = 0, dev = 0, sms = 148;
-        cudaGetDevice(&dev);
+        int per_sm = 0, sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lz<Cfg>, kLzWarps * 32, smem);
         resident = std::max(1, per_sm) * sms;
+        resident_by_dev[slot].store(resident, std::memory_order_release);
     }
     const int ctas = std::min((b.nitems + kLzWarps - 1) / kLzWarps, resident);
     k_lz<Cfg><<<ctas, kLzWarps * 32, smem, st>>>(b);

@@ -16,6 +16,7 @@
 // stored as aligned 32-bit words.  A row identical to the one above (blank paper) skips the candidates.
 // HBM-bound by design: algorithmic traffic = read W*bpp + write 1 + W*bpp per row.
 #include "vcp_internal.cuh"
+#include <atomic>
 
 namespace vcp {
 
@@ -264,10 +265,16 @@ int launch_png_filter(const PageD* d_pages, int npages, int max_h, int max_rowby
     if (npages == 0 || max_h == 0) return 0;
     const int words = ((max_rowbytes + 64) / 4 + 3) & ~3;
     const size_t smem = (size_t)words * 3 * sizeof(uint32_t);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
+    if (smem > 48 * 1024) {
+        // per-device function attribute (one process may drive several GPUs): remember what each device was given
+        static std::atomic<size_t> configured_by_dev[kMaxDevices];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int slot = dev < 0 ? 0 : (dev < kMaxDevices ? dev : kMaxDevices - 1);
+        if (dev >= kMaxDevices || smem > configured_by_dev[slot].load(std::memory_order_acquire)) {
+            cudaFuncSetAttribute(k_png_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured_by_dev[slot].store(smem, std::memory_order_release);
+        }
     }
     dim3 grid((max_h + kRowsPerCta - 1) / kRowsPerCta, npages);
     k_png_filter<<<grid, kThreads, smem, st>>>(d_pages, optimize, row_adler, row_busy, words);

@@ -17,6 +17,7 @@ constexpr int kNumD       = 30;
 constexpr int kHistSize   = kNumLL + kNumD;   // 316
 constexpr int kCodeStride = 320;          // per-block code table stride (u16 codes / u8 lengths)
 constexpr int kHdrBytes   = 768;          // per-block dynamic-header scratch (<= 17 + 57 + 316*14 bits)
+constexpr int kMaxDevices = 64;           // per-device caches of kernel attributes (a process may drive every GPU of the box)
 constexpr int kStreamPad  = 256;          // bytes of addressable slack before and after every page stream
 
 // One page of a batch (lives in device memory, built on the host per plan).
