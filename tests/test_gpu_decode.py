@@ -22,6 +22,32 @@ def _px(im):
     return a.reshape(im.height, im.width, -1)
 
 
+def _pillow(png):
+    """What Image.open(png).load() does with these bytes: its pixels, or None when it raises."""
+    try:
+        im = Image.open(io.BytesIO(png))
+        im.load()
+        return _px(im).copy()
+    except Exception:
+        return None
+
+
+def _assert_like_pillow(V, pngs, names=None):
+    """The decode contract: a ValueError exactly where Pillow raises, Pillow's pixels everywhere else.  Returns the number of rejects."""
+    dec = V.decode_pages(pngs)
+    n_err = 0
+    for k, (png, d) in enumerate(zip(pngs, dec)):
+        want = _pillow(png)
+        tag = names[k] if names else k
+        if want is None:
+            assert isinstance(d, ValueError), f"{tag}: Pillow rejects this file, the GPU decoder returned pixels"
+            n_err += 1
+        else:
+            assert not isinstance(d, Exception), f"{tag}: Pillow decodes this file, the GPU decoder rejected it ({d})"
+            assert d.shape == want.shape and np.array_equal(d, want), f"{tag}: pixels differ from Pillow's"
+    return n_err
+
+
 def test_decode_own_pngs_round_trip(V, ref_page):
     from vision_compression_project_b200 import synth
     pages = [ref_page, synth.make_page(1, "letter", 200, photo=True), synth.make_page(2, size=(333, 517), mode="L"),
@@ -77,8 +103,8 @@ def test_decode_recorded_reference_png_and_errors(V, golden_dir, ref_page):
     corrupt = bytearray(raw); corrupt[5000:5040] = bytes(40)
     dec = V.decode_pages([raw, b"not a png", trunc, bytes(corrupt)])
     assert np.array_equal(dec[0], _px(ref_page))
-    assert all(isinstance(d, ValueError) for d in dec[1:3])
-    assert isinstance(dec[3], ValueError) or not np.array_equal(dec[3], _px(ref_page))
+    assert all(isinstance(d, ValueError) for d in dec[1:4])
+    assert _assert_like_pillow(V, [raw, b"not a png", trunc, bytes(corrupt)]) == 3
     pal = io.BytesIO(); Image.new("P", (4, 4)).save(pal, format="PNG")
     assert isinstance(V.decode_pages([pal.getvalue()])[0], ValueError)
 
@@ -155,7 +181,7 @@ def test_decode_large_batch_mixed_and_corrupt_segment(V):
     dec = V.decode_pages(batch, to_device=True)
     for k, d in enumerate(dec):
         if k == 2 * len(pages):
-            assert isinstance(d, ValueError) or not np.array_equal(d.cpu().numpy(), _px(pages[0]))
+            assert isinstance(d, ValueError) and _pillow(batch[k]) is None        # rejected, as Pillow does
             continue
         assert not isinstance(d, Exception), k
         assert np.array_equal(d.cpu().numpy(), _px(pages[k % len(pages) if k < 2 * len(pages) else k - 2 * len(pages) - 1])), k
@@ -182,18 +208,19 @@ def test_decode_two_groups_keep_page_order(V):
         assert np.array_equal(d, _px(im)), k
 
 
-@pytest.mark.timeout(180)
-def test_decode_corrupted_streams_end_in_a_status(V):
-    """Random damage anywhere in the file (container, zlib header, Huffman tables, tokens, Adler): every PNG of the batch comes back
-    as an error or as some array of the right shape, the intact neighbours stay exact, nothing hangs."""
+@pytest.mark.timeout(300)
+def test_decode_corrupted_streams_like_pillow(V):
+    """Random damage anywhere in the file (container, zlib header, Huffman tables, tokens, Adler-32, chunk lengths and CRCs): every PNG of
+    the batch is rejected exactly when Image.open(png).load() raises, and otherwise decodes to Pillow's pixels; intact neighbours stay
+    exact; nothing hangs."""
     from vision_compression_project_b200 import synth
     rng = np.random.default_rng(99)
     page = synth.make_page(7, size=(700, 900), photo=True)
     good = [V.prepare_pages([page], want_base64=False)[0].png, U.pillow_png(page)]
-    batch, kind = [], []
-    for t in range(48):
+    batch, names = [], []
+    for t in range(96):
         b = bytearray(good[t % 2])
-        mode = t % 4
+        mode = t % 6
         if mode == 0:
             for _ in range(3):
                 b[int(rng.integers(33, len(b)))] ^= int(rng.integers(1, 256))           # behind IHDR: the geometry stays
@@ -201,22 +228,96 @@ def test_decode_corrupted_streams_end_in_a_status(V):
             o = int(rng.integers(60, len(b) - 200)); b[o:o + 64] = rng.integers(0, 256, 64, dtype=np.uint8).tobytes()
         elif mode == 2:
             del b[int(rng.integers(100, len(b) - 100)):]
-        else:
+        elif mode == 3:
             o = int(rng.integers(41, 120)); b[o] ^= 0xFF                      # inside the first block header
-        batch.append(bytes(b)); kind.append(mode)
-        if t % 8 == 7:
-            batch.append(good[(t // 8) % 2]); kind.append(-1)
-    dec = V.decode_pages(batch)
-    exp = _px(page)
-    n_err = 0
-    for d, k in zip(dec, kind):
-        if k == -1:
-            assert not isinstance(d, Exception) and np.array_equal(d, exp)
-        elif isinstance(d, Exception):
-            n_err += 1
+        elif mode == 4:
+            o = len(b) - int(rng.integers(13, 40)); b[o] ^= 1 << int(rng.integers(0, 8))   # the last tokens / end-of-block / Adler-32 / IEND
         else:
-            assert d.shape == exp.shape
-    assert n_err >= 24                                                         # most damage is detected (chunk CRCs are not checked)
+            o = int(rng.integers(8, 33)); b[o] ^= 1 << int(rng.integers(0, 8))             # IHDR: length, tag, fields, CRC
+        batch.append(bytes(b)); names.append(f"case {t} (mode {mode})")
+        if t % 8 == 7:
+            batch.append(good[(t // 8) % 2]); names.append("intact")
+    n_err = _assert_like_pillow(V, batch, names)
+    assert n_err >= 48, n_err                                                  # the damage is real: most of it must be detected
+
+
+def test_decode_accepts_and_rejects_what_pillow_does(V):
+    """Hand-made files for every rule of Pillow's PNG loader that is not 'the stream is valid': chunk CRCs are checked in front of
+    the image data only; the Adler-32 is checked only when inflate() meets it in the call that produced the last row; data behind
+    the last row are ignored; a stream that ends early leaves black rows; zlib's header and code-completeness rules."""
+    import struct
+    from oracle import restate as R
+
+    def chunk(tag, data, crc=None):
+        c = zlib.crc32(tag + data) if crc is None else crc
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", c & 0xFFFFFFFF)
+
+    def png(w, h, c, idats, ihdr_crc=None, idat_crc=None, iend=True, pre=b"", post=b""):
+        out = [R.PNG_SIG, chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, R.COLOR_TYPE[c], 0, 0, 0), ihdr_crc), pre]
+        out += [chunk(b"IDAT", d, idat_crc) for d in idats]
+        out.append(post)
+        if iend:
+            out.append(chunk(b"IEND", b""))
+        return b"".join(out)
+
+    rng = np.random.default_rng(1)
+    cases = {}
+    for tag, (w, h, c) in {"small": (30, 20, 3), "rows": (700, 300, 3), "gray": (1000, 150, 1)}.items():
+        px = (rng.integers(0, 6, (h, w, c)) * 40).astype(np.uint8)
+        filt = _filtered(px)
+        rowlen = 1 + w * c
+        z = zlib.compress(filt, 6)
+        mk = lambda idats, **kw: png(w, h, c, idats, **kw)
+        cases[f"{tag}: good"] = mk([z])
+        cases[f"{tag}: bad IDAT crc (not checked)"] = mk([z], idat_crc=123)
+        cases[f"{tag}: bad IHDR crc"] = mk([z], ihdr_crc=123)
+        bad = bytearray(z); bad[-1] ^= 1
+        cases[f"{tag}: bad adler"] = mk([bytes(bad)])
+        cases[f"{tag}: bad adler in its own IDAT (never read)"] = mk([bytes(bad[:-4]), bytes(bad[-4:])])
+        cases[f"{tag}: adler split over two IDATs, wrong"] = mk([bytes(bad[:-2]), bytes(bad[-2:])])
+        cases[f"{tag}: no IEND"] = mk([z], iend=False)
+        cases[f"{tag}: adler cut"] = mk([z[:-1]])
+        cases[f"{tag}: adler missing"] = mk([z[:-4]])
+        cases[f"{tag}: garbage behind the stream"] = mk([z + b"abcdef"])
+        cases[f"{tag}: garbage IDAT behind the stream"] = mk([z, b"zzzzzzzz"])
+        cases[f"{tag}: one extra row"] = mk([zlib.compress(filt + bytes(rowlen), 6)])
+        cases[f"{tag}: extra partial row"] = mk([zlib.compress(filt + bytes(rowlen // 3), 6)])
+        cases[f"{tag}: one row short"] = mk([zlib.compress(filt[:-rowlen], 6)])
+        cases[f"{tag}: half the rows"] = mk([zlib.compress(filt[:rowlen * (h // 2) + 5], 6)])
+        short_bad = bytearray(zlib.compress(filt[:-rowlen], 6)); short_bad[-2] ^= 4
+        cases[f"{tag}: one row short, bad adler"] = mk([bytes(short_bad)])
+        cases[f"{tag}: one row short, adler missing"] = mk([zlib.compress(filt[:-rowlen], 6)[:-4]])
+        f5 = bytearray(filt); f5[rowlen * 3] = 5
+        cases[f"{tag}: filter type 5"] = mk([zlib.compress(bytes(f5), 6)])
+        for cinfo in (8, 6):
+            zz = bytearray(z); zz[0] = (cinfo << 4) | 8
+            zz[1] = next(f for f in range(256) if ((zz[0] << 8) | f) % 31 == 0 and not f & 0x20)
+            cases[f"{tag}: window bits {cinfo + 8}"] = mk([bytes(zz)])
+        zz = bytearray(z); zz[1] ^= 1
+        cases[f"{tag}: bad zlib header check"] = mk([bytes(zz)])
+        cases[f"{tag}: unknown chunk in front, good crc"] = mk([z], pre=chunk(b"abCd", b"hello"))
+        cases[f"{tag}: unknown chunk in front, bad crc"] = mk([z], pre=chunk(b"abCd", b"hello", 5))
+        cases[f"{tag}: text chunk behind, bad crc"] = mk([z], post=chunk(b"tEXt", b"k\0v", 5))
+        cases[f"{tag}: junk behind the data"] = mk([z], post=b"\0\0\0\1\xff\xff\xff\xffAAAAA")
+        cases[f"{tag}: empty IDAT in the middle"] = mk([z[:10], b"", z[10:]])
+        cases[f"{tag}: other chunk between IDATs (data end there)"] = png(w, h, c, [z[:len(z) // 2]], post=chunk(b"tEXt", b"k\0v") + chunk(b"IDAT", z[len(z) // 2:]))
+        co = zlib.compressobj(0)
+        cases[f"{tag}: stored blocks"] = mk([co.compress(filt) + co.flush()])
+        g = mk([z])
+        cases[f"{tag}: truncated in the data"] = g[:len(g) - 40]
+        cases[f"{tag}: truncated in IEND"] = g[:len(g) - 6]
+        cases[f"{tag}: IDAT longer than the file"] = g[:33] + struct.pack(">I", len(z) + 1000) + g[37:]
+        co = zlib.compressobj(6)
+        body = co.compress(filt) + co.flush(zlib.Z_SYNC_FLUSH)
+        tail = co.flush()                                                   # empty final block + Adler-32
+        cases[f"{tag}: empty final block, good"] = mk([body + tail])
+        t2 = bytearray(tail); t2[-1] ^= 0x10
+        cases[f"{tag}: empty final block, bad adler"] = mk([body + bytes(t2)])
+        cases[f"{tag}: empty final block in its own IDAT, bad adler"] = mk([body, bytes(t2)])
+        cases[f"{tag}: bad block type behind the last row"] = mk([body + b"\x07\x00\x00"])
+    names = list(cases)
+    n_err = _assert_like_pillow(V, [cases[k] for k in names], names)
+    assert n_err >= 3 * 9
 
 
 def test_decode_png_cut_into_thousands_of_idats(V):

@@ -305,3 +305,76 @@ def test_prepare_stream_keeps_batch_order_and_bytes(V, synth):
         for g, w in zip(got, want):
             assert [(x.png, x.b64, x.error is None) for x in g] == [(x.png, x.b64, x.error is None) for x in w]
     assert want[4][-1].error is not None
+
+
+def test_more_resize_geometries_than_the_table_cache_holds(V):
+    """A handle caches Pillow's coefficient tables per geometry and evicts the cache when it holds more than 256: pages planned earlier in
+    the same launch set must keep their tables (round-1 advisor finding: eviction freed tables a group still pointed to)."""
+    rng = np.random.default_rng(61)
+    pages = [Image.fromarray(rng.integers(0, 256, (24, 40 + i, 3), dtype=np.uint8), "RGB") for i in range(300)]
+    res = V.prepare_pages(pages, max_side=20, want_base64=False)             # 300 distinct (in, out) pairs per axis in ONE launch set
+    for im, r in zip(pages, res):
+        assert r.error is None
+        _, _, exp = PP.prepare_page_cpu(im, max_side=20)
+        dec = Image.open(io.BytesIO(r.png)); dec.load()
+        assert dec.size == exp.size and dec.tobytes() == exp.tobytes()
+    again = V.prepare_pages(pages[::-1], max_side=20, want_base64=False)     # and again, against a cache that was evicted in between
+    assert [r.png for r in again] == [r.png for r in res[::-1]]
+
+
+def test_wide_pages_and_best_level_on_every_device(V, synth):
+    """Kernels that need more than 48 KB of dynamic shared memory (the PNG filter for rows wider than ~4000 RGB pixels, the LZ tables of
+    compress_level 7-9) carry a per-device attribute: every GPU a process drives must get it, not only the first one used."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    wide = synth.make_page(3, size=(5100, 400), photo=True)                  # 600-DPI letter width
+    ref = None
+    for dev in range(n_dev):
+        r = V.prepare_pages([wide, wide], device=dev, compress_level=9)
+        assert all(x.error is None for x in r)
+        U.check_png_against(r[0].png, wide, pillow_kw={"compress_level": 9})
+        ref = ref or r[0].png
+        assert r[0].png == ref == r[1].png
+    if n_dev >= 2:
+        pages = [synth.make_page(i, size=(5100, 300)) for i in range(2 * n_dev)]
+        got = V.prepare_pages_all_gpus(pages, compress_level=9)
+        one = V.prepare_pages(pages, compress_level=9)
+        assert [g.png for g in got] == [o.png for o in one]
+
+
+def test_streaming_batch_refuses_other_calls_instead_of_blocking(V, synth):
+    """vcp_batch_begin .. vcp_batch_end: the handle belongs to the worker; a second call on it from the same thread returns VCP_EINVAL
+    (round 1 held a non-recursive mutex across begin..end: the same call dead-locked)."""
+    import ctypes as C
+    from vision_compression_project_b200 import _native as N
+    from vision_compression_project_b200.api import PagePrep
+    eng = PagePrep(0)
+    try:
+        a = np.ascontiguousarray(np.asarray(synth.make_page(2, size=(640, 480))))
+        d = (N.PageDesc * 1)()
+        d[0].src, d[0].width, d[0].height, d[0].channels = a.ctypes.data, 640, 480, 3
+        o = N.Opts(); o.out_channels, o.resample, o.compress_level, o.want_b64 = 3, 1, 6, 0
+        bp, _ = eng.output_bound(d, 1, o)
+        buf = np.empty(bp, np.uint8)
+        res = (N.PageResult * 1)()
+        N.check(eng.lib.vcp_batch_begin(eng.handle, d, 1, C.byref(o), buf.ctypes.data, bp, None, 0, res))
+        st = N.Stats()
+        assert eng.lib.vcp_get_stats(eng.handle, C.byref(st)) == N.VCP_EINVAL and "in flight" in N.last_error()
+        assert eng.lib.vcp_batch_begin(eng.handle, d, 1, C.byref(o), buf.ctypes.data, bp, None, 0, res) == N.VCP_EINVAL
+        first, last = C.c_int(), C.c_int()
+        assert eng.lib.vcp_batch_next(eng.handle, C.byref(first), C.byref(last)) == 1 and (first.value, last.value) == (0, 0)
+        assert eng.lib.vcp_batch_next(eng.handle, C.byref(first), C.byref(last)) == 0
+        N.check(eng.lib.vcp_batch_end(eng.handle))
+        assert eng.lib.vcp_get_stats(eng.handle, C.byref(st)) == 0
+        png = bytes(buf[res[0].png_off:res[0].png_off + res[0].png_len])
+        assert png == V.prepare_page(a, want_base64=False).png
+    finally:
+        eng.close()
+
+
+def test_filter_mode_keyword(V, synth):
+    im = synth.make_page(4, size=(600, 400), photo=True)
+    assert V.prepare_page(im, filter_mode="all5").png == V.prepare_page(im, optimize=True).png
+    assert V.prepare_page(im, filter_mode="pillow").png == V.prepare_page(im).png
+    with pytest.raises(ValueError):
+        V.prepare_page(im, filter_mode="best")

@@ -11,6 +11,7 @@
 #include "vcp_internal.cuh"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -611,6 +612,58 @@ int vcp_output_bound(const vcp_page_desc* pages, int n, const vcp_opts* opts, ui
 
 namespace {
 
+struct Idat { const uint8_t* p; size_t n; };       // payload of one IDAT chunk (host memory)
+
+// Accept or reject a page whose stream inflated without error, the way Image.open(png).load() would (returns the reason, or NULL).
+// Pillow feeds zlib's inflate() one piece at a time — at most 64 KiB, never across IDAT chunks (PngImageFile.load_read with
+// ImageFile.MAXBLOCK) — and stops as soon as the last row is out.  inflate() finishes everything that needs no output space in the
+// call that produced that row: so a malformed block header there, or a wrong Adler-32 behind the final block, fails the image only
+// when its bytes lie in the same piece as the end of the image; a trailer in a later piece is never looked at.  A stream whose final
+// block ends before the image does, on a row boundary, is taken as it is when its Adler-32 is right (the missing rows stay black).
+const char* decode_verdict(const DecPageD& R, const std::vector<Idat>& idats) {
+    auto locate = [&](unsigned long long zoff, size_t* k, size_t* o) {
+        size_t cum = 0;
+        for (size_t q = 0; q < idats.size(); q++) { if (zoff < cum + idats[q].n) { *k = q; *o = (size_t)(zoff - cum); return true; } cum += idats[q].n; }
+        return false;
+    };
+    auto piece_of = [&](unsigned long long zoff) -> long long { size_t k, o; return locate(zoff, &k, &o) ? (long long)((k << 24) | (o >> 16)) : -1; };
+    auto trailer_at = [&](unsigned long long zoff, uint32_t* v) {
+        uint32_t t = 0;
+        for (int q = 0; q < 4; q++) { size_t k, o; if (!locate(zoff + q, &k, &o)) return false; t = (t << 8) | idats[k].p[o]; }
+        *v = t; return true;
+    };
+    uint32_t want = 0;
+    if (R.valid_len < R.filt_len) {
+        // ZipDecode.c acts on the end of the stream only in a call that also completed a row: whole rows, and the final block with
+        // its Adler-32 in the piece that completed the last of them
+        const unsigned long long rowlen = 1ull + (unsigned long long)R.w * R.c;
+        const unsigned long long a = (R.end_bit + 7) / 8;
+        if (!R.end_bit || R.valid_len == 0 || R.valid_len % rowlen != 0 || !trailer_at(a, &want) ||
+            piece_of(a + 3) != piece_of((R.end_bit - 1) >> 3)) return "image data truncated";
+        return want == R.adler ? nullptr : "broken data stream (Adler-32 mismatch)";
+    }
+    if (!R.done_bit) return nullptr;                                  // the image ended inside a match: inflate() stopped right there
+    const long long pc = piece_of((R.done_bit - 1) >> 3);
+    if (R.post_err && piece_of(R.post_err_bit >> 3) == pc) return "broken data stream (malformed block behind the last row)";
+    if (R.end_bit) {
+        const unsigned long long a = (R.end_bit + 7) / 8;
+        if (piece_of(a + 3) == pc && trailer_at(a, &want) && want != R.adler) return "broken data stream (Adler-32 mismatch)";
+    }
+    return nullptr;
+}
+
+// CRC-32 (IEEE 802.3, as zlib's crc32()) of a few host bytes: the chunk checks of the PNG container parse
+uint32_t crc32_host(const uint8_t* p, size_t n) {
+    static uint32_t tab[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; tab[i] = c; }
+    });
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+
 int check_batch_args(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* opts, void* out_png, void* out_b64, vcp_page_result* results) {
     if (!h || n < 0 || (n > 0 && (!pages || !results)) || !opts) return fail(VCP_EINVAL, "bad arguments");
     if (n > 0 && !out_png) return fail(VCP_EINVAL, "out_png is NULL");
@@ -818,24 +871,47 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     if (!h || n < 0 || (n > 0 && (!pngs || !png_lens || !results || !out_pixels))) return fail(VCP_EINVAL, "bad arguments");
     LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
-    struct Idat { const uint8_t* p; size_t n; };
     std::vector<std::vector<Idat>> idats(n);
     std::vector<DecPageD> dp(n);
     auto be32 = [](const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; };
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
-    // ---- container parse on the host (PngImagePlugin's chunk loop): IHDR, IDAT ranges, IEND
+    // ---- container parse on the host, as PngImagePlugin does it (PIL/PngImagePlugin.py: PngImageFile._open, load_read, load_end):
+    //      every chunk in front of the first IDAT must be whole and carry a correct CRC-32 (ChunkStream.crc); the image data are the
+    //      CONSECUTIVE IDAT chunks from there (their CRCs are skipped, not checked); an IDAT that runs past the end of the file gives
+    //      what is there; whatever follows the data (IEND, or nothing at all) is not needed.
     for (int i = 0; i < n; i++) {
         memset(&results[i], 0, sizeof results[i]);
         DecPageD& D = dp[i]; memset(&D, 0, sizeof D);
         const uint8_t* p = (const uint8_t*)pngs[i]; const size_t len = (size_t)png_lens[i];
         int st = VCP_OK;
-        if (!p || len < 8 + 25 + 12 || memcmp(p, sig, 8) != 0) st = fail(VCP_EINVAL, "PNG %d: not a PNG", i);
-        size_t off = 8; bool seen_end = false, seen_hdr = false;
-        while (st == VCP_OK && !seen_end) {
-            if (off + 12 > len) { st = fail(VCP_EINVAL, "PNG %d: truncated chunk header", i); break; }
+        if (!p || len < 8 || memcmp(p, sig, 8) != 0) st = fail(VCP_EINVAL, "PNG %d: not a PNG", i);
+        size_t off = 8; bool seen_hdr = false, in_data = false;
+        auto is_cid = [](const uint8_t* t) { for (int k = 0; k < 4; k++) if (!(isalnum(t[k]) || t[k] == '_')) return false; return true; };
+        while (st == VCP_OK) {
+            if (off + 8 > len) {                                       // no further chunk header
+                if (!in_data) st = fail(VCP_EINVAL, "PNG %d: truncated before the image data", i);
+                break;
+            }
             const size_t cl = be32(p + off);
-            if (off + 12 + cl > len) { st = fail(VCP_EINVAL, "PNG %d: truncated chunk", i); break; }
             const uint8_t* tag = p + off + 4; const uint8_t* data = p + off + 8;
+            if (!is_cid(tag)) {
+                // in front of the data: "broken PNG file (chunk ...)".  Behind an IDAT Pillow meets the bad header only if its decoder
+                // still wants bytes — then the image is incomplete and fails here as well; if it is complete nothing reads the header.
+                if (!in_data) st = fail(VCP_EINVAL, "PNG %d: broken chunk header", i);
+                break;
+            }
+            if (!memcmp(tag, "IDAT", 4)) {
+                if (!seen_hdr) { st = fail(VCP_EINVAL, "PNG %d: IDAT before IHDR", i); break; }
+                in_data = true;
+                const size_t have = std::min(cl, len - (off + 8));
+                if (have) idats[i].push_back({data, have});
+                if (have < cl) break;                                  // the file ends inside this chunk
+                off += 12 + cl;
+                continue;
+            }
+            if (in_data) break;                                        // the first other chunk ends the image data
+            if (off + 12 + cl > len) { st = fail(VCP_EINVAL, "PNG %d: truncated chunk", i); break; }
+            if (crc32_host(tag, 4 + cl) != be32(data + cl)) { st = fail(VCP_EINVAL, "PNG %d: bad checksum in chunk %.4s", i, (const char*)tag); break; }
             if (!memcmp(tag, "IHDR", 4)) {
                 if (cl != 13) { st = fail(VCP_EINVAL, "PNG %d: bad IHDR", i); break; }
                 D.w = (int32_t)be32(data); D.h = (int32_t)be32(data + 4);
@@ -845,10 +921,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
                     (int64_t)D.w * D.c > (1 << 24) || D.h > (1 << 24))
                     { st = fail(VCP_EINVAL, "PNG %d: only 8-bit gray/gray+alpha/RGB/RGBA non-interlaced images are on the path", i); break; }
                 seen_hdr = true;
-            } else if (!memcmp(tag, "IDAT", 4)) {
-                if (!seen_hdr) { st = fail(VCP_EINVAL, "PNG %d: IDAT before IHDR", i); break; }
-                if (cl) idats[i].push_back({data, cl});
-            } else if (!memcmp(tag, "IEND", 4)) seen_end = true;
+            } else if (!memcmp(tag, "IEND", 4)) { st = fail(VCP_EINVAL, "PNG %d: no image data", i); break; }
             off += 12 + cl;
         }
         if (st == VCP_OK && (!seen_hdr || idats[i].empty())) st = fail(VCP_EINVAL, "PNG %d: no image data", i);
@@ -887,7 +960,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             nbands += (D.h + 31) / 32;
             // parse units: every IDAT start, plus up to kMaxCand block headers the scan finds on the device.  A parse can produce at
             // most the whole page: page_iv checkpoint slots each.
-            const unsigned long long page_iv = D.filt_len / kCkpt + 2;
+            const unsigned long long page_iv = D.filt_len / kCkpt + 3;
             D.page_iv = (int32_t)page_iv;
             int n_idat = 0; size_t o = 0, q = 0;
             const size_t keep_every = (idats[i0 + j].size() + 2047) / 2048;       // parse units are optional: a PNG cut into very many IDATs offers a subset
@@ -914,6 +987,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
                 for (unsigned long long bb = 0; bb < zl * 8ull; bb += kScanBits) { scan_page.push_back((uint32_t)j); scan_bit.push_back((uint32_t)bb); }
             D.iv_cap = (int32_t)(page_iv + (unsigned long long)D.seg_cap);
             iv_total += (size_t)D.iv_cap;
+            D.chunk0 = (int32_t)chunk_page.size();
             for (unsigned long long p = 0; p < D.filt_len; p += kResolveChunk) { chunk_page.push_back((uint32_t)j); chunk_pos.push_back((uint32_t)p); }
         }
         if (nslots >= (1ull << 31) || iv_total >= (1ull << 31) || surv_total >= (1ull << 31)) return fail(VCP_ESIZE, "PNG batch too large");
@@ -948,6 +1022,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         const size_t o_flag = bump.take(flag_bytes);
         const size_t o_slots = bump.take((nslots + 1) * sizeof(DecIvD)), o_ivs = bump.take((iv_total + 1) * sizeof(DecIvD));
         const size_t o_segs = bump.take((seg_total + 1) * sizeof(DecSegD)), o_surv = bump.take((surv_total + 1) * sizeof(uint32_t));
+        const size_t o_cadl = bump.take((chunk_page.size() + 1) * 2 * sizeof(uint32_t));
         if (G.pix_base + pix_total > out_cap) return fail(VCP_ESIZE, "out_pixels too small: need %llu bytes", (unsigned long long)(G.pix_base + pix_total));
         // device output: the un-filter writes the caller's buffer directly (it reads whole words, so the buffer must hold the last page's padding)
         const bool direct = dst_device && G.pix_base + align_up(pix_total, 4) <= out_cap;
@@ -1000,6 +1075,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         B.chunk_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes);
         B.chunk_pos = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + chunk_bytes);
         B.nchunks = (int32_t)chunk_page.size();
+        B.chunk_adler = reinterpret_cast<uint32_t*>(A + o_cadl);
         B.counters = reinterpret_cast<uint32_t*>(A + o_flag);
         B.band_flag = B.counters + 64; B.nbands = nbands;
         B.band_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes);
@@ -1040,8 +1116,11 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     for (int g = 0; g < 2; g++)
         for (int i = G[g].i0; i < G[g].i1; i++) {
             if (!G[g].hd) continue;
-            const int st_dev = G[g].hd[i - G[g].i0].status;
-            if (!results[i].status && st_dev) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: corrupt zlib stream or filter byte (code %d)", i, st_dev); }
+            const DecPageD& R = G[g].hd[i - G[g].i0];
+            if (results[i].status) continue;
+            if (R.status) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: corrupt zlib stream or filter byte (code %d)", i, R.status); continue; }
+            const char* why = decode_verdict(R, idats[i]);
+            if (why) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: %s", i, why); }
         }
     return 0;
 }

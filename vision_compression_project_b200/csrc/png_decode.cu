@@ -146,16 +146,19 @@ __device__ __forceinline__ uint32_t sym_entry(int s) {
 
 // Whole warp: canonical decode structures for n symbols with code lengths L.  Lane 0 counts and sorts, all lanes fill the lookup
 // table (one symbol per lane at a time, every replica of its code).  Returns false for an over-subscribed code.
+// `strict` applies zlib's inftrees.c rule to a code sent in a dynamic header: an incomplete code is an error too, unless it is a
+// literal/length or distance code with a single 1-bit symbol (or no symbol at all); the fixed codes of BTYPE 1 are taken as given.
 template <int KIND>
-__device__ bool build_table(InflMem& M, const uint8_t* L, int n, uint16_t* cnt, uint16_t* sorted, uint32_t* fast, int fastbits) {
+__device__ bool build_table(InflMem& M, const uint8_t* L, int n, uint16_t* cnt, uint16_t* sorted, uint32_t* fast, int fastbits, bool strict) {
     const int lane = threadIdx.x & 31;
     int ok = 1, total = 0;
     if (lane == 0) {
         for (int i = 0; i < 16; i++) cnt[i] = 0;
         for (int i = 0; i < n; i++) cnt[L[i]]++;
         cnt[0] = 0;
-        int left = 1;
-        for (int l = 1; l < 16; l++) { left <<= 1; left -= cnt[l]; if (left < 0) ok = 0; }
+        int left = 1, maxl = 0;
+        for (int l = 1; l < 16; l++) { left <<= 1; left -= cnt[l]; if (left < 0) ok = 0; if (cnt[l]) maxl = l; }
+        if (strict && ok && left > 0 && maxl != 0 && (KIND == T_CL || maxl != 1)) ok = 0;
         uint16_t o[16]; o[1] = 0; M.offs[1] = 0; M.fcode[1] = 0;
         for (int l = 1; l < 15; l++) { o[l + 1] = o[l] + cnt[l]; M.offs[l + 1] = o[l + 1]; M.fcode[l + 1] = (uint16_t)((M.fcode[l] + cnt[l]) << 1); }
         if (ok) for (int i = 0; i < n; i++) if (L[i]) sorted[o[L[i]]++] = (uint16_t)i;
@@ -236,7 +239,7 @@ __device__ int block_header(InflMem& M, BitReader& br, uint32_t& filled, int* la
         if (status != INF_OK) return status;
         __syncwarp();
         // the code-length code borrows the distance table's slots (rebuilt right after)
-        if (!build_table<T_CL>(M, M.lens, 19, M.cnt_d, M.sorted_d, M.fast_d, 7)) return INF_BAD_CODE;
+        if (!build_table<T_CL>(M, M.lens, 19, M.cnt_d, M.sorted_d, M.fast_d, 7, true)) return INF_BAD_CODE;
         if (lane == 0) {
             uint8_t* LL = M.lens + 32;        // decoded behind the 19 code-length-code lengths, moved into place below
             int i = 0;
@@ -267,8 +270,8 @@ __device__ int block_header(InflMem& M, BitReader& br, uint32_t& filled, int* la
         if (status != INF_OK) return status;
         __syncwarp();
     }
-    if (!build_table<T_LL>(M, M.lens, 288, M.cnt_ll, M.sorted_ll, M.fast_ll, kFastLL)) return INF_BAD_CODE;
-    if (!build_table<T_D>(M, M.lens + 288, 30, M.cnt_d, M.sorted_d, M.fast_d, kFastD)) return INF_BAD_CODE;
+    if (!build_table<T_LL>(M, M.lens, 288, M.cnt_ll, M.sorted_ll, M.fast_ll, kFastLL, bt == 2)) return INF_BAD_CODE;
+    if (!build_table<T_D>(M, M.lens + 288, 30, M.cnt_d, M.sorted_d, M.fast_d, kFastD, bt == 2)) return INF_BAD_CODE;
     return INF_OK;
 }
 
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(256) k_infl_sort(const DecBatchD b) {
     if (P.status != 0) return;
     if (threadIdx.x == 0) {
         if (P.zlen < 6) P.status = INF_SHORT;
-        else { const uint32_t cmf = P.z[0], flg = P.z[1]; if ((cmf & 15) != 8 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) P.status = INF_BAD_HEADER; }
+        else { const uint32_t cmf = P.z[0], flg = P.z[1]; if ((cmf & 15) != 8 || (cmf >> 4) > 7 || ((cmf << 8) | flg) % 31 != 0 || (flg & 32)) P.status = INF_BAD_HEADER; }   // inflate(): method, window size, check bits, no preset dictionary
     }
     const int K = (int)min(P.ncand, (uint32_t)P.seg_cap);
     const unsigned long long* C = b.cand_bits + P.cand0;
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
     bool done = false;
     auto emit = [&](unsigned long long out_now, unsigned long long hdr_bit, unsigned long long bit_now) {   // lane 0: close the interval at a token boundary
         if (out_now > iv_out) {
-            if (niv < S.iv_cap) { DecIvD& I = slots[S.iv0 + niv]; I.hdr_bit = iv_hdr; I.start_bit = iv_start; I.out = (uint32_t)iv_out; I.len = (uint32_t)(out_now - iv_out); I.seg = (uint32_t)sg; }
+            if (niv < S.iv_cap) { DecIvD& I = slots[S.iv0 + niv]; I.hdr_bit = iv_hdr; I.start_bit = iv_start; I.out = (uint32_t)iv_out; I.len = (uint32_t)(out_now - iv_out); I.seg = (uint32_t)sg; I.last = 0; }
             niv++;
         }
         iv_hdr = hdr_bit; iv_start = bit_now; iv_out = out_now;
@@ -540,8 +543,8 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
         status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
         if (status != INF_OK) break;
         if (btype == 0) {
-            if (pos + slen > cap) { status = INF_OVERRUN; break; }
             pos += slen;
+            if (pos > cap) { status = INF_OVERRUN; break; }
         } else {
             bool eob = false;
             unsigned long long B = __shfl_sync(kFull, br.bits_used(), 0);      // bit position of the next token
@@ -601,14 +604,21 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
         done = __shfl_sync(kFull, stop, 0) != 0;
     }
     if (lane == 0) {
-        if (status == INF_OK) { const unsigned long long used = br.bits_used(); emit(pos, used, used); }
-        if (status == INF_OK && niv > S.iv_cap) status = INF_OVERRUN;
-        S.olen = (uint32_t)pos; S.next = next; S.fin = last; S.niv = niv;
+        // A parse that failed (or ran past the size of the image) still keeps what it produced up to there: Pillow's decoder stops
+        // at the last row of the image and never looks at what follows, so k_infl_plan accepts a failed unit if the image ends in it.
+        const unsigned long long used = br.bits_used();
+        emit(min(pos, cap), used, used);
+        if (niv > S.iv_cap) { status = INF_OVERRUN; pos = 0; niv = 0; }
+        S.olen = (uint32_t)min(pos, cap); S.next = next; S.fin = status == INF_OK ? last : 0; S.niv = niv;
+        S.end_bit = (status == INF_OK && last) ? used : 0ull;
         S.ok = status == INF_OK ? 1 : status;
     }
 }
 
-// Walk the chain of IDATs whose parse began at a true block boundary; copy their intervals, in stream order, with absolute offsets.
+// Walk the chain of parse units whose parse began at a true block boundary; copy their intervals, in stream order, with absolute
+// offsets.  The image ends where filt_len bytes have been produced — Pillow's decoder (ZipDecode.c) stops at its last row and never
+// looks at what follows — so a unit that failed or overran after that point is as good as any; the interval that reaches the end is
+// clipped and marked (k_infl_exec inspects what lies behind it).  A stream whose final block ends early is kept too (valid_len).
 __global__ void __launch_bounds__(32) k_infl_plan(DecPageD* __restrict__ pages, DecSegD* __restrict__ segs, const DecIvD* __restrict__ slots,
                                                   DecIvD* __restrict__ ivs, int n) {
     const int pg = blockIdx.x, lane = threadIdx.x;
@@ -616,23 +626,88 @@ __global__ void __launch_bounds__(32) k_infl_plan(DecPageD* __restrict__ pages, 
     DecPageD& P = pages[pg];
     if (P.status != 0) return;
     DecSegD* S = segs + P.seg0;
-    unsigned long long opos = 0; uint32_t niv = 0;
+    const unsigned long long flen = P.filt_len;
+    unsigned long long opos = 0, end_bit = 0; uint32_t niv = 0;
     int s = 0, fin = 0, status = INF_OK;
+    bool complete = false;
     for (int guard = 0; s < P.nseg && guard <= P.nseg; guard++) {
         const int ok = S[s].ok;
-        if (ok != 1) { status = ok < 0 ? ok : INF_SEG; break; }
-        if (niv + S[s].niv > (uint32_t)P.iv_cap || opos + S[s].olen > P.filt_len) { status = INF_OVERRUN; break; }
-        for (uint32_t i = lane; i < S[s].niv; i += 32) {
-            DecIvD I = slots[S[s].iv0 + i];
-            I.out += (uint32_t)opos;
-            ivs[P.iv0 + niv + i] = I;
+        const unsigned long long avail = S[s].olen;
+        const bool enough = opos + avail >= flen;
+        if (ok != 1 && !enough) { status = ok < 0 ? ok : INF_SEG; break; }
+        if (niv + S[s].niv > (uint32_t)P.iv_cap) { status = INF_OVERRUN; break; }
+        uint32_t kept = 0;
+        for (uint32_t i0 = 0; i0 < S[s].niv; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool keep = false; DecIvD I;
+            if (i < S[s].niv) {
+                I = slots[S[s].iv0 + i];
+                const unsigned long long a = opos + I.out;
+                keep = a < flen;
+                if (keep) {
+                    I.out = (uint32_t)a;
+                    if (a + I.len >= flen) { I.len = (uint32_t)(flen - a); I.last = 1; }
+                }
+            }
+            const uint32_t m = __ballot_sync(kFull, keep);          // intervals are in output order: the kept ones are a prefix
+            if (keep) ivs[P.iv0 + niv + kept + __popc(m & ((1u << lane) - 1u))] = I;
+            kept += __popc(m);
         }
         if (lane == 0) S[s].opos = (uint32_t)opos;
-        niv += S[s].niv; opos += S[s].olen; fin = S[s].fin;
+        niv += kept;
+        if (enough) { complete = true; break; }
+        opos += avail; fin = S[s].fin; end_bit = S[s].end_bit;
+        if (fin) break;
         s = S[s].next;
     }
-    if (status == INF_OK && (!fin || opos != P.filt_len)) status = INF_SHORT;
-    if (lane == 0) { P.niv = (int32_t)niv; if (status != INF_OK) P.status = status; }
+    if (status == INF_OK && !complete && !fin) status = INF_SHORT;
+    if (lane == 0) {
+        P.niv = (int32_t)niv;
+        P.valid_len = complete ? flen : opos;
+        P.done_bit = 0; P.end_bit = complete ? 0ull : end_bit; P.post_err_bit = 0; P.post_err = 0; P.adler = 0;
+        if (status != INF_OK) P.status = status;
+    }
+}
+
+// Whole warp, once per page, behind the token that produced the last byte of the image.  zlib's inflate() — which Pillow drives one
+// image row at a time — goes on from there through everything that needs no output space: end-of-block codes, block headers, empty
+// stored blocks, and after a final block the Adler-32.  So a malformed header there, or a wrong checksum, fails the image in Pillow
+// (if the bytes were handed to inflate() in the same call: the host checks that, api.cu decode_verdict), while anything behind the
+// first literal or match is never seen.  B = bit position of the next token (in_block) or block header; last = BFINAL of the block.
+__device__ void post_complete(InflMem& M, BitReader& br, uint32_t& filled, unsigned long long B, bool in_block, int last, DecPageD& P) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nbits = br.n * 8ull;
+    unsigned long long end_bit = 0, err_bit = 0; int err = 0;
+    for (int guard = 0; guard < 64; guard++) {
+        if (in_block) {
+            if (B >= nbits) break;                                            // out of input: inflate() would wait for more
+            topup(M, br, filled, (uint32_t)((B + 8ull * (unsigned)br.mis) >> 5));
+            uint32_t w0, w1, info = 0, tok = 0;
+            ring_window(M, br, B + lane, &w0, &w1);
+            spec_decode<true>(M, w0, w1, &info, &tok);
+            const uint32_t inf = __shfl_sync(kFull, info, 0);
+            if (inf & SP_BAD) { if (B + 15 <= nbits) { err = INF_BAD_CODE; err_bit = B; } break; }
+            if (!(inf & SP_EOB)) break;                                       // a literal or a match: needs output space, never decoded
+            B += inf & 63u;
+            if (B > nbits) break;                                             // the end-of-block code itself is cut off
+            in_block = false;
+            seek_bit(M, br, filled, B);
+        }
+        if (last) { end_bit = B; break; }
+        if (B + 3 > nbits) break;
+        int btype = 0, slen = 0; unsigned long long ssrc = 0;
+        const int st = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
+        const unsigned long long after = __shfl_sync(kFull, br.bits_used(), 0);
+        if (st == INF_SHORT || after > nbits) break;                          // the header is cut off
+        if (st != INF_OK) { err = st; err_bit = B; break; }
+        if (btype == 0) {
+            if (slen > 0) break;                                              // stored bytes need output space
+            B = 8ull * ssrc;
+            continue;
+        }
+        B = after; in_block = true;
+    }
+    if (lane == 0) { P.end_bit = end_bit; P.post_err = err; P.post_err_bit = err_bit; }
 }
 
 // ------------------------------------------------------------------------------------------ exec: one warp per interval
@@ -657,6 +732,8 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
     uint32_t pos = 0;
     int status = INF_OK, last = 0;
     bool first = true;
+    bool clipped = false, in_block = false;                                   // I.last: how the image ended
+    unsigned long long end_B = 0;
     while (status == INF_OK && pos < target) {
         int btype = 0, slen = 0; unsigned long long ssrc = 0;
         status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
@@ -670,7 +747,11 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
             }
         }
         if (btype == 0) {
-            if (pos + (uint32_t)slen > target) { status = INF_SEG; break; }
+            if (pos + (uint32_t)slen > target) {
+                if (!I.last) { status = INF_SEG; break; }
+                slen = (int)(target - pos); clipped = true;                   // the image ends inside this stored block
+            }
+            in_block = false; end_B = 8ull * (ssrc + (unsigned long long)slen);
             const uint8_t* s = P.z + ssrc;
             for (int k = lane; k < slen; k += 32) out[pos + k] = (uint16_t)s[k];
             pos += (uint32_t)slen;
@@ -707,8 +788,12 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
                         if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
                         if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
                     }
-                    const uint32_t sz = (inf >> 6) & 511u;
-                    if (sz > room) { status = INF_SEG; break; }               // the probe cut at a token boundary: must land exactly
+                    uint32_t sz = (inf >> 6) & 511u;
+                    if (sz > room) {                                          // the probe cut at a token boundary: must land exactly ...
+                        if (!I.last) { status = INF_SEG; break; }
+                        if (lane == o) tok = (tok & ~511u) | room;            // ... except where the image ends inside a match
+                        sz = room; clipped = true;
+                    }
                     if (lane == o) M.tok[ntok] = tok;
                     ntok++; room -= sz; o += (int)(inf & 63u);
                 }
@@ -764,8 +849,14 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
         }
         if (status == INF_OK && eob && last && pos < target) status = INF_SHORT;
         if (status == INF_OK && pos < target) seek_bit(M, br, filled, B);     // the header reader continues behind the end-of-block code
+        in_block = !eob; end_B = B;
     }
     if (lane == 0 && status != INF_OK) atomicMin(&P.status, status);
+    if (I.last && status == INF_OK && !clipped) {
+        // the image ended on a token boundary: record it and look at what inflate() would still have processed
+        if (lane == 0) P.done_bit = end_B;
+        post_complete(M, br, filled, end_B, in_block, last, P);
+    }
 }
 
 // The last 32 KiB of every interval, in stream order: symbol -> byte through the (already concrete) 32 KiB in front of the interval.
@@ -814,7 +905,7 @@ __global__ void __launch_bounds__(256) k_infl_resolve(const DecBatchD b) {
     if (P.status != 0) return;
     const DecIvD* __restrict__ S = b.ivs + P.iv0;
     const int nseg = P.niv;
-    const unsigned long long c0 = b.chunk_pos[ck], flen = P.filt_len;
+    const unsigned long long c0 = b.chunk_pos[ck], flen = P.valid_len;      // (a stream that ended early has nothing behind valid_len)
     const uint16_t* __restrict__ sym = P.sym;
     uint8_t* filt = P.filt;
     // interval of the chunk's first position (last s with out <= c0), searched once per CTA; threads walk on from there
@@ -867,6 +958,68 @@ __global__ void __launch_bounds__(256) k_infl_resolve(const DecBatchD b) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ Adler-32 of the inflated stream
+// zlib checks it inside inflate() (adler32.c), so Pillow rejects a PNG whose pixels decode but whose trailer does not match.  Same
+// row-partial scheme as the encoder (png_filter.cu): a CTA folds one 32 KiB chunk into (sum b, sum (n - i) b) mod 65521, a warp per
+// page chains the chunks with  b += n * a + s2 ; a += s1.  A stream whose final block ended early (valid_len < filt_len: Pillow
+// leaves the missing rows black) is checked over what exists, and its missing rows are written as filter type 0, zeros.
+__global__ void __launch_bounds__(256) k_dec_adler_part(const DecBatchD b) {
+    __shared__ uint32_t r1[8], r2[8];
+    const int ck = blockIdx.x;
+    const DecPageD& P = b.pages[b.chunk_page[ck]];
+    if (P.status != 0) return;
+    const unsigned long long c0 = b.chunk_pos[ck], vlen = P.valid_len, flen = P.filt_len;
+    uint8_t* filt = P.filt;
+    const int n = c0 < vlen ? (int)min((unsigned long long)kResolveChunk, vlen - c0) : 0;
+    uint32_t s1 = 0; unsigned long long s2 = 0;
+    const uint4* __restrict__ q = reinterpret_cast<const uint4*>(filt + c0);           // chunks start 32 KiB apart in a 256-byte aligned stream
+    for (int i = threadIdx.x * 16; i < n; i += 256 * 16) {
+        if (i + 16 <= n) {
+            const uint4 v = q[i >> 4];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t t = __dp4a(w[k], 0x01010101u, 0u);
+                s1 += t;
+                s2 += (unsigned long long)(uint32_t)(n - (i + 4 * k)) * t - __dp4a(w[k], 0x03020100u, 0u);
+            }
+        } else {
+            for (int k = i; k < n; k++) { const uint32_t v = filt[c0 + k]; s1 += v; s2 += (unsigned long long)(uint32_t)(n - k) * v; }
+        }
+    }
+    uint32_t s2m = (uint32_t)(s2 % 65521ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(kFull, s1, o); s2m += __shfl_xor_sync(kFull, s2m, o); }
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = s1; r2[threadIdx.x >> 5] = s2m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t1 = 0, t2 = 0;
+        for (int w = 0; w < 8; w++) { t1 += r1[w]; t2 += r2[w]; }
+        b.chunk_adler[2 * ck] = t1 % 65521u; b.chunk_adler[2 * ck + 1] = t2 % 65521u;
+    }
+    if (vlen < flen) {                                                                 // rows the stream never reached
+        const unsigned long long rowlen = 1ull + (unsigned long long)P.w * P.c;
+        const unsigned long long z0 = max(c0, vlen / rowlen * rowlen), z1 = min(flen, c0 + (unsigned long long)kResolveChunk);
+        __syncthreads();
+        for (unsigned long long k = z0 + threadIdx.x; k < z1; k += 256) filt[k] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_dec_adler_fin(const DecBatchD b) {
+    DecPageD& P = b.pages[blockIdx.x];
+    if (P.status != 0 || threadIdx.x != 0) return;
+    const unsigned long long vlen = P.valid_len;
+    uint32_t a = 1, s = 0;
+    const int nck = (int)((vlen + kResolveChunk - 1) / kResolveChunk);
+    for (int k = 0; k < nck; k++) {
+        const uint32_t n = (uint32_t)min((unsigned long long)kResolveChunk, vlen - (unsigned long long)k * kResolveChunk);
+        const uint32_t p1 = b.chunk_adler[2 * (P.chunk0 + k)], p2 = b.chunk_adler[2 * (P.chunk0 + k) + 1];
+        s = (uint32_t)((s + (unsigned long long)n * a + p2) % 65521ull);
+        a = (a + p1) % 65521u;
+    }
+    P.adler = (s << 16) | a;
+}
+
 int launch_inflate(const DecBatchD& b, cudaStream_t st) {
     if (b.npages == 0 || b.seg_total == 0) return 0;
     if (b.nscan && !b.no_scan) {
@@ -878,8 +1031,12 @@ int launch_inflate(const DecBatchD& b, cudaStream_t st) {
     k_infl_plan<<<b.npages, 32, 0, st>>>(b.pages, b.segs, b.slots, b.ivs, b.npages);
     k_infl_exec<<<b.iv_total, 32, 0, st>>>(b.pages, b.segs, b.ivs, b.npages, b.iv_total);
     k_infl_window<<<b.npages * kWinCluster, 1024, 0, st>>>(b.pages, b.ivs, b.npages);
-    if (b.nchunks) k_infl_resolve<<<b.nchunks, 256, 0, st>>>(b);
-    return 7 + (b.nchunks ? 1 : 0);
+    if (b.nchunks) {
+        k_infl_resolve<<<b.nchunks, 256, 0, st>>>(b);
+        k_dec_adler_part<<<b.nchunks, 256, 0, st>>>(b);
+    }
+    k_dec_adler_fin<<<b.npages, 32, 0, st>>>(b);
+    return 8 + (b.nchunks ? 2 : 0);
 }
 
 // ------------------------------------------------------------------------------------------ un-filter

@@ -112,6 +112,15 @@ struct DecPageD {
     int32_t slot0, page_iv;                         // first checkpoint slot; slots per parse unit (filt_len / 64 Ki + 2)
     int32_t iv0, iv_cap, niv;                       // its intervals in the DecIvD array (niv written by k_infl_plan)
     int32_t band0;                                  // first 32-row band of this page in the un-filter's band numbering
+    int32_t chunk0;                                 // first 32 KiB chunk of this page in the resolve / Adler work list
+    // ---- what Pillow's decoder (zlib inflate driven row by row, ZipDecode.c) would have seen at the end of the image; the host
+    //      turns these into accept / reject exactly as Image.open(png).load() does (api.cu: decode_verdict)
+    unsigned long long valid_len;                   // inflated bytes that exist: filt_len, or less when the final block ended early
+    unsigned long long done_bit;                    // bit position behind the token that produced the last byte of the image (0: it ended inside a token)
+    unsigned long long end_bit;                     // bit position behind the final block when nothing but block ends / headers lie between (0: not reached)
+    unsigned long long post_err_bit;                // where a malformed element sits between done_bit and the first thing that needs output space
+    int32_t post_err;                               // its error code (0: none)
+    uint32_t adler;                                 // Adler-32 of the valid_len inflated bytes (k_dec_adler_fin)
 };
 
 // A place where a parse of a page's deflate stream may begin: an IDAT start or a block header found by the scan (k_infl_probe).
@@ -124,6 +133,7 @@ struct DecSegD {
     int32_t fin;             // it met the final block
     uint32_t niv;            // intervals it wrote
     uint32_t iv0, iv_cap;    // its private range of checkpoint slots
+    unsigned long long end_bit;     // fin: bit position behind the final block (the Adler-32 follows at the next byte boundary)
 };
 
 // A stretch of tokens between two checkpoints of a parse: the unit of k_infl_exec.
@@ -131,7 +141,8 @@ struct DecIvD {
     unsigned long long hdr_bit;    // bit position (in the page's zlib stream) of the header of the deflate block it starts in
     unsigned long long start_bit;  // bit position of its first token
     uint32_t out, len;             // output range (relative to the parse unit in the probe's slots, absolute after k_infl_plan)
-    uint32_t seg, pad;
+    uint32_t seg;
+    uint32_t last;                 // 1 = the interval that ends the image: its last token may reach past the end (clipped), and what follows is inspected
 };
 
 struct DecBatchD {
@@ -142,7 +153,8 @@ struct DecBatchD {
     const uint32_t* scan_page; const uint32_t* scan_bit; int32_t nscan;       // scan work list: 8 Ki bit positions each
     DecIvD* slots;                                                            // checkpoint slots, one private range per parse unit
     DecIvD* ivs; int32_t iv_total;                                            // intervals in stream order, one range per page
-    const uint32_t* chunk_page; const uint32_t* chunk_pos; int32_t nchunks;   // resolve work list: 32 Ki positions each
+    const uint32_t* chunk_page; const uint32_t* chunk_pos; int32_t nchunks;   // resolve / Adler work list: 32 Ki positions each
+    uint32_t* chunk_adler;                                                    // per chunk: (sum of bytes, position-weighted sum) mod 65521
     uint32_t* band_flag; int32_t nbands;                                      // un-filter progress per band (zeroed per launch)
     const uint32_t* band_page; const uint32_t* band_idx;                      // un-filter work list in ticket order (band-major over pages)
     uint32_t* counters;                                                       // [0] un-filter CTA ticket (zeroed per launch)
