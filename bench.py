@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py — pages/sec of the page-image prep path (convert -> PNG filter+deflate -> base64) on B200.
+"""bench.py — pages/sec of the page-image prep path (convert -> [resize] -> PNG filter+deflate -> base64) on B200.
 
 Contract (task statement §④):  python bench.py --gpus N --steps K --warmup W  [--impl reference]
-  * workload at every N: BASELINE.json configs[1] per GPU — a batch of 64 synthetic letter-size pages at 200 DPI
+  * headline workload at every N: BASELINE.json configs[1] per GPU — a batch of 64 synthetic letter-size pages at 200 DPI
     (1700x2200 RGB, seeds = global page index); "step" = one pass of the whole path over that batch.
     N > 1 is weak scaling: every rank owns its own page range, no data-path collective (SURVEY.md §8 e).
   * value   = pages/s with the pages already resident in HBM and the outputs left in HBM (whole job, all ranks).
-  * e2e     = the same metric through the public function `prepare_pages` with HOST (pinned) page buffers in and
-              Python bytes out: H2D, every kernel, D2H and the bytes slicing are inside the timed region.
+  * e2e     = the same metric through the public function `prepare_stream` / `prepare_pages` with HOST (pinned) page buffers in and
+              Python bytes out: H2D, every kernel, D2H and the bytes slicing are inside the timed region; next to it the same call
+              with PIL images in (the reference's own input type) and the reference's calling pattern (5 threads, one page per call).
   * roofline= the dominant kernel (LZ77 match finding) — algorithmic bytes of the step / its CUDA-event time.
   * cpu_baseline / --impl reference = the reference's own CPU path (Pillow save + base64, oracle/pillow_path.py)
-    on all host cores of this box, on a bounded sample of the same pages.
+    on all host cores of this box, on the same 64 pages.
+  * configs = the other BASELINE.json configs, each pixel-checked against the Pillow path outside the timed region:
+      C1 the reference's recorded output/page_1.png, one call;  C3 256 letter-300 pages -> LANCZOS 1568;  C5 the 48-type mix  (N = 1)
+      c4  = the 2,000-page document (25 % photo pages) sharded by page range over the N ranks through sharding.py: STRONG scaling.
 """
 from __future__ import annotations
 
 import argparse
 import base64
+import hashlib
 import json
 import os
 import subprocess
@@ -29,6 +34,8 @@ sys.path.insert(0, ROOT)
 PAGES_PER_GPU = 64
 PAPER, DPI = "letter", 200
 WORKLOAD = "C2: 64 synthetic letter-size pages @200 DPI (1700x2200 RGB) per GPU, convert('RGB') + PNG + base64"
+L2_NOTE = "inputs (718 MB/step) larger than L2, no flush needed"
+C3_PAGES, C4_PAGES, MAX_SIDE = 256, 2000, 1568
 
 
 def host_cores() -> int:
@@ -38,22 +45,48 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def make_pages(first_seed: int, n: int):
-    from concurrent.futures import ThreadPoolExecutor
+def bench_config() -> dict:
+    """`config` of the JSON line — the same dict for this arm and for --impl reference."""
+    return {"workload": WORKLOAD, "pages_per_gpu": PAGES_PER_GPU, "l2": L2_NOTE}
+
+
+# ------------------------------------------------------------------------------------------------ synthetic pages
+def PageFactory(workers: int):
     from vision_compression_project_b200 import synth
-    with ThreadPoolExecutor(min(host_cores(), 16)) as ex:
-        return list(ex.map(lambda s: synth.make_page(s, PAPER, DPI), range(first_seed, first_seed + n)))
+    return synth.PageFactory(workers)
+
+
+def c2_specs(first_seed, n):
+    return [(s, PAPER, DPI, "RGB", False) for s in range(first_seed, first_seed + n)]
+
+
+def c3_specs(n):
+    return [(s, "letter", 300, "RGB", s % 4 == 3) for s in range(n)]
+
+
+def c4_specs(lo, hi):
+    return [(s, "letter", 200, "RGB", s % 4 == 3) for s in range(lo, hi)]
+
+
+def c5_specs():
+    from vision_compression_project_b200 import synth
+    return [(i, p, d, m, c) for i, (p, d, m, c) in enumerate(synth.mixed_page_types())]
+
+
+def to_pil(a):
+    from PIL import Image
+    return Image.fromarray(a, "RGB" if a.ndim == 3 else "L")
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_path_pages_per_s(pages, threads: int, repeats: int = 1):
-    """The reference's CPU path (Pillow PNG save + base64) over `pages` on `threads` host threads.
+def cpu_path_pages_per_s(pages, threads: int, repeats: int = 1, **kw):
+    """The reference's CPU path (Pillow [resize +] PNG save + base64) over `pages` on `threads` host threads.
     Pillow releases the GIL inside its encoder, so threads scale like the reference's own 5-thread pool."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle.pillow_path import prepare_page_cpu
 
     def one(im):
-        png, b64, _ = prepare_page_cpu(im)
+        png, b64, _ = prepare_page_cpu(im, **kw)
         return len(png)
     best = None
     with ThreadPoolExecutor(threads) as ex:
@@ -70,8 +103,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = host_cores()
-    sample = max(8, min(PAGES_PER_GPU, 2 * cores))
-    pages = make_pages(0, sample)
+    fac = PageFactory(cores)
+    pages = [to_pil(a) for a in fac.arrays(c2_specs(0, PAGES_PER_GPU))]
+    fac.close()
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_path_pages_per_s(pages[:max(1, cores // 2)], cores)
     t0 = time.perf_counter()
@@ -85,9 +119,9 @@ def run_reference(args):
         "impl": "reference", "metric": "pages/sec (resize+PNG+base64)", "value": v, "unit": "pages/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pages_per_step": len(pages)},
+        "config": bench_config(),
         "cpu_baseline": {"value": v, "unit": "pages/s", "cores": cores, "kind": "reference",
-                         "sample": f"{len(pages)} of the 64 pages per step, Pillow {__import__('PIL').__version__} Image.save(PNG)+base64 on {cores} threads"},
+                         "sample": f"all {len(pages)} pages of the step, Pillow {__import__('PIL').__version__} Image.save(PNG)+base64 on {cores} threads"},
         "e2e": {"value": v, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -134,30 +168,144 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm helpers
+def pinned_like(torch, arrays):
+    """One pinned host block holding copies of `arrays` (same shapes); returns the list of numpy views, or None if pinning fails."""
+    import numpy as np
+    total = sum(int(a.nbytes) for a in arrays)
+    try:
+        block = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    except RuntimeError:
+        return None
+    out, off = [], 0
+    flat = block.numpy()
+    for a in arrays:
+        v = flat[off:off + a.nbytes].reshape(a.shape)
+        np.copyto(v, a)
+        out.append(v)
+        off += a.nbytes
+    out.append(block)                                   # keep-alive rides at the end of the list
+    return out
+
+
+def device_resident_rate(eng, torch, N, arrays, kw, steps, warm=2):
+    """pages/s of one vcp_prepare_batch over `arrays` already in HBM, outputs left in HBM; also the per-stage CUDA-event times."""
+    from vision_compression_project_b200.api import PagePrep, _as_source
+    dev = [torch.from_numpy(a).cuda() for a in arrays]
+    n = len(dev)
+    descs = (N.PageDesc * n)()
+    for i, t in enumerate(dev):
+        descs[i] = PagePrep._plan(_as_source(t, None), None, kw.get("max_side"), "RGB", 1, kw.get("reducing_gap"))
+    o = N.Opts()
+    o.out_channels, o.resample, o.compress_level, o.want_b64, o.src_device, o.dst_device = 3, 1, 6, 1, 1, 1
+    bp, bb = eng.output_bound(descs, n, o)
+    cap_p, cap_b = max(64 << 20, bp // 3), max(88 << 20, bb // 3)
+    op = torch.empty(cap_p, dtype=torch.uint8, device="cuda")
+    ob = torch.empty(cap_b, dtype=torch.uint8, device="cuda")
+    for _ in range(warm):
+        eng.run(descs, n, o, op.data_ptr(), cap_p, ob.data_ptr(), cap_b)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage, launches = {}, 0
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(steps):
+        eng.run(descs, n, o, op.data_ptr(), cap_p, ob.data_ptr(), cap_b)
+        st = eng.stats()
+        launches += st["kernel_launches"]
+        for k_, v_ in st.items():
+            if k_.startswith("ms_"):
+                stage[k_] = stage.get(k_, 0.0) + v_ / steps
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del dev, op, ob
+    return n / (ms / 1e3), ms, {k_: round(v_, 4) for k_, v_ in stage.items()}, launches
+
+
+def check_against_pillow(outs, arrays, idx, kw):
+    """Outside every timed region: pages `idx` decode to exactly the pixels of the Pillow path; returns ours/Pillow PNG size over them."""
+    import io
+    from PIL import Image
+    from oracle.pillow_path import prepare_page_cpu
+    ours = ref = 0
+    for i in idx:
+        png, _, exp = prepare_page_cpu(to_pil(arrays[i]), **kw)
+        dec = Image.open(io.BytesIO(outs[i].png)); dec.load()
+        assert dec.size == exp.size and dec.mode == exp.mode and dec.tobytes() == exp.tobytes(), f"page {i}: pixels differ from the Pillow path"
+        assert outs[i].b64 == base64.b64encode(outs[i].png), f"page {i}: base64 mismatch"
+        ours += len(outs[i].png); ref += len(png)
+    return ours / max(1, ref)
+
+
+def sub_config(name, fn):
+    """A side config must never take the headline down with it: its failure is reported in its record."""
+    t0 = time.perf_counter()
+    try:
+        rec = fn()
+    except Exception as e:  # noqa: BLE001
+        rec = {"error": f"{type(e).__name__}: {e}"[:300]}
+    rec["bench_wall_s"] = round(time.perf_counter() - t0, 2)
+    return rec
+
+
+def lz_traffic():
+    """DRAM bytes of one k_lz launch on the C2 batch from the committed ncu capture — only if it was taken from this kernel source
+    (the file records the sha256 of deflate_lz.cu; .git does not travel to the GPU box, so HEAD cannot be compared there)."""
+    try:
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_k_lz_traffic.json"))
+        tj = json.load(open(os.path.join(ROOT, "profiles", cands[-1])))
+        src = open(os.path.join(ROOT, "vision_compression_project_b200", "csrc", "deflate_lz.cu"), "rb").read()
+        if tj.get("source_sha16") != hashlib.sha256(src).hexdigest()[:16]:
+            return None, f"{cands[-1]} is from another version of deflate_lz.cu"
+        return tj["dram_bytes_read"] + tj["dram_bytes_write"], cands[-1]
+    except Exception as e:  # noqa: BLE001
+        return None, f"no capture ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = args.steps, max(args.warmup, 3)
+    cores = host_cores()
+    from vision_compression_project_b200 import sharding
+
     import torch
     import torch.distributed as dist
     from vision_compression_project_b200 import _native as N
     from vision_compression_project_b200.api import PagePrep
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import vision_compression_project_b200 as V
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    K, W = args.steps, max(args.warmup, 3)
 
-    pages = make_pages(rank * PAGES_PER_GPU, PAGES_PER_GPU)
-    n = len(pages)
-    h, w = pages[0].height, pages[0].width
+    # ---- synthetic pages: drawn by spawned worker processes (FreeType rendering holds the GIL; spawn, not fork, so CUDA in this
+    #      process is no concern), written straight into pinned host memory
+    t_gen = time.perf_counter()
+    fac = PageFactory(max(2, cores // world))
+    n = PAGES_PER_GPU
+    w, h = 1700, 2200
     host = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)          # pinned host copies of the pages
-    for i, im in enumerate(pages):
-        host[i] = torch.from_numpy(np.array(im))
+    arrs = fac.arrays(c2_specs(rank * PAGES_PER_GPU, PAGES_PER_GPU), out=[host[i].numpy() for i in range(n)])
+    c4_lo, c4_hi = sharding.page_range(args.c4_pages, rank, world)
+    c4_arrs, c4_pinned = [], False
+    if args.c4_pages:
+        m4 = c4_hi - c4_lo
+        try:
+            c4_block = torch.empty((m4, h, w, 3), dtype=torch.uint8, pin_memory=True)
+            c4_pinned = True
+        except RuntimeError:                                                       # not enough lockable memory on this box: pageable arrays
+            c4_block = torch.empty((m4, h, w, 3), dtype=torch.uint8)
+        c4_arrs = fac.arrays(c4_specs(c4_lo, c4_hi), out=[c4_block[i].numpy() for i in range(m4)])
+    side = {}
+    if world == 1 and not args.headline_only:
+        side["C3"] = fac.arrays(c3_specs(args.c3_pages))
+        side["C5"] = fac.arrays(c5_specs())
+    fac.close()
+    t_gen = time.perf_counter() - t_gen
+
     dev = host.cuda()
     eng = PagePrep(local)
 
@@ -175,6 +323,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def step_device():
         return eng.run(descs, n, opts, out_p.data_ptr(), cap_p, out_b.data_ptr(), cap_b)
@@ -198,12 +352,7 @@ def run_ours(args):
             if k_.startswith("ms_"):
                 stage[k_] = stage.get(k_, 0.0) + v_
     e1.record(); barrier()
-    t1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step = float(tmax.item()) / K
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / K
     value = world * n / (ms_step / 1e3)
 
     # ---- end to end through the public function: pinned host pages in, Python bytes out
@@ -217,15 +366,10 @@ def run_ours(args):
     for _ in range(Ke):
         outs = eng.prepare_pages(host_np)
     torch.cuda.synchronize()
-    dte = time.perf_counter() - t0e
-    te = torch.tensor([dte], device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_sync = world * n * Ke / float(te.item())           # one synchronous prepare_pages call per step
-    # the same K steps through prepare_stream: up to three steps in flight, so one step's pipeline drains (LZ / Huffman / D2H of its
-    # last pages, ~3 ms with the PCIe link idle) while the next one copies.  Every step still moves its 718 MB in and its bytes out.
-    import vision_compression_project_b200 as V
-    depth = max(1, min(3, host_cores() // (4 * world)))    # host threads are the scarce resource once several ranks share the box
+    e2e_sync = world * n * Ke / max_over_ranks(time.perf_counter() - t0e)       # one synchronous prepare_pages call per step
+    # the same K steps through prepare_stream: several steps in flight, so one step's pipeline drains (LZ / Huffman / D2H of its
+    # last pages with the PCIe link idle) while the next one copies.  Every step still moves its 718 MB in and its bytes out.
+    depth = max(2, min(3, cores // (4 * world)))            # host threads are the scarce resource once several ranks share the box
     for _o in V.prepare_stream((host_np for _ in range(4)), depth=depth, device=local):
         assert all(o.error is None for o in _o)
     barrier()
@@ -236,22 +380,86 @@ def run_ours(args):
     torch.cuda.synchronize()
     dte = time.perf_counter() - t0e
     assert n_done == n * Ke and _o[0].png == outs[0].png and _o[-1].b64 == outs[-1].b64
-    te = torch.tensor([dte], device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_v = world * n * Ke / float(te.item())
+    e2e_v = world * n * Ke / max_over_ranks(dte)
     clocks = sampler.stop(t0, time.perf_counter()) if sampler else None      # both timed regions (device-resident steps and e2e steps)
     e2e_detail = dict(getattr(eng, "last_timing", {}))
     e2e_detail.update({k_: v_ for k_, v_ in eng.stats().items() if k_.startswith("ms_")})
     # the same call with PIL images in (the reference's own input type): Pillow's pixel storage is read in place (pageable memory)
+    pages = [to_pil(a) for a in arrs]
     for _ in range(2):
         outs_pil = eng.prepare_pages(pages)
+    barrier()
     t0p = time.perf_counter()
     Kp = max(1, min(K, 5))
     for _ in range(Kp):
         outs_pil = eng.prepare_pages(pages)
-    e2e_pil = n * Kp / (time.perf_counter() - t0p)
-    assert outs_pil[0].png == outs[0].png
+    e2e_pil = world * n * Kp / max_over_ranks(time.perf_counter() - t0p)
+    assert outs_pil[0].png == outs[0].png and outs_pil[-1].png == outs[-1].png
+    # the reference's calling pattern (pdf_extract.py:313-333): 5 worker threads, each page its own prepare_page(PIL image) call
+    def five_threads(reps):
+        errs = []
+
+        def work(k):
+            try:
+                for r_ in range(reps):
+                    for i in range(k, n, 5):
+                        V.prepare_page(pages[i], device=local)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(5)]
+        t_ = time.perf_counter()
+        [x.start() for x in ths]; [x.join() for x in ths]
+        if errs:
+            raise errs[0]
+        return reps * n / (time.perf_counter() - t_)
+    five_threads(1)
+    barrier()
+    e2e_five = five_threads(2)
+    t_five = torch.tensor([e2e_five], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_five, op=dist.ReduceOp.SUM)                        # independent ranks: rates add
+    e2e_five = float(t_five.item())
+
+    # ---- C4: the 2,000-page document, STRONG scaling — page ranges from sharding.page_range, every rank streams its range through
+    #      prepare_stream (host arrays in, Python bytes out, batches of 64 pages), no exchange between ranks while the document is
+    #      processed; afterwards rank 0 collects the bytes in page order (gather_in_page_order: control plane, timed separately)
+    c4 = None
+    if args.c4_pages:
+        def run_c4():
+            src = c4_arrs
+            batches = [src[i:i + 64] for i in range(0, len(src), 64)]
+            for _o in V.prepare_stream(iter(batches[:2]), depth=depth, device=local):
+                pass
+            best, per_rank, outs4 = None, None, None
+            for _rep in range(2):
+                barrier()
+                t_ = time.perf_counter()
+                outs4 = [o for b_ in V.prepare_stream(iter(batches), depth=depth, device=local) for o in b_]
+                dt_ = time.perf_counter() - t_
+                tt = torch.zeros(world, device="cuda", dtype=torch.float64); tt[rank] = dt_
+                if world > 1:
+                    dist.all_reduce(tt)
+                tmax = float(tt.max().item())
+                if best is None or tmax < best:
+                    best, per_rank = tmax, [round(1e3 * float(x), 1) for x in tt.tolist()]
+            assert len(outs4) == c4_hi - c4_lo and all(o.error is None for o in outs4)
+            rec = {"pages": args.c4_pages, "scaling": "strong", "pages_per_s": args.c4_pages / best, "per_rank_ms": per_rank,
+                   "page_ranges": [list(sharding.page_range(args.c4_pages, r_, world)) for r_ in range(world)],
+                   "host_memory": "pinned" if c4_pinned else "pageable", "api": f"sharding.page_range + prepare_stream(batches of 64, depth={depth}) per rank",
+                   "what": "2,000 letter-200 pages, every 4th photo-heavy, host arrays in -> PNG + base64 bytes on the rank that owns the page "
+                           "(the reference's workers each write their own page file, pdf_extract.py:130); fastest of 2 passes, max over ranks"}
+            if world > 1:
+                t_ = time.perf_counter()
+                allp = sharding.gather_in_page_order([(o.png, o.b64) for o in outs4], c4_lo, args.c4_pages)
+                rec["gather_to_rank0_ms"] = round(1e3 * max_over_ranks(time.perf_counter() - t_), 1)
+                if rank == 0:
+                    assert len(allp) == args.c4_pages and all(p is not None for p in allp) and allp[c4_lo][0] == outs4[0].png
+                    rec["gathered_pages_per_s"] = args.c4_pages / (best + rec["gather_to_rank0_ms"] / 1e3)
+            idx = [0, len(outs4) - 1] if rank == 0 else []
+            rec["png_size_vs_pillow"] = check_against_pillow(outs4, c4_arrs, idx, {}) if idx else None
+            rec["png_bytes_per_page"] = sum(len(o.png) for o in outs4) / max(1, len(outs4))
+            return rec
+        c4 = sub_config("C4", run_c4)
 
     if rank == 0:
         # correctness of what was timed (not timed): first page decodes to the input and base64 matches
@@ -274,13 +482,11 @@ def run_ours(args):
 
         def _pil_dec(b_):
             im_ = Image.open(io.BytesIO(b_)); im_.load(); return im_.size
-        cores_d = host_cores()
-        sample_d = pngs[:max(8, min(n, 2 * cores_d))]
-        with ThreadPoolExecutor(cores_d) as ex:
-            list(ex.map(_pil_dec, sample_d[:cores_d]))
-            t0d = time.perf_counter(); list(ex.map(_pil_dec, sample_d)); dec_cpu = len(sample_d) / (time.perf_counter() - t0d)
-        decode_info = {"value": dec_v, "unit": "pages/s", "batch": n, "what": "vcp_png_decode_batch: this step's PNG bytes (host) -> pixels in HBM, pixel-checked",
-                       "pillow_cpu_pages_per_s": dec_cpu, "cores": cores_d}
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(_pil_dec, pngs[:cores]))
+            t0d = time.perf_counter(); list(ex.map(_pil_dec, pngs)); dec_cpu = len(pngs) / (time.perf_counter() - t0d)
+        decode_info = {"value": dec_v, "unit": "pages/s", "batch": n, "what": "vcp_png_decode_batch: this step's PNG bytes (host) -> pixels in HBM, pixel-checked, Adler-32 verified",
+                       "pillow_cpu_pages_per_s": dec_cpu, "cores": cores}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -292,41 +498,98 @@ def run_ours(args):
         dom = max((k_ for k_ in per if k_ not in ("ms_total", "ms_h2d", "ms_d2h")), key=lambda k_: per[k_])
         dom_ms = per[dom]
         achieved = alg_bytes / (dom_ms / 1e3) / 1e9
-        traffic = None
-        try:                                                              # dram bytes of the dominant kernel from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_lz_traffic.json")))
-            if dom == "ms_lz":
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        except Exception:
-            pass
-        cores = host_cores()
-        sample = max(8, min(n, 2 * cores))
-        cpu_v, cpu_sizes = cpu_path_pages_per_s(pages[:sample], cores, repeats=2)
-        ratio = sum(o and len(o.png) for o in outs[:sample]) / max(1, sum(cpu_sizes))
+        traffic, traffic_src = lz_traffic() if dom == "ms_lz" else (None, "dominant kernel is not k_lz")
+        cpu_v, cpu_sizes = cpu_path_pages_per_s(pages, cores, repeats=2)
+        ratio = sum(len(o.png) for o in outs) / max(1, sum(cpu_sizes))
+
+        # ---- the other BASELINE configs (N = 1 runs): device-resident rate, end-to-end rate, size against Pillow, pixel check
+        configs = {}
+        if world == 1 and not args.headline_only:
+            def run_c1():
+                ref = Image.open(os.path.join(ROOT, "tests", "golden", "ref_page_1.png")); ref.load()
+                a = np.ascontiguousarray(np.asarray(ref))
+                for _ in range(3):
+                    r1 = V.prepare_page(ref)
+                t_ = time.perf_counter()
+                for _ in range(20):
+                    r1 = V.prepare_page(ref)
+                lat_pil = (time.perf_counter() - t_) / 20
+                t_ = time.perf_counter()
+                for _ in range(20):
+                    V.prepare_page(a)
+                lat_np = (time.perf_counter() - t_) / 20
+                dev_rate, dev_ms, st_, _ = device_resident_rate(eng, torch, N, [a], {}, 20)
+                t_ = time.perf_counter()
+                from oracle.pillow_path import prepare_page_cpu
+                for _ in range(3):
+                    prepare_page_cpu(ref)
+                cpu_ms = (time.perf_counter() - t_) / 3 * 1e3
+                return {"workload": "C1: the reference's recorded output/page_1.png (1654x2339 RGB), one prepare_page call", "pages": 1,
+                        "e2e_pages_per_s": 1 / lat_pil, "latency_ms_pil_in": 1e3 * lat_pil, "latency_ms_numpy_in": 1e3 * lat_np,
+                        "device_resident_pages_per_s": dev_rate, "device_ms": dev_ms, "stage_ms": st_,
+                        "pillow_cpu_ms": cpu_ms, "png_bytes": len(r1.png),
+                        "png_size_vs_pillow": check_against_pillow([r1], [a], [0], {})}
+
+            def run_side(label, arrays, kw, workload, cpu_sample):
+                dev_rate, dev_ms, st_, _ = device_resident_rate(eng, torch, N, arrays, kw, 3)
+                pin = pinned_like(torch, arrays)
+                src = pin[:-1] if pin else arrays
+                outs_ = eng.prepare_pages(src, **kw)
+                t_ = time.perf_counter()
+                for _ in range(2):
+                    outs_ = eng.prepare_pages(src, **kw)
+                e2e_ = 2 * len(src) / (time.perf_counter() - t_)
+                assert all(o.error is None for o in outs_)
+                pil_ = [to_pil(a) for a in arrays]
+                eng.prepare_pages(pil_[:8], **kw)
+                t_ = time.perf_counter()
+                outs_p = eng.prepare_pages(pil_, **kw)
+                e2e_p = len(pil_) / (time.perf_counter() - t_)
+                assert outs_p[0].png == outs_[0].png and outs_p[-1].png == outs_[-1].png
+                idx = sorted(set([0, len(arrays) - 1] + list(range(0, len(arrays), max(1, len(arrays) // cpu_sample)))))
+                ratio_ = check_against_pillow(outs_, arrays, idx, kw)
+                cpu_rate, _ = cpu_path_pages_per_s([pil_[i] for i in idx], cores, **kw)
+                return {"workload": workload, "pages": len(arrays), "device_resident_pages_per_s": dev_rate, "device_ms": dev_ms, "stage_ms": st_,
+                        "e2e_pages_per_s": e2e_, "e2e_pil_images_in_pages_per_s": e2e_p, "host_memory": "pinned" if pin else "pageable",
+                        "sizes_out": sorted({o.size for o in outs_})[:4], "png_bytes_per_page": sum(len(o.png) for o in outs_) / len(outs_),
+                        "png_size_vs_pillow": ratio_, "pixel_checked_pages": len(idx),
+                        "pillow_cpu_pages_per_s": cpu_rate, "cpu_sample": f"{len(idx)} of the pages on {cores} threads"}
+            configs["C1"] = sub_config("C1", run_c1)
+            configs["C3"] = sub_config("C3", lambda: run_side(
+                "C3", side["C3"], {"max_side": MAX_SIDE},
+                f"C3: {len(side['C3'])} synthetic letter pages @300 DPI (2550x3300 RGB, every 4th photo-heavy) -> LANCZOS to {MAX_SIDE} px long edge (1212x1568) + PNG + base64", 16))
+            configs["C5"] = sub_config("C5", lambda: run_side(
+                "C5", side["C5"], {"max_side": MAX_SIDE, "reducing_gap": 2.0},
+                f"C5: 48 page types (A4/letter/legal x 150/200/300/600 DPI x L/RGB x text/photo), thumbnail rule to {MAX_SIDE} px with reducing_gap=2.0, convert('RGB') + PNG + base64", 48))
         line = {
             "metric": "pages/sec (resize+PNG+base64)", "value": value, "unit": "pages/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pages_per_gpu": n, "l2": "inputs (718 MB/step) larger than L2, no flush needed",
-                       "png_bytes_per_page": png_bytes / n, "png_size_vs_pillow": ratio},
+            "config": bench_config(),
+            "size": {"png_bytes_per_page": png_bytes / n, "png_size_vs_pillow": ratio, "tolerance": 1.05},
             "e2e": {"value": e2e_v, "unit": "pages/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": png_bytes + b64_bytes,
                     "api": f"prepare_stream(K batches of pinned uint8 arrays, depth={depth}) -> PreparedPage(png bytes, b64 bytes) per page",
                     "single_call_pages_per_s": e2e_sync,
                     "last_step_ms": {k_: round(v_, 3) for k_, v_ in e2e_detail.items()},
-                    "pil_images_in_pages_per_s": e2e_pil},
+                    "pil_images_in_pages_per_s": e2e_pil,
+                    "five_thread_single_page_pages_per_s": e2e_five},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": {"ms_lz": "k_lz", "ms_filter": "k_png_filter", "ms_huff": "k_huff_build/k_layout/k_payload_init/k_huff_emit",
-                                                    "ms_b64": "k_base64_pages", "ms_assemble": "k_png_finish", "ms_convert": "pixel kernels"}.get(dom, dom),
+                                                    "ms_b64": "k_base64_pages", "ms_assemble": "k_png_finish", "ms_convert": "pixel kernels",
+                                                    "ms_resample": "k_resample_h/k_resample_v"}.get(dom, dom),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_own_bytes": in_bytes + int(0.066 * in_bytes),   # k_lz itself: reads the filtered stream once, writes ~0.07 B of tokens per byte
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_own_bytes": int(1.066 * n * h * (1 + 3 * w)),   # k_lz itself: reads the filtered stream once, writes ~0.07 B of tokens per byte
                          "kernel_ms": dom_ms,
                          "stage_ms": per},
             "cpu_baseline": {"value": cpu_v, "unit": "pages/s", "cores": cores, "kind": "reference",
-                             "sample": f"first {sample} pages of the batch, best of 2, Pillow Image.save(PNG)+base64 on {cores} threads"},
+                             "sample": f"all {n} pages of the batch, best of 2, Pillow Image.save(PNG)+base64 on {cores} threads"},
             "decode": decode_info,
+            "configs": configs,
+            "c4": c4,
+            "page_generation_s": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -341,6 +604,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--c3-pages", type=int, default=C3_PAGES, help="pages of the C3 side config (BASELINE: 256)")
+    ap.add_argument("--c4-pages", type=int, default=C4_PAGES, help="pages of the C4 document (BASELINE: 2000; 0 = skip the leg)")
+    ap.add_argument("--headline-only", action="store_true", help="C2 only (profiling runs): no C1/C3/C5 side configs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

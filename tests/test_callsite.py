@@ -152,10 +152,16 @@ def test_reference_call_site_on_the_gpu_path(monkeypatch, tmp_path, fixtures):
     rec_im = Image.open(os.path.join(REC, "page_001.png")); rec_im.load()
     assert page == 1 and parts[0] == mod.EXTRACTION_PROMPT
     assert parts[1] == V.prepare_page(rec_im).inline_data() == {"mime_type": "image/png", "data": png}
-    rec = json.load(open(os.path.join(REC, "page_001.json"), encoding="utf-8"))
-    got = json.load(open(pages / "page_001.json", encoding="utf-8"))
-    want = mod.safe_json_loads(rec["raw_response"])
-    assert got["markdown"] == want["markdown"] and got["summary"] == want["summary"] and got["page_number"] == 1
+    # everything behind the image is untouched: the page JSON is byte for byte what the UNPATCHED reference writes from the same response
+    stubs0 = _Stubs(1)
+    mod0 = _load_call_site(monkeypatch, stubs0, patched=False)
+    images0, pages0 = tmp_path / "images0", tmp_path / "pages0"
+    images0.mkdir(); pages0.mkdir()
+    ok0, err0, _ = mod0._process_single_page(1, tmp_path / "doc.pdf", 200, images0, pages0)
+    assert ok0 and (pages / "page_001.json").read_bytes() == (pages0 / "page_001.json").read_bytes()
+    assert json.load(open(pages / "page_001.json", encoding="utf-8"))["page_number"] == 1
+    for name, m_ in stubs.modules.items():              # the second load swapped the stub modules: put this test's back
+        monkeypatch.setitem(sys.modules, name, m_)
     # ---- the whole document through the reference's 5-thread pool (pdf_extract.py:313-350)
     stats = mod.extract_pdf_to_page_jsons(tmp_path / "doc.pdf", pages, images, dpi=200, overwrite=True)
     assert stats == {"pages_total": 6, "processed_pages": [1, 2, 3, 4, 5, 6], "failed_pages": []}
@@ -167,7 +173,7 @@ def test_reference_call_site_on_the_gpu_path(monkeypatch, tmp_path, fixtures):
     assert sorted(c[0] for c in stubs.calls[1:]) == [1, 2, 3, 4, 5, 6]
     assert all(isinstance(c[1][1], dict) and c[1][1]["mime_type"] == "image/png" for c in stubs.calls)
     # ---- the reference's error convention survives: a page the GPU path rejects becomes a failed page, not an exception
-    stubs.modules["pdf2image"].convert_from_path = lambda *a, **k: [Image.new("CMYK", (8, 8))]
+    mod.convert_from_path = lambda *a, **k: [Image.new("CMYK", (8, 8))]         # (the module bound the name at import)
     ok, err, data = mod._process_single_page(3, tmp_path / "doc.pdf", 200, images, pages, overwrite=True)
     assert not ok and err.startswith("Error converting page 3 to image: ValueError")
 

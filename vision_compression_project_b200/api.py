@@ -537,10 +537,92 @@ def decode_pages(pngs: Sequence[bytes], *, device: int = 0, to_device: bool = Fa
         _pool.give_back(eng)
 
 
+class _Combiner:
+    """Micro-batcher for the reference's calling pattern (SURVEY.md §8 b): `_process_single_page` runs on 5 worker threads and each
+    calls the page body once per page (pdf_extract.py:313-333).  Five one-page launch sets cannot fill a B200, and each pays its own
+    H2D / launch / D2H latency; so while one caller's page is in flight, the pages of the callers that arrive meanwhile are queued
+    here and go out together as ONE launch set (same keyword arguments only).  Nobody ever waits for a batch to fill: a caller that
+    finds the device idle runs its page directly on its own thread, and a worker takes whatever has queued up the moment it is free."""
+
+    WORKERS = 2          # two launch sets in flight: the copy of one overlaps the kernels of the other
+
+    def __init__(self, device: int):
+        import queue
+        self.device = device
+        self.q: "queue.SimpleQueue" = queue.SimpleQueue()
+        self.lock = threading.Lock()
+        self.active = 0                                   # callers inside prepare_page on this device
+        self.threads = [threading.Thread(target=self._work, name=f"vcprep-combiner-{device}-{k}", daemon=True) for k in range(self.WORKERS)]
+        for t in self.threads:
+            t.start()
+
+    def _work(self):
+        import queue
+        while True:
+            items = [self.q.get()]
+            try:
+                while len(items) < 64:
+                    items.append(self.q.get_nowait())
+            except queue.Empty:
+                pass
+            groups: dict = {}
+            for it in items:
+                groups.setdefault(it[1], []).append(it)
+            for key, its in groups.items():
+                try:
+                    res = prepare_pages([it[0] for it in its], device=self.device, **dict(key))
+                    for it, r in zip(its, res):
+                        it[2].append(r); it[3].set()
+                except BaseException as e:  # noqa: BLE001 - handed to the callers
+                    for it in its:
+                        it[2].append(e); it[3].set()
+
+    def submit(self, image, kw) -> "PreparedPage":
+        try:
+            key = tuple(sorted(kw.items()))
+            hash(key)
+        except TypeError:                                 # unhashable keyword value: no batching for this call
+            return prepare_pages([image], device=self.device, **kw)[0]
+        with self.lock:
+            self.active += 1
+            alone = self.active == 1
+        try:
+            if alone:                                     # idle device: no hand-off, the single-page latency stays what it was
+                return prepare_pages([image], device=self.device, **kw)[0]
+            box: list = []
+            done = threading.Event()
+            self.q.put((image, key, box, done))
+            done.wait()
+            if isinstance(box[0], BaseException):
+                raise box[0]
+            return box[0]
+        finally:
+            with self.lock:
+                self.active -= 1
+
+
+_combiners: dict = {}
+_combiners_lock = threading.Lock()
+
+
+def _combiner(device: int) -> _Combiner:
+    c = _combiners.get(device)
+    if c is None:
+        with _combiners_lock:
+            c = _combiners.get(device)
+            if c is None:
+                c = _combiners[device] = _Combiner(device)
+    return c
+
+
 def prepare_page(image: Any, *, device: int = 0, **kw) -> PreparedPage:
     """Single page; raises (ValueError / MemoryError / RuntimeError) like the Pillow calls it replaces, so the
-    reference's per-page try/except (pdf_extract.py:133-136) keeps working."""
-    r = prepare_pages([image], device=device, **kw)[0]
+    reference's per-page try/except (pdf_extract.py:133-136) keeps working.  Concurrent callers (the reference's 5-thread pool)
+    are coalesced into shared launch sets, see _Combiner; VCP_NO_COMBINE=1 gives every call its own launch set."""
+    if os.environ.get("VCP_NO_COMBINE"):
+        r = prepare_pages([image], device=device, **kw)[0]
+    else:
+        r = _combiner(device).submit(image, kw)
     if r.error is not None:
         kind, _, msg = r.error.partition(": ")
         raise {"ValueError": ValueError, "TypeError": TypeError, "MemoryError": MemoryError}.get(kind, RuntimeError)(msg or r.error)

@@ -48,7 +48,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Coeffs { int ksize; std::vector<int32_t> bounds; std::vector<int32_t> kt; };   // kt transposed: [k][out]
 typedef std::tuple<int, int, int, float, float> CoeffKey;
 
-enum { EV_START, EV_H2D, EV_PIXEL, EV_FILTER, EV_LZ, EV_HUFF, EV_ASSEMBLE, EV_B64, EV_D2H, EV_COUNT };
+enum { EV_START, EV_H2D, EV_CONV, EV_PIXEL, EV_FILTER, EV_LZ, EV_HUFF, EV_ASSEMBLE, EV_B64, EV_D2H, EV_COUNT };
 
 }  // namespace
 
@@ -471,6 +471,9 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     if (!stream_in) {
         if (any_conv) launches += launch_convert(B.pages, n, max_sh, max_sw, st);
         if (any_red) launches += launch_reduce(B.pages, n, max_rh, max_rw, st);
+    }
+    CU(cudaEventRecord(L.ev[EV_CONV], st));
+    if (!stream_in) {
         if (any_h) launches += launch_resample_h(B.pages, n, max_resh_rows, max_w, st);
         if (any_v) launches += launch_resample_v(B.pages, n, max_h, max_wc, st);
     }
@@ -523,7 +526,7 @@ int finish_group(vcp_handle* h, GroupOut& out) {
     h->stats.in_bytes += out.in_bytes; h->stats.filtered_bytes += out.filt_bytes;
     float ms = 0;
     auto el = [&](int a, int b) { cudaEventElapsedTime(&ms, L.ev[a], L.ev[b]); return ms; };
-    h->stats.ms_h2d += el(EV_START, EV_H2D); h->stats.ms_convert += el(EV_H2D, EV_PIXEL); h->stats.ms_filter += el(EV_PIXEL, EV_FILTER);
+    h->stats.ms_h2d += el(EV_START, EV_H2D); h->stats.ms_convert += el(EV_H2D, EV_CONV); h->stats.ms_resample += el(EV_CONV, EV_PIXEL); h->stats.ms_filter += el(EV_PIXEL, EV_FILTER);
     h->stats.ms_lz += el(EV_FILTER, EV_LZ); h->stats.ms_huff += el(EV_LZ, EV_HUFF); h->stats.ms_assemble += el(EV_HUFF, EV_ASSEMBLE);
     h->stats.ms_b64 += el(EV_ASSEMBLE, EV_B64);
     return 0;
@@ -776,7 +779,7 @@ int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* 
         if (!rc && l < G) { float ms = 0; if (cudaEventElapsedTime(&ms, L.ev[EV_B64], L.ev[EV_D2H]) == cudaSuccess) h->stats.ms_d2h += ms; }
     }
     if (rc) return rc;
-    h->stats.ms_total = h->stats.ms_h2d + h->stats.ms_convert + h->stats.ms_filter + h->stats.ms_lz + h->stats.ms_huff +
+    h->stats.ms_total = h->stats.ms_h2d + h->stats.ms_convert + h->stats.ms_resample + h->stats.ms_filter + h->stats.ms_lz + h->stats.ms_huff +
                         h->stats.ms_assemble + h->stats.ms_b64 + h->stats.ms_d2h;
     return 0;
 }

@@ -83,3 +83,44 @@ def mixed_page_types():
              for m in ("L", "RGB") for c in (False, True)]
     order = np.random.default_rng(0).permutation(len(types))
     return [types[int(i)] for i in order]
+
+
+# ---------------------------------------------------------------------------------------------- parallel generation
+def _gen_one(spec):
+    """Worker of PageFactory: one page as raw bytes (size, mode, bytes)."""
+    seed, paper, dpi, mode, photo = spec
+    im = make_page(seed, paper, dpi, mode, photo)
+    return im.size, im.mode, im.tobytes()
+
+
+class PageFactory:
+    """Draws pages on `workers` SPAWNED processes: FreeType rendering holds the GIL (threads do not help), and spawn (not fork)
+    keeps it safe to use from a process that already initialised CUDA.  specs = (seed, paper, dpi, mode, photo) tuples."""
+
+    def __init__(self, workers: int):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        self.ex = ProcessPoolExecutor(max(1, workers), mp_context=mp.get_context("spawn"))
+
+    def arrays(self, specs, out=None):
+        """specs -> list of (H, W, 3) / (H, W) uint8 arrays in order; `out` = optional preallocated arrays (e.g. pinned) to fill."""
+        res = []
+        for i, ((w, h), mode, raw) in enumerate(self.ex.map(_gen_one, specs, chunksize=2)):
+            a = np.frombuffer(raw, np.uint8).reshape((h, w, 3) if mode == "RGB" else (h, w))
+            if out is not None:
+                out[i][...] = a
+                a = out[i]
+            res.append(a)
+        return res
+
+    def images(self, specs):
+        return [Image.fromarray(a, "RGB" if a.ndim == 3 else "L") for a in self.arrays(specs)]
+
+    def close(self):
+        self.ex.shutdown(wait=True, cancel_futures=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
