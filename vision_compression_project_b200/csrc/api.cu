@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <immintrin.h>
 #include <condition_variable>
 #include <map>
 #include <memory>
@@ -126,26 +128,123 @@ int ensure_stage(Lane& L, size_t need) {
     return 0;
 }
 
-// copy n byte ranges on T host threads, splitting the total evenly (a page of rows counts as one range per row when strided)
-struct CopyJob { uint8_t* dst; const uint8_t* src; size_t len; };
+// ---- host worker pool.  The byte work the host does per launch set (packing pageable page sources into the pinned bounce buffer,
+// filling the caller's bytes objects) runs on a few persistent threads: spawning 16 threads per 96 MB group cost ~0.5 ms each time.
+// One job at a time (callers queue on job_m); the calling thread works too.  Leaked on purpose: no destructor order at exit.
+class HostPool {
+public:
+    static HostPool& get() { static HostPool* p = new HostPool(); return *p; }
+    // runs fn(0) .. fn(parts - 1), at most `threads` of them at once
+    void run(int parts, int threads, const std::function<void(int)>& fn) {
+        if (parts <= 0) return;
+        threads = std::max(1, std::min({threads, parts, kMaxThreads + 1}));
+        if (threads == 1) { for (int i = 0; i < parts; i++) fn(i); return; }
+        std::lock_guard<std::mutex> job(job_m);
+        grow(threads - 1);
+        {
+            std::lock_guard<std::mutex> g(m);
+            cur = &fn; total = parts; next = 0; pending = parts; helpers = threads - 1; epoch++;
+        }
+        cv_work.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(m);
+        cv_done.wait(g, [&] { return pending == 0; });
+        cur = nullptr;
+    }
+
+private:
+    static constexpr int kMaxThreads = 32;
+    std::mutex job_m, m;
+    std::condition_variable cv_work, cv_done;
+    const std::function<void(int)>* cur = nullptr;
+    int total = 0, next = 0, pending = 0, helpers = 0, nthreads = 0;
+    unsigned long long epoch = 0;
+
+    void grow(int want) {
+        while (nthreads < std::min(want, kMaxThreads)) {
+            const int id = nthreads++;
+            std::thread([this, id] { loop(id); }).detach();
+        }
+    }
+    void work() {
+        for (;;) {
+            int i;
+            const std::function<void(int)>* f;
+            { std::lock_guard<std::mutex> g(m); if (!cur || next >= total) return; i = next++; f = cur; }
+            (*f)(i);
+            { std::lock_guard<std::mutex> g(m); if (--pending == 0) cv_done.notify_all(); }
+        }
+    }
+    void loop(int id) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m);
+                cv_work.wait(g, [&] { return epoch != seen; });
+                seen = epoch;
+                if (id >= helpers) continue;               // this job asked for fewer threads
+            }
+            work();
+        }
+    }
+};
+
+// copy n byte ranges on T host threads, splitting the total evenly (a page of rows counts as one range per row when strided).
+// drop4 ranges are RGBX / RGBA pixels (Pillow's 4-byte storage of RGB images) of which only the first three bytes of every pixel are
+// wanted: len counts SOURCE bytes (a multiple of 4), the destination receives 3/4 of them.
+struct CopyJob { uint8_t* dst; const uint8_t* src; size_t len; bool drop4; };
+
+__attribute__((target("ssse3"))) void pack_rgbx_ssse3(uint8_t* d, const uint8_t* s, size_t npix) {
+    const __m128i sh = _mm_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1);
+    size_t i = 0;
+    const bool aligned = ((uintptr_t)d & 15) == 0;
+    for (; i + 16 <= npix; i += 16) {                         // 64 source bytes -> 48
+        const __m128i a = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(s + 4 * i)), sh);
+        const __m128i b = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(s + 4 * i + 16)), sh);
+        const __m128i c = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(s + 4 * i + 32)), sh);
+        const __m128i e = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(s + 4 * i + 48)), sh);
+        const __m128i o0 = _mm_or_si128(a, _mm_slli_si128(b, 12));
+        const __m128i o1 = _mm_or_si128(_mm_srli_si128(b, 4), _mm_slli_si128(c, 8));
+        const __m128i o2 = _mm_or_si128(_mm_srli_si128(c, 8), _mm_slli_si128(e, 4));
+        __m128i* o = (__m128i*)(d + 3 * i);
+        if (aligned) { _mm_stream_si128(o, o0); _mm_stream_si128(o + 1, o1); _mm_stream_si128(o + 2, o2); }   // the bounce buffer is read next by the DMA engine, not by this core
+        else { _mm_storeu_si128(o, o0); _mm_storeu_si128(o + 1, o1); _mm_storeu_si128(o + 2, o2); }
+    }
+    for (; i < npix; i++) { d[3 * i] = s[4 * i]; d[3 * i + 1] = s[4 * i + 1]; d[3 * i + 2] = s[4 * i + 2]; }
+    if (aligned) _mm_sfence();
+}
+
+void pack_rgbx(uint8_t* d, const uint8_t* s, size_t npix) {
+    static const bool has = __builtin_cpu_supports("ssse3");
+    if (has) { pack_rgbx_ssse3(d, s, npix); return; }
+    for (size_t i = 0; i < npix; i++) { d[3 * i] = s[4 * i]; d[3 * i + 1] = s[4 * i + 1]; d[3 * i + 2] = s[4 * i + 2]; }
+}
+
 void parallel_copy(const std::vector<CopyJob>& jobs, int T) {
     size_t total = 0;
     for (auto& j : jobs) total += j.len;
     T = std::max(1, std::min(T, 16));
-    if (T == 1 || total < ((size_t)1 << 20)) { for (auto& j : jobs) memcpy(j.dst, j.src, j.len); return; }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < T; t++) {
+    if (total < ((size_t)1 << 20)) T = 1;
+    // part t takes the source bytes [t * total / T, (t + 1) * total / T) of the concatenation, cut on 64-byte (16-pixel) boundaries
+    // of each range so that packed pixels never straddle two parts
+    HostPool::get().run(T, T, [&jobs, total, T](int t) {
         const size_t lo = total * t / T, hi = total * (t + 1) / T;
-        pool.emplace_back([&jobs, lo, hi]() {
-            size_t pos = 0;
-            for (size_t i = 0; i < jobs.size() && pos < hi; i++) {
-                const size_t a = std::max(lo, pos), b = std::min(hi, pos + jobs[i].len);
-                if (a < b) memcpy(jobs[i].dst + (a - pos), jobs[i].src + (a - pos), b - a);
-                pos += jobs[i].len;
+        size_t pos = 0;
+        for (size_t i = 0; i < jobs.size() && pos < hi; i++) {
+            const CopyJob& j = jobs[i];
+            size_t a = std::max(lo, pos) - pos, b = std::min(hi, pos + j.len) - pos;
+            if (std::max(lo, pos) < std::min(hi, pos + j.len)) {
+                if (a) a = (a + 63) & ~(size_t)63;
+                if (b < j.len) b = (b + 63) & ~(size_t)63;
+                a = std::min(a, j.len); b = std::min(b, j.len);
+                if (a < b) {
+                    if (j.drop4) pack_rgbx(j.dst + a / 4 * 3, j.src + a, (b - a) / 4);
+                    else memcpy(j.dst + a, j.src + a, b - a);
+                }
             }
-        });
-    }
-    for (auto& th : pool) th.join();
+            pos += j.len;
+        }
+    });
 }
 
 typedef std::shared_ptr<const Coeffs> CoeffRef;
@@ -179,6 +278,8 @@ struct PagePlan {
     const uint8_t* src = nullptr; int64_t src_stride = 0;
     int sw = 0, sh = 0, sc = 0, c = 0, pc = 0, fx = 1, fy = 1, rw = 0, rh = 0, w = 0, h = 0;
     bool need_conv = false, need_red = false, need_h = false, need_v = false;
+    bool staged = false;     // host source in pageable memory: packed into the lane's pinned bounce buffer by host threads
+    int dsc = 0;             // channels of the page as it arrives on the device (3 when the host pack dropped the X of RGBX storage)
     float box[4] = {0, 0, 0, 0};
     size_t o_raw = kNone, o_conv = kNone, o_red = kNone, o_tmp = kNone, o_vout = kNone, o_filt = kNone;
     size_t o_hb = kNone, o_hk = kNone, o_vb = kNone, o_vk = kNone;
@@ -265,8 +366,20 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     auto put_coeff = [&](const std::vector<int32_t>& v) { const size_t o2 = coeff_blob.size(); coeff_blob.insert(coeff_blob.end(), v.begin(), v.end()); return o2; };
     std::map<const Coeffs*, std::pair<size_t, size_t>> coeff_at;   // -> (bounds idx, kt idx) in coeff_blob; the plans' references keep the keys alive
     for (auto& P : plans) {
+        P.dsc = P.sc;
+        if (!stream_in && !o.src_device) {
+            // Pinned (or registered) sources are DMA'd where they lie.  Pageable ones — e.g. Pillow's own pixel storage — would make
+            // cudaMemcpyAsync stage them on one thread at ~11 GB/s: host threads pack them into the lane's pinned bounce buffer instead
+            // (the previous group's DMA and kernels run meanwhile).  Pillow keeps RGB images as 4-byte RGBX pixels: the pack drops
+            // the X there and then (3/4 of the bytes cross PCIe, and the convert kernel has nothing left to do).
+            cudaPointerAttributes at;
+            const bool pinned = cudaPointerGetAttributes(&at, P.src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+            cudaGetLastError();
+            P.staged = !pinned;
+            if (P.staged && P.sc == 4 && P.c == 3) { P.dsc = 3; P.need_conv = false; }
+        }
         if (!stream_in) {
-            if (!o.src_device) P.o_raw = bump.take((size_t)P.sw * P.sc * P.sh + 16);
+            if (!o.src_device) P.o_raw = bump.take((size_t)P.sw * P.dsc * P.sh + 16);
             if (P.need_conv) P.o_conv = bump.take((size_t)P.sw * P.sh * P.pc + 16);
             if (P.need_red) P.o_red = bump.take((size_t)P.rw * P.rh * P.pc + 16);
             if (P.need_h) P.o_tmp = bump.take(align_up((size_t)P.w * P.pc, 16) * P.rh + 16);      // rows padded to 16 B: aligned word loads in the V pass
@@ -346,12 +459,12 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     for (int i = 0; i < n; i++) {
         PagePlan& P = plans[i];
         PageD& D = hp[i];
-        D.sw = P.sw; D.sh = P.sh; D.sc = P.sc; D.c = P.c; D.pc = P.pc; D.fx = P.fx; D.fy = P.fy; D.rw = P.rw; D.rh = P.rh; D.w = P.w; D.h = P.h;
+        D.sw = P.sw; D.sh = P.sh; D.sc = P.dsc; D.c = P.c; D.pc = P.pc; D.fx = P.fx; D.fy = P.fy; D.rw = P.rw; D.rh = P.rh; D.w = P.w; D.h = P.h;
         D.color_type = color_type_of(P.c);
         const uint8_t* cur = nullptr; int64_t cur_stride = 0;
         if (!stream_in) {
             if (o.src_device) { cur = P.src; cur_stride = P.src_stride; }
-            else { cur = A + P.o_raw; cur_stride = (int64_t)P.sw * P.sc; }
+            else { cur = A + P.o_raw; cur_stride = (int64_t)P.sw * P.dsc; }
             D.src = cur; D.src_stride = cur_stride;
             if (P.need_conv) { D.conv = A + P.o_conv; cur = D.conv; cur_stride = (int64_t)P.sw * P.pc; any_conv = true; }
             D.rdin = cur; D.rdin_stride = cur_stride;
@@ -429,35 +542,28 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     CU(cudaMemcpyAsync(A + o_coeff, M, desc_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(R, 0, (o_cnt + 1024) - o_res, st));
     if (!stream_in && !o.src_device) {
-        // Pinned (or registered) sources are DMA'd where they lie.  Pageable ones — e.g. Pillow's own pixel storage — would make
-        // cudaMemcpyAsync stage them on one thread at ~11 GB/s: pack them into the lane's pinned bounce buffer on several host
-        // threads instead (the previous group's DMA and kernels run meanwhile) and DMA from there.
         std::vector<CopyJob> jobs;
         std::vector<size_t> stage_off(n, kNone);
         size_t stage_need = 0;
-        for (int i = 0; i < n; i++) {
-            cudaPointerAttributes at;
-            const bool pinned = cudaPointerGetAttributes(&at, plans[i].src) == cudaSuccess &&
-                                (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
-            cudaGetLastError();
-            if (!pinned) { stage_off[i] = stage_need; stage_need += align_up((size_t)plans[i].sw * plans[i].sc * plans[i].sh, 256); }
-        }
+        for (int i = 0; i < n; i++)
+            if (plans[i].staged) { stage_off[i] = stage_need; stage_need += align_up((size_t)plans[i].sw * plans[i].dsc * plans[i].sh, 256); }
         if (stage_need) {
             rc = ensure_stage(L, stage_need);
             if (rc) return rc;
             for (int i = 0; i < n; i++) {
                 if (stage_off[i] == kNone) continue;
                 const PagePlan& P = plans[i];
-                const size_t rowb = (size_t)P.sw * P.sc;
+                const size_t srow = (size_t)P.sw * P.sc, drow = (size_t)P.sw * P.dsc;
+                const bool drop4 = P.dsc != P.sc;
                 uint8_t* d = L.stage + stage_off[i];
-                if ((size_t)P.src_stride == rowb) jobs.push_back({d, P.src, rowb * P.sh});
-                else for (int y = 0; y < P.sh; y++) jobs.push_back({d + (size_t)y * rowb, P.src + (size_t)y * P.src_stride, rowb});
+                if ((size_t)P.src_stride == srow) jobs.push_back({d, P.src, srow * P.sh, drop4});
+                else for (int y = 0; y < P.sh; y++) jobs.push_back({d + (size_t)y * drow, P.src + (size_t)y * P.src_stride, srow, drop4});
             }
             parallel_copy(jobs, h->copy_threads);
         }
         for (int i = 0; i < n; i++) {
             const PagePlan& P = plans[i];
-            const size_t rowb = (size_t)P.sw * P.sc;
+            const size_t rowb = (size_t)P.sw * P.dsc;
             if (stage_off[i] != kNone) CU(cudaMemcpyAsync(A + P.o_raw, L.stage + stage_off[i], rowb * P.sh, cudaMemcpyHostToDevice, st));
             else if ((size_t)P.src_stride == rowb) CU(cudaMemcpyAsync(A + P.o_raw, P.src, rowb * P.sh, cudaMemcpyHostToDevice, st));
             else CU(cudaMemcpy2DAsync(A + P.o_raw, rowb, P.src, (size_t)P.src_stride, rowb, (size_t)P.sh, cudaMemcpyHostToDevice, st));
@@ -1037,7 +1143,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             DecPageD& D = dp[i0 + j];
             if (D.status) continue;
             size_t o = s_z[j];
-            for (auto& c : idats[i0 + j]) { jobs.push_back({L.stage + o, c.p, c.n}); o += c.n; }
+            for (auto& c : idats[i0 + j]) { jobs.push_back({L.stage + o, c.p, c.n, false}); o += c.n; }
             D.z = A + o_zreg + s_z[j]; D.filt = A + o_f[j];
             D.pix = direct ? (uint8_t*)out_pixels + G.pix_base + (o_p[j] - o_preg) : A + o_p[j];
             D.sym = reinterpret_cast<uint16_t*>(A + o_s[j]);
@@ -1145,20 +1251,16 @@ int vcp_host_scatter(const void* src_base, const uint64_t* offs, const uint64_t*
         for (int i = 0; i < n; i++) if (lens[i]) memcpy(dsts[i], base + offs[i], (size_t)lens[i]);
         return 0;
     }
-    // split the total byte count evenly: thread t copies the byte interval [t*total/T, (t+1)*total/T) of the concatenation
-    std::vector<std::thread> pool;
-    for (int t = 0; t < T; t++) {
+    // split the total byte count evenly: part t copies the byte interval [t*total/T, (t+1)*total/T) of the concatenation
+    HostPool::get().run(T, T, [=](int t) {
         const uint64_t lo = total * t / T, hi = total * (t + 1) / T;
-        pool.emplace_back([=]() {
-            uint64_t pos = 0;
-            for (int i = 0; i < n && pos < hi; i++) {
-                const uint64_t a = std::max(lo, pos), b = std::min(hi, pos + lens[i]);
-                if (a < b) memcpy((uint8_t*)dsts[i] + (a - pos), base + offs[i] + (a - pos), (size_t)(b - a));
-                pos += lens[i];
-            }
-        });
-    }
-    for (auto& th : pool) th.join();
+        uint64_t pos = 0;
+        for (int i = 0; i < n && pos < hi; i++) {
+            const uint64_t a = std::max(lo, pos), b = std::min(hi, pos + lens[i]);
+            if (a < b) memcpy((uint8_t*)dsts[i] + (a - pos), base + offs[i] + (a - pos), (size_t)(b - a));
+            pos += lens[i];
+        }
+    });
     return 0;
 }
 

@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
     int status = INF_OK;
     const unsigned long long start_bit = S.start_bit;
     seek_bit(M, br, filled, start_bit);
-    const unsigned long long cap = P.filt_len;
+    const unsigned long long cap = P.filt_len, nbits = P.zlen * 8ull;
     unsigned long long pos = 0;                         // output bytes so far
     // interval being built (lane 0)
     unsigned long long iv_hdr = start_bit, iv_start = start_bit, iv_out = 0, next_ck = kCkpt;
@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
         if (lane == 0) hdr_bit = br.bits_used();
         int btype = 0, slen = 0; unsigned long long ssrc = 0;
         status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
+        if (__shfl_sync(kFull, br.bits_used(), 0) > nbits) status = INF_SHORT;   // the header runs past the end of the data (bits behind it are not the stream's)
         if (status != INF_OK) break;
         if (btype == 0) {
             pos += slen;
@@ -558,13 +559,16 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
                     ring_window(M, br, B + lane, &w0, &w1);
                     spec_decode<false>(M, w0, w1, &info, &tok);
                     int o = 0;
+                    const bool near_end = B + 2048ull > nbits;                // a round eats < 2048 bits: only the last ones look at the end
                     while (o < 32) {
                         uint32_t inf = __shfl_sync(kFull, info, o);
-                        if (inf & (SP_SLOW | SP_BAD | SP_EOB)) {              // the common token pays one test for all three
+                        if ((inf & (SP_SLOW | SP_BAD | SP_EOB)) || near_end) {    // the common token pays one test for all of these
                             if (inf & SP_SLOW) {
                                 if (lane == o) spec_decode<true>(M, w0, w1, &info, &tok);
                                 inf = __shfl_sync(kFull, info, o);
                             }
+                            // a code cut off by the end of the data is no code (the bits behind the data are not the stream's)
+                            if (near_end && B + o + ((inf & SP_BAD) ? 48u : (inf & 63u)) > nbits) { status = INF_SHORT; break; }
                             if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
                             if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
                         }
@@ -727,7 +731,7 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
     uint32_t filled = 0;
     seek_bit(M, br, filled, I.hdr_bit);
     uint16_t* __restrict__ out = P.sym + I.out;
-    const unsigned long long abs0 = I.out;
+    const unsigned long long abs0 = I.out, nbits = P.zlen * 8ull;
     const uint32_t target = I.len;
     uint32_t pos = 0;
     int status = INF_OK, last = 0;
@@ -778,13 +782,15 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
                 ring_window(M, br, B + lane, &x0, &x1);
                 spec_decode<false>(M, x0, x1, &info, &tok);
                 int o = 0;
+                const bool near_end = B + 2048ull > nbits;
                 while (o < 32 && ntok < 32 && room > 0) {
                     uint32_t inf = __shfl_sync(kFull, info, o);
-                    if (inf & (SP_SLOW | SP_BAD | SP_EOB)) {
+                    if ((inf & (SP_SLOW | SP_BAD | SP_EOB)) || near_end) {
                         if (inf & SP_SLOW) {
                             if (lane == o) spec_decode<true>(M, x0, x1, &info, &tok);
                             inf = __shfl_sync(kFull, info, o);
                         }
+                        if (near_end && B + o + ((inf & SP_BAD) ? 48u : (inf & 63u)) > nbits) { status = INF_SHORT; break; }
                         if (inf & SP_BAD) { status = INF_BAD_CODE; break; }
                         if (inf & SP_EOB) { o += (int)(inf & 63u); eob = true; break; }
                     }
