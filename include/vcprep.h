@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VCP_VERSION 100
+#define VCP_VERSION 101
 
 #define VCP_OK            0
 #define VCP_EINVAL       -1   /* bad argument / unsupported mode or size   (Python: ValueError)   */
@@ -53,6 +53,9 @@ typedef struct {
     int32_t dst_height;
     int32_t reduce_x;       /* Image.reduce factors applied before the resample (thumbnail's         */
     int32_t reduce_y;       /* reducing_gap step); 0 or 1 = none                                     */
+    const void* const* row_ptrs;  /* optional (host sources only): `height` row pointers, row y = row_ptrs[y], for images whose
+                                     rows do not lie at one stride — Pillow keeps images above 16 MB in several blocks
+                                     (libImaging/Storage.c) and addresses them through exactly such a table; NULL = src + y*row_stride */
 } vcp_page_desc;
 
 typedef struct {

@@ -150,3 +150,29 @@ def test_host_scatter_fills_fresh_bytes(lib):
         out = N.gather_bytes(src.ctypes.data, ranges, threads)
         assert all(type(o) is bytes and o == src[a:a + n].tobytes() for o, (a, n) in zip(out, ranges))
     assert N.gather_bytes(src.ctypes.data, [], 4) == []
+
+
+def test_pillow_row_table_reads_the_real_pixels():
+    """PIL images above Pillow's 16 MB block size live in several blocks; api._pil_row_table finds libImaging's row-pointer table
+    (validated, not assumed).  Every row read through it must be the image's row — checked here on the CPU for multi-block and
+    single-block images of every storage kind; a layout that is not recognised must give None, never a wrong table."""
+    import ctypes as C
+    import numpy as np
+    from PIL import Image
+    from vision_compression_project_b200 import api
+    rng = np.random.default_rng(4)
+    for mode, (w, h) in (("RGB", (2550, 3300)), ("L", (5100, 4000)), ("RGBA", (2300, 2100)), ("RGB", (64, 48)), ("L", (33, 7))):
+        bands = len(mode)
+        a = rng.integers(0, 256, (h, w, bands), dtype=np.uint8)
+        im = Image.fromarray(a[:, :, 0] if bands == 1 else a, mode)
+        rt = api._pil_row_table(im)
+        assert rt is not None, (mode, w, h)
+        keep, table, px = rt
+        rows = (C.c_void_p * h).from_address(table)
+        for y in (0, 1, h // 3, h // 2, h - 2, h - 1):
+            raw = np.frombuffer((C.c_ubyte * (w * px)).from_address(rows[y]), np.uint8).reshape(w, px)
+            assert np.array_equal(raw[:, :bands], a[y].reshape(w, bands)), (mode, y)
+        src = api._as_source(im, None)
+        assert (src.row_ptrs is not None) == (api._pil_zero_copy(im) is None) and src.logical_c == bands
+    assert api._pil_row_table(Image.new("CMYK", (8, 8))) is None
+    assert api._pil_row_table(Image.new("LA", (8, 8))) is None

@@ -128,6 +128,25 @@ def test_input_kinds_agree(V, synth):
     assert V.prepare_page(pgm, mode="L").png == V.prepare_page(g, mode="L").png
 
 
+def test_multi_block_pil_images_are_read_through_the_row_table(V, synth):
+    """Pillow keeps images above 16 MB in several memory blocks (every 300-DPI page): they are read in place through libImaging's
+    row-pointer table (vcp_page_desc.row_ptrs) — same bytes as the packed numpy copy of the same pixels, RGB, RGBA-kept and L."""
+    big = synth.make_page(9, "letter", 300, photo=True)                       # 2550x3300 RGB: 33.7 MB of RGBX storage, 3 blocks
+    gray = synth.make_page(10, "a4", 300, "L")                                # one block
+    wide = Image.fromarray(np.random.default_rng(3).integers(0, 256, (4200, 5100), dtype=np.uint8), "L")   # 21 MB of L storage, 2 blocks
+    rgba = Image.merge("RGBA", (*big.split(), big.convert("L")))
+    from vision_compression_project_b200 import api
+    assert api._as_source(big, None).row_ptrs is not None and api._as_source(wide, None).row_ptrs is not None
+    for im, kw in ((big, {}), (big, {"max_side": 1568}), (wide, {"mode": "L"}), (rgba, {"mode": None}), (rgba, {}), (gray, {})):
+        a = np.ascontiguousarray(np.asarray(im))
+        got, ref = V.prepare_page(im, **kw), V.prepare_page(a, **kw)
+        assert got.png == ref.png and got.mode == ref.mode and got.size == ref.size, (im.mode, kw)
+    res = V.prepare_pages([big, gray, big, wide], max_side=1568)              # mixed in one call
+    assert [r.error for r in res] == [None] * 4 and res[0].png == res[2].png
+    _, _, exp = PP.prepare_page_cpu(big, max_side=1568)
+    U.check_png_against(res[0].png, exp)
+
+
 def test_errors_and_partial_batch(V, synth):
     good = synth.make_page(1, size=(300, 200))
     with pytest.raises(ValueError):

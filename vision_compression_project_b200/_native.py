@@ -13,7 +13,7 @@ VCP_OK, VCP_EINVAL, VCP_ECUDA, VCP_ENOMEM, VCP_ESIZE = 0, -1, -2, -3, -4
 class PageDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
                 ("row_stride", C.c_int64), ("dst_width", C.c_int32), ("dst_height", C.c_int32),
-                ("reduce_x", C.c_int32), ("reduce_y", C.c_int32)]
+                ("reduce_x", C.c_int32), ("reduce_y", C.c_int32), ("row_ptrs", C.c_void_p)]
 
 
 class Opts(C.Structure):

@@ -132,11 +132,12 @@ def split_pnm_stream(data) -> list:
 
 
 class _Source:
-    __slots__ = ("keep", "ptr", "w", "h", "c", "stride", "device", "logical_c")
+    __slots__ = ("keep", "ptr", "w", "h", "c", "stride", "device", "logical_c", "row_ptrs")
 
     def __init__(self, keep, ptr, w, h, c, stride, device, logical_c=None):
         self.keep, self.ptr, self.w, self.h, self.c, self.stride, self.device = keep, ptr, w, h, c, stride, device
         self.logical_c = c if logical_c is None else logical_c      # channels of the image's mode (RGB is stored RGBX by Pillow)
+        self.row_ptrs = None                                        # address of a table of h row pointers (Pillow's multi-block images)
 
 
 class _ArrowArray(C.Structure):
@@ -179,6 +180,53 @@ def _pil_zero_copy(image):
     return (image, schema, array), child.buffers[1], 4
 
 
+_capsule_name = C.pythonapi.PyCapsule_GetName
+_capsule_name.restype = C.c_char_p
+_capsule_name.argtypes = [C.py_object]
+
+
+def _pil_row_table(image):
+    """Images Pillow keeps in several blocks (above 16 MB of storage: 300-DPI pages and up) cannot be exported in one piece, but
+    libImaging itself addresses every image through a table of row pointers (`char **image` of ImagingMemoryInstance, Imaging.h).
+    Its address is read from the core object's capsule; the struct layout is not assumed but recognised — the (bands, xsize, ysize)
+    triple must be found, the three row-table pointers must agree with the mode, pixelsize / linesize must fit, and the first pixel
+    must read back as getpixel((0, 0)) — otherwise None (the packed-copy path takes over).
+    Returns (keepalive, address of the row table, storage channels)."""
+    if image.mode not in ("RGB", "RGBA", "L"):
+        return None
+    try:
+        image.load()
+        core = image.im
+        cap = core.ptr
+        if _capsule_name(cap) != b"Pillow Imaging":
+            return None
+        base = _capsule_ptr(cap, b"Pillow Imaging")
+        w, h = image.size
+        bands = {"L": 1, "RGB": 3, "RGBA": 4}[image.mode]
+        px = 1 if image.mode == "L" else 4
+        ints = (C.c_int32 * 16).from_address(base)
+        k = next((i for i in range(1, 12) if ints[i] == w and ints[i + 1] == h and ints[i - 1] == bands), None)
+        if k is None:
+            return None
+        off = ((k + 2) * 4 + 7) & ~7                        # palette, image8, image32, image, block, blocks, then pixelsize, linesize
+        ptrs = (C.c_void_p * 6).from_address(base + off)
+        table = ptrs[3]
+        pixelsize, linesize = (C.c_int32 * 2).from_address(base + off + 48)
+        if not table or table != (ptrs[1] if px == 1 else ptrs[2]) or (ptrs[2] if px == 1 else ptrs[1]) or pixelsize != px or linesize < w * px:
+            return None
+        rows = (C.c_void_p * h).from_address(table)
+        if not rows[0] or (h > 1 and rows[1] - rows[0] != linesize):
+            return None
+        first = bytes((C.c_ubyte * px).from_address(rows[0]))
+        want = image.getpixel((0, 0))
+        want = bytes([want]) if px == 1 else bytes(want) + (b"" if len(want) == 4 else first[3:4])
+        if first != want:
+            return None
+        return (image, core, cap), table, px
+    except Exception:
+        return None
+
+
 def _as_source(image: Any, raw_shape) -> _Source:
     if _PILImage is not None and isinstance(image, _PILImage.Image):
         if image.mode not in _MODE_CH:
@@ -187,6 +235,12 @@ def _as_source(image: Any, raw_shape) -> _Source:
         if zc is not None:
             keep, addr, sc = zc
             return _Source(keep, addr, image.width, image.height, sc, image.width * sc, False, _MODE_CH[image.mode])
+        rt = _pil_row_table(image)
+        if rt is not None:
+            keep, table, sc = rt
+            src = _Source(keep, 0, image.width, image.height, sc, image.width * sc, False, _MODE_CH[image.mode])
+            src.row_ptrs = table
+            return src
         arr = np.asarray(image)                              # packs Pillow's RGBX storage to interleaved bytes
         if not arr.flags.c_contiguous:
             arr = np.ascontiguousarray(arr)
@@ -340,6 +394,7 @@ class PagePrep:
     def _plan(src: _Source, size, max_side, mode, resample, reducing_gap) -> N.PageDesc:
         d = N.PageDesc()
         d.src, d.width, d.height, d.channels, d.row_stride = src.ptr, src.w, src.h, src.c, src.stride
+        d.row_ptrs = src.row_ptrs
         target = None
         if size is not None:
             target = (int(size[0]), int(size[1]))

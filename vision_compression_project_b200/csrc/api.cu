@@ -276,6 +276,7 @@ constexpr size_t kNone = (size_t)-1;
 struct PagePlan {
     int status = 0;
     const uint8_t* src = nullptr; int64_t src_stride = 0;
+    const uint8_t* const* row_ptrs = nullptr;      // host source addressed through a row table (Pillow's multi-block images)
     int sw = 0, sh = 0, sc = 0, c = 0, pc = 0, fx = 1, fy = 1, rw = 0, rh = 0, w = 0, h = 0;
     bool need_conv = false, need_red = false, need_h = false, need_v = false;
     bool staged = false;     // host source in pageable memory: packed into the lane's pinned bounce buffer by host threads
@@ -298,12 +299,15 @@ int color_type_of(int c) { return c == 1 ? 0 : c == 2 ? 4 : c == 3 ? 2 : 6; }
 
 // geometry + validation of one page; no allocation
 int plan_geometry(const vcp_page_desc& d, const vcp_opts& o, PagePlan& P) {
-    if (!d.src) return fail(VCP_EINVAL, "page src is NULL");
+    if (!d.src && !d.row_ptrs) return fail(VCP_EINVAL, "page src is NULL");
+    if (d.row_ptrs && o.src_device) return fail(VCP_EINVAL, "row_ptrs describes host memory; device pages are strided");
     if (d.width <= 0 || d.height <= 0) return fail(VCP_EINVAL, "bad page size %dx%d", d.width, d.height);
     if (d.channels < 1 || d.channels > 4) return fail(VCP_EINVAL, "unsupported channel count %d (1=L 2=LA 3=RGB 4=RGBA)", d.channels);
     if ((int64_t)d.width * d.channels > (1 << 20)) return fail(VCP_EINVAL, "page too wide (%d px)", d.width);
     if (d.height > (1 << 20)) return fail(VCP_EINVAL, "page too tall (%d px)", d.height);
     P.src = (const uint8_t*)d.src; P.sw = d.width; P.sh = d.height; P.sc = d.channels;
+    P.row_ptrs = (const uint8_t* const*)d.row_ptrs;
+    if (P.row_ptrs) P.src = P.row_ptrs[0];
     P.src_stride = d.row_stride ? d.row_stride : (int64_t)d.width * d.channels;
     if (P.src_stride < (int64_t)d.width * d.channels) return fail(VCP_EINVAL, "row_stride %lld smaller than a row", (long long)d.row_stride);
     P.c = o.out_channels ? o.out_channels : d.channels;
@@ -373,7 +377,8 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
             // (the previous group's DMA and kernels run meanwhile).  Pillow keeps RGB images as 4-byte RGBX pixels: the pack drops
             // the X there and then (3/4 of the bytes cross PCIe, and the convert kernel has nothing left to do).
             cudaPointerAttributes at;
-            const bool pinned = cudaPointerGetAttributes(&at, P.src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+            const bool pinned = !P.row_ptrs && cudaPointerGetAttributes(&at, P.src) == cudaSuccess &&
+                                (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
             cudaGetLastError();
             P.staged = !pinned;
             if (P.staged && P.sc == 4 && P.c == 3) { P.dsc = 3; P.need_conv = false; }
@@ -556,7 +561,15 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
                 const size_t srow = (size_t)P.sw * P.sc, drow = (size_t)P.sw * P.dsc;
                 const bool drop4 = P.dsc != P.sc;
                 uint8_t* d = L.stage + stage_off[i];
-                if ((size_t)P.src_stride == srow) jobs.push_back({d, P.src, srow * P.sh, drop4});
+                if (P.row_ptrs) {
+                    // a row table: consecutive rows that happen to lie back to back (all rows of one Pillow block) go as one range
+                    for (int y = 0; y < P.sh;) {
+                        int y1 = y + 1;
+                        while (y1 < P.sh && P.row_ptrs[y1] == P.row_ptrs[y1 - 1] + srow) y1++;
+                        jobs.push_back({d + (size_t)y * drow, P.row_ptrs[y], srow * (size_t)(y1 - y), drop4});
+                        y = y1;
+                    }
+                } else if ((size_t)P.src_stride == srow) jobs.push_back({d, P.src, srow * P.sh, drop4});
                 else for (int y = 0; y < P.sh; y++) jobs.push_back({d + (size_t)y * drow, P.src + (size_t)y * P.src_stride, srow, drop4});
             }
             parallel_copy(jobs, h->copy_threads);
