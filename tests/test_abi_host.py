@@ -36,7 +36,8 @@ def test_library_exports_every_declared_symbol(lib):
     out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (vcp_[a-z0-9_]+)", out))
     assert set(declared) <= exported, sorted(set(declared) - exported)
-    assert lib.vcp_version() == 100
+    header = open(os.path.join(ROOT, "include", "vcprep.h")).read()
+    assert lib.vcp_version() == int(re.search(r"#define VCP_VERSION (\d+)", header).group(1)) == 101
 
 
 def test_library_is_sm100a_only():
