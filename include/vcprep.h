@@ -156,7 +156,10 @@ int vcp_png_filter(vcp_handle* h, const void* d_pix, int width, int height, int 
 int vcp_deflate(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, int level,
                 void* d_out, uint64_t cap, uint64_t* out_len);
 /* LZ77 token stream of the deflate (test hook; compared against tests/model/deflate_model.c).
- * d_tokens: len uint32; sub_ntok: ceil(len/32768) uint32 (host). Tokens of sub-chunk j start at j*32768. */
+ * The stream is cut into deflate blocks of 512 KiB and those into sub-chunks of vcp_lz_sub_bytes() (one warp each).
+ * d_tokens: len uint32, the tokens of a sub-chunk lie compact from its first byte position; sub_ntok_host: one uint32 per
+ * sub-chunk; sub_hist_host: 316 per sub-chunk or NULL. */
+int vcp_lz_sub_bytes(void);
 int vcp_lz_tokens(vcp_handle* h, const void* d_stream, uint64_t len, int bpp,
                   uint32_t* d_tokens, uint32_t* sub_ntok_host, uint32_t* sub_hist_host /* nsub*316 or NULL */);
 int vcp_adler32(vcp_handle* h, const void* d_data, uint64_t len, uint32_t* out);

@@ -104,18 +104,19 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
        highest lane of each hash group writes, and for ways>1 it shifts the bucket ONCE. */
     int64_t hs = s - P->prime_bytes; if (hs < 0) hs = 0;
     if (cont) hs = s;                               /* continuing: nothing to prime */
-    for (int64_t w0 = hs; w0 < s; w0 += WIN) {
-        for (int i = 0; i < WIN; i++) {
+    const int PW = P->prime_win > 0 ? P->prime_win : WIN;
+    for (int64_t w0 = hs; w0 < s; w0 += PW) {
+        for (int i = 0; i < PW; i++) {
             int64_t q = w0 + i; if (q >= s) continue;
-            /* per table: only the highest lane of a same-bucket group writes (atomicMax on the device) */
+            /* per table: only the highest position of a same-bucket group writes (atomicMax on the device) */
             if (q + 2 < F) {
                 uint32_t h = hash3(S + q, hb); int winner = 1;
-                for (int j = i + 1; j < WIN; j++) { int64_t q2 = w0 + j; if (q2 >= s || q2 + 2 >= F) continue; if (hash3(S + q2, hb) == h) { winner = 0; break; } }
+                for (int j = i + 1; j < PW; j++) { int64_t q2 = w0 + j; if (q2 >= s || q2 + 2 >= F) continue; if (hash3(S + q2, hb) == h) { winner = 0; break; } }
                 if (winner) INSERT(q);
             }
             if (nb2 && q + nb2 <= F) {
                 uint32_t h = hashN(S + q, nb2, hb2); int winner = 1;
-                for (int j = i + 1; j < WIN; j++) { int64_t q2 = w0 + j; if (q2 >= s || q2 + nb2 > F) continue; if (hashN(S + q2, nb2, hb2) == h) { winner = 0; break; } }
+                for (int j = i + 1; j < PW; j++) { int64_t q2 = w0 + j; if (q2 >= s || q2 + nb2 > F) continue; if (hashN(S + q2, nb2, hb2) == h) { winner = 0; break; } }
                 if (winner) INSERT2(q);
             }
         }

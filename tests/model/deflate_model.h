@@ -34,6 +34,7 @@ typedef struct {
     int32_t row_gate;     /* 0: always probe; 1: only where S[q] != S[q-1]; 2: not in noisy windows */
     int32_t exact_sel;    /* 1: a selected token whose lane has capped candidates compares all of them to the limit */
     int32_t group_subs;   /* consecutive sub-chunks of a page that share one pair of tables (first primed, rest continue) */
+    int32_t prime_win;    /* positions per priming step (32 or 128): within a step only the highest position of a bucket is inserted */
     int64_t block_bytes;  /* deflate block (multiple of sub_bytes) */
 } dm_params;
 typedef struct { int64_t tokens, blocks, stored_blocks; } dm_stats;

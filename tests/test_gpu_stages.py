@@ -167,14 +167,15 @@ def test_deflate_valid_and_size(S, ref_page):
 def test_lz_tokens_match_sequential_model(S, ref_page):
     """Token-for-token equality with tests/model/deflate_model.c (the sequential statement of the kernel)."""
     lib = M.load()
+    assert M.KERNEL_PARAMS["sub_bytes"] == S.engine().lib.vcp_lz_sub_bytes()      # the model mirrors the build's sub-chunk size
     for name, d in _streams(ref_page).items():
         tok, ntok, hist = S.lz_tokens(d, bpp=3)
         ref = M.lz_tokens(lib, d)
         assert len(ref) == len(ntok), name
-        # sub-chunk j of block b starts at b*512Ki + k*32Ki
+        # sub-chunk j of block b starts at b*512Ki + k*sub_bytes
         starts = []
         for bs in range(0, len(d), 524288):
-            for s in range(bs, min(len(d), bs + 524288), 32768):
+            for s in range(bs, min(len(d), bs + 524288), S.engine().lib.vcp_lz_sub_bytes()):
                 starts.append(s)
         for j, (rt, rh) in enumerate(ref):
             assert ntok[j] == len(rt), (name, j, int(ntok[j]), len(rt))

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvcprep.so")
+LIB_PATH = os.environ.get("VCP_LIBRARY") or os.path.join(HERE, "libvcprep.so")    # VCP_LIBRARY: dev A/B builds of the same ABI
 
 VCP_OK, VCP_EINVAL, VCP_ECUDA, VCP_ENOMEM, VCP_ESIZE = 0, -1, -2, -3, -4
 
@@ -67,6 +67,7 @@ SYMBOLS = {
     "vcp_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "vcp_png_filter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32)]),
     "vcp_deflate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "vcp_lz_sub_bytes": (C.c_int, []),
     "vcp_lz_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vcp_adler32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]),
     "vcp_crc32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]),

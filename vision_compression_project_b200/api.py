@@ -593,13 +593,16 @@ def decode_pages(pngs: Sequence[bytes], *, device: int = 0, to_device: bool = Fa
 
 
 class _Combiner:
-    """Micro-batcher for the reference's calling pattern (SURVEY.md §8 b): `_process_single_page` runs on 5 worker threads and each
-    calls the page body once per page (pdf_extract.py:313-333).  Five one-page launch sets cannot fill a B200, and each pays its own
-    H2D / launch / D2H latency; so while one caller's page is in flight, the pages of the callers that arrive meanwhile are queued
-    here and go out together as ONE launch set (same keyword arguments only).  Nobody ever waits for a batch to fill: a caller that
-    finds the device idle runs its page directly on its own thread, and a worker takes whatever has queued up the moment it is free."""
+    """Micro-batcher for callers that arrive one page at a time (SURVEY.md §8 b: `_process_single_page` runs on 5 worker threads and
+    each calls the page body once per page, pdf_extract.py:313-333).
+    Measured on B200 (tools/quick_threads.py, letter-200 pages): a one-page launch set is latency-bound (the LZ stage waits for its
+    heaviest sub-chunk), so independent launch sets on separate engines overlap almost perfectly — 5 threads reach 3.9 x the rate of
+    one — and funnelling them through a queue only lowers the number of sets in flight (1140 against 1600 pages/s).  So the first
+    DIRECT concurrent callers each run on their own thread and engine; only beyond that (thread pools much wider than the
+    reference's) are pages queued and sent out together, which bounds the engines (arenas, pinned buffers) a process creates."""
 
-    WORKERS = 2          # two launch sets in flight: the copy of one overlaps the kernels of the other
+    WORKERS = 2          # launch sets the queue keeps in flight beside the direct callers
+    DIRECT = 8           # callers served on their own thread before queueing starts
 
     def __init__(self, device: int):
         import queue
@@ -640,9 +643,9 @@ class _Combiner:
             return prepare_pages([image], device=self.device, **kw)[0]
         with self.lock:
             self.active += 1
-            alone = self.active == 1
+            direct = self.active <= self.DIRECT
         try:
-            if alone:                                     # idle device: no hand-off, the single-page latency stays what it was
+            if direct:                                    # few callers: each runs its page on its own thread and engine, no hand-off
                 return prepare_pages([image], device=self.device, **kw)[0]
             box: list = []
             done = threading.Event()

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "pixel_ops.cu", "png_filter.cu", "deflate_lz.cu", "deflate_huff.cu", "png_container.cu", "png_decode.cu"]
-LIB = os.path.join(HERE, "libvcprep.so")
+LIB = os.environ.get("VCP_LIBRARY") or os.path.join(HERE, "libvcprep.so")    # VCP_LIBRARY: dev A/B builds
 
 
 def nvcc_path() -> str:
@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += os.environ.get("VCP_NVCC_FLAGS", "").split()          # dev: -D overrides of tuning constants for A/B builds
     if verbose:
         cmd += ["-Xptxas", "-v"]
         print(" ".join(cmd), flush=True)

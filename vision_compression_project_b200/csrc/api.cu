@@ -1427,6 +1427,8 @@ int vcp_deflate(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, int 
     return 0;
 }
 
+int vcp_lz_sub_bytes(void) { return kSubBytes; }
+
 int vcp_lz_tokens(vcp_handle* h, const void* d_stream, uint64_t len, int bpp, uint32_t* d_tokens, uint32_t* sub_ntok_host, uint32_t* sub_hist_host) {
     if (!h || !d_tokens || !sub_ntok_host) return fail(VCP_EINVAL, "bad arguments");
     LOCK_HANDLE(h);

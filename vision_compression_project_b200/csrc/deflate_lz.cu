@@ -39,9 +39,17 @@ namespace {
 //   LAZY        one-step lazy rule applies to matches shorter than this (0 = greedy)
 //   PROBE       row-above candidate: 0 none, 1 only where a run starts, 2 everywhere
 struct CfgFast    { static constexpr int HB3 = 9,  HB6 = 9,  NOISY = 0,          LAZY = 0,  PROBE = 0; };
-struct CfgDefault { static constexpr int HB3 = 10, HB6 = 10, NOISY = 160,        LAZY = 16, PROBE = 1; };
+#ifndef VCP_HB3
+#define VCP_HB3 10
+#endif
+#ifndef VCP_HB6
+#define VCP_HB6 10
+#endif
+struct CfgDefault { static constexpr int HB3 = VCP_HB3, HB6 = VCP_HB6, NOISY = 160, LAZY = 16, PROBE = 1; };
 struct CfgBest    { static constexpr int HB3 = 11, HB6 = 12, NOISY = 0x7fffffff, LAZY = 16, PROBE = 2; };
 constexpr int kH2Bytes = 4;           // bytes keyed by the second table
+static_assert(kGroupSubs == 1 || kSubBytes == 32768, "the table rebase of grouped sub-chunks shifts by 32 KiB");
+static_assert(kPrimeBytes % 512 == 0 && kPrimeBytes <= kMaxDist && kSubBytes % 512 == 0 && kSubBytes <= kMaxDist, "sub-chunk geometry");
 constexpr int kLzWarps = 2;           // warps (= sub-chunks) per CTA
 constexpr int kLaneCap = 16;          // compare depth of a hash candidate inside a lane (deeper only for tokens the parse selects)
 constexpr int kCostMaxLen = 8;
@@ -200,13 +208,15 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     }
     __syncwarp();
 
-    // ---- prime with the previous 32 KiB of the page.  The history streams through 512-byte register blocks (one uint4 per
-    //      lane, two blocks ahead in flight: priming is bound by bytes in flight, not by instructions).  Per window the
-    //      arithmetic is the main loop's insert: the highest lane of a bucket group wins (atomicMax) and shifts the bucket once.
-    //      A block — or a 128-byte chunk — that is one repeated byte (white paper after filtering: most of a text page) hashes
-    //      every position to the same two buckets: its windows' inserts collapse to one store per table.
+    // ---- prime with the kPrimeBytes in front of the sub-chunk.  The history streams through 512-byte register blocks (one uint4
+    //      per lane, two blocks ahead in flight).  A block is ONE insert step: a lane hashes its own 16 positions (its 16 bytes and
+    //      the first 3 of its neighbour's), reads their buckets, and after one barrier the highest position of every bucket wins
+    //      (atomicMax) and shifts the bucket once: newest = highest position of the block, older = newest in front of the block.
+    //      (Steps of 32 positions, like the main loop's, cost 16 barriers and twice the instructions per block for the same PNG
+    //      size within 0.1 %: tests/model/deflate_model.c prime_win.)  A block that is one repeated byte (white paper after
+    //      filtering: most of a text page) hashes every position to the same two buckets: one store per table.
     if (si == 0) {
-        const int h0 = max(0, s - kMaxDist);                                     // multiple of 512 (s is a multiple of 32 KiB)
+        const int h0 = max(0, s - kPrimeBytes);                                  // multiple of 512 (s and kPrimeBytes are)
         const uint4* __restrict__ S128 = reinterpret_cast<const uint4*>(S);
         uint4 bc = make_uint4(0, 0, 0, 0), bn = bc;
         if (h0 < s) { bc = __ldg(S128 + (h0 >> 4) + lane); bn = __ldg(S128 + ((h0 + 512) >> 4) + lane); }
@@ -218,60 +228,42 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 if (lane == 0) {
                     const uint32_t h3 = ((c00 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
                     const uint32_t h6 = (c00 * 0x9E3779B1u) >> (32 - HB6);
-                    const uint32_t v = ((uint32_t)(b0 + 511 - base) << 16) | (uint32_t)(b0 + 479 - base);
-                    M.t3[h3] = v; M.t6[h6] = v;
+                    const uint32_t pos = (uint32_t)(b0 + 511 - base) << 16;
+                    M.t3[h3] = pos | (M.t3[h3] >> 16); M.t6[h6] = pos | (M.t6[h6] >> 16);
                 }
                 __syncwarp();
                 bc = bn; bn = bf;
                 continue;
             }
-#pragma unroll
-            for (int kc = 0; kc < 4; kc++) {
-                // words 32*kc + lane (this chunk) and 32*(kc+1) + lane (the next one) of the block
-                const int w0 = b0 + 128 * kc;
-                const int src = 8 * kc + (lane >> 2), srcn = (8 * (kc + 1) + (lane >> 2)) & 31;
-                const uint4& nb = kc < 3 ? bc : bn;
-                uint32_t cw, cn;
-                {
-                    const uint32_t v0 = __shfl_sync(kFull, bc.x, src), v1 = __shfl_sync(kFull, bc.y, src);
-                    const uint32_t v2 = __shfl_sync(kFull, bc.z, src), v3 = __shfl_sync(kFull, bc.w, src);
-                    const uint32_t u0 = __shfl_sync(kFull, nb.x, srcn), u1 = __shfl_sync(kFull, nb.y, srcn);
-                    const uint32_t u2 = __shfl_sync(kFull, nb.z, srcn), u3 = __shfl_sync(kFull, nb.w, srcn);
-                    const int cmp = lane & 3;
-                    cw = cmp == 0 ? v0 : cmp == 1 ? v1 : cmp == 2 ? v2 : v3;
-                    cn = cmp == 0 ? u0 : cmp == 1 ? u1 : cmp == 2 ? u2 : u3;
-                }
-                const uint32_t k00 = __shfl_sync(kFull, cw, 0), kn0 = __shfl_sync(kFull, cn, 0);
-                if (__all_sync(kFull, cw == k00) && k00 == __funnelshift_l(k00, k00, 8) && kn0 == k00 && w0 + 132 <= F) {
-                    if (lane == 0) {
-                        const uint32_t h3 = ((k00 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
-                        const uint32_t h6 = (k00 * 0x9E3779B1u) >> (32 - HB6);
-                        const uint32_t v = ((uint32_t)(w0 + 127 - base) << 16) | (uint32_t)(w0 + 95 - base);
-                        M.t3[h3] = v; M.t6[h6] = v;
-                    }
-                    __syncwarp();
-                    continue;
-                }
-                const int sh = (lane & 3) * 8;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int i = 8 * t + (lane >> 2);
-                    const uint32_t a0 = __shfl_sync(kFull, cw, i);
-                    uint32_t a1 = __shfl_sync(kFull, cw, (i + 1) & 31);
-                    if (t == 3) { const uint32_t b1 = __shfl_sync(kFull, cn, (i + 1) & 31); if (i + 1 >= 32) a1 = b1; }
-                    const uint32_t cur4 = __funnelshift_r(a0, a1, sh);
-                    const int q = w0 + 32 * t + lane;
-                    const bool ok3 = q + 2 < F, ok6 = q + kH2Bytes <= F;
-                    const uint32_t h3 = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
-                    const uint32_t h6 = (cur4 * 0x9E3779B1u) >> (32 - HB6);
-                    const uint32_t b3 = M.t3[h3], b6 = M.t6[h6];
-                    __syncwarp();
-                    const uint32_t pos = (uint32_t)(q - base);
-                    if (ok3) atomicMax(&M.t3[h3], (pos << 16) | (b3 >> 16));
-                    if (ok6) atomicMax(&M.t6[h6], (pos << 16) | (b6 >> 16));
-                    __syncwarp();
-                }
+            // this lane's 16 bytes and the 4 behind them (the last lane's neighbour is lane 0 of the next block)
+            uint32_t wd[5] = {bc.x, bc.y, bc.z, bc.w, 0u};
+            {
+                const uint32_t nx = __shfl_down_sync(kFull, bc.x, 1), nb0 = __shfl_sync(kFull, bn.x, 0);
+                wd[4] = lane == 31 ? nb0 : nx;
             }
+            const int q0 = b0 + 16 * lane;
+            uint32_t hh[16], bb[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t cur4 = __funnelshift_r(wd[k >> 2], wd[(k >> 2) + 1], (k & 3) * 8);
+                hh[k] = ((cur4 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
+                bb[k] = M.t3[hh[k]];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (q0 + k + 2 < F) atomicMax(&M.t3[hh[k]], ((uint32_t)(q0 + k - base) << 16) | (bb[k] >> 16));
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint32_t cur4 = __funnelshift_r(wd[k >> 2], wd[(k >> 2) + 1], (k & 3) * 8);
+                hh[k] = (cur4 * 0x9E3779B1u) >> (32 - HB6);
+                bb[k] = M.t6[hh[k]];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                if (q0 + k + kH2Bytes <= F) atomicMax(&M.t6[hh[k]], ((uint32_t)(q0 + k - base) << 16) | (bb[k] >> 16));
+            __syncwarp();
             bc = bn; bn = bf;
         }
     }

@@ -6,7 +6,18 @@
 
 namespace vcp {
 
-constexpr int kSubBytes   = 32768;        // LZ sub-chunk: one warp, one 64 Ki-position window of u16 table entries
+#ifndef VCP_SUB_BYTES
+#define VCP_SUB_BYTES 16384
+#endif
+#ifndef VCP_PRIME_BYTES
+#define VCP_PRIME_BYTES 16384
+#endif
+// Measured on B200 (gpurun_out/r2_variants*.log -> profiles/r02_lz_granularity.md): the LZ stage of a launch set ends with its heaviest
+// sub-chunk (one warp walking dense glyph rows), and hashing the history in front of a sub-chunk costs as much per byte as a quarter
+// of the parse.  16 KiB sub-chunks primed with 16 KiB: same kernel time as 32/32 on a full batch, half the latency of a small one
+// (single page 2.85 -> 2.0 ms, the reference's 5-thread pattern 1600 -> 2100 pages/s), +1.3 % PNG size on text pages.
+constexpr int kSubBytes   = VCP_SUB_BYTES;   // LZ sub-chunk: one warp; table entries are u16 positions relative to (start - 32 KiB)
+constexpr int kPrimeBytes = VCP_PRIME_BYTES; // bytes in front of a sub-chunk that are hashed into its tables before it starts (<= 32 KiB, multiple of 512)
 constexpr int kBlockBytes = 512 * 1024;   // deflate block = one IDAT chunk = 16 sub-chunks
 constexpr int kGroupSubs  = 1;            // consecutive sub-chunks of a page one warp handles with one pair of hash tables
                                           // (2 halves the priming work but measured slower on B200: fewer, longer work items -> ragged tail)

@@ -90,9 +90,10 @@ def lz_tokens(stream, bpp: int = 3, device: int = 0):
     n = t.numel()
     nblk = -(-n // (512 * 1024))
     nsub = 0
+    sub_bytes = e.lib.vcp_lz_sub_bytes()
     for b in range(nblk):
         ln = min(512 * 1024, n - b * 512 * 1024)
-        nsub += -(-ln // 32768)
+        nsub += -(-ln // sub_bytes)
     tok = torch.empty(n, dtype=torch.int32, device=t.device)
     ntok = np.zeros(nsub, np.uint32)
     hist = np.zeros((nsub, 316), np.uint32)
