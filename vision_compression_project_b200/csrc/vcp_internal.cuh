@@ -173,6 +173,28 @@ struct DecBatchD {
     int32_t no_scan;                                                          // VCP_DECODE_NO_SCAN: parse units are the IDAT starts only
 };
 
+// ---- TMA 1-D bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier).  Used to stage byte rows whose global
+// addresses share no word phase (3-byte pixels: a 2550-pixel RGB row is 7650 bytes): the copy engine needs only 16-byte alignment,
+// so a row is fetched from its address rounded down to 16 and lands with a per-row byte offset (address & 15) in shared memory.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");     // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {   // 16-byte aligned, size % 16 == 0
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 // ---- launchers (each returns the number of kernels it launched) ----
 int launch_inflate(const DecBatchD& b, cudaStream_t st);
 int launch_unfilter(const DecBatchD& b, cudaStream_t st);
