@@ -20,18 +20,18 @@ namespace vcp {
 // (R*19595 + G*38470 + B*7471 + 0x8000) >> 16.  A thread owns 4 consecutive pixels: 4-byte pixels are read as words (one 128-bit
 // load when the row allows), 3-byte pixels as three words, and the 12 or 4 output bytes leave as words when the output row is word
 // aligned (page rows of 4k pixels always are); everything else goes byte by byte.
+constexpr int kConvRows = 8;
 __device__ __forceinline__ uint32_t luma8(uint32_t r, uint32_t g, uint32_t b) { return (r * 19595u + g * 38470u + b * 7471u + 0x8000u) >> 16; }
 
 __global__ void __launch_bounds__(256) k_convert(const PageD* __restrict__ pages) {
     const PageD& P = pages[blockIdx.z];
     if (!P.conv) return;
-    const int y = blockIdx.y;
-    if (y >= P.sh) return;
+    const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (x4 >= P.sw) return;
+  for (int y = blockIdx.y * kConvRows; y < min(P.sh, (int)(blockIdx.y + 1) * kConvRows); y++) {     // several rows per CTA: fewer, longer-lived blocks
     const int sc = P.sc, c = P.pc;
     const uint8_t* __restrict__ srow = P.src + (int64_t)y * P.src_stride;
     uint8_t* __restrict__ drow = P.conv + (int64_t)y * P.sw * c;
-    const int x4 = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-    if (x4 >= P.sw) return;
     const bool full = x4 + 4 <= P.sw;
     const bool src_w = (((uintptr_t)srow) & 3) == 0, dst_w = (((uintptr_t)drow) & 3) == 0;
     if (full && sc == 4 && src_w) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_convert(const PageD* __restrict__ pages
             if (dst_w) reinterpret_cast<uint32_t*>(drow)[x4 >> 2] = o;
             else for (int k = 0; k < 4; k++) drow[x4 + k] = (uint8_t)(o >> (8 * k));
         }
-        return;
+        continue;
     }
     if (full && sc == 3 && c == 1 && src_w) {
         const uint32_t* g = reinterpret_cast<const uint32_t*>(srow + (int64_t)x4 * 3);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_convert(const PageD* __restrict__ pages
                            (luma8((b >> 16) & 255u, b >> 24, d2 & 255u) << 16) | (luma8((d2 >> 8) & 255u, (d2 >> 16) & 255u, d2 >> 24) << 24);
         if (dst_w) reinterpret_cast<uint32_t*>(drow)[x4 >> 2] = o;
         else for (int k = 0; k < 4; k++) drow[x4 + k] = (uint8_t)(o >> (8 * k));
-        return;
+        continue;
     }
     for (int x = x4; x < min(P.sw, x4 + 4); x++) {
         const uint8_t* s = srow + (int64_t)x * sc;
@@ -73,11 +73,12 @@ __global__ void __launch_bounds__(256) k_convert(const PageD* __restrict__ pages
             else d[0] = (uint8_t)luma8(__ldg(s), __ldg(s + 1), __ldg(s + 2));
         }
     }
+  }
 }
 
 int launch_convert(const PageD* d_pages, int npages, int max_rows, int max_w, cudaStream_t st) {
     if (npages == 0 || max_rows == 0) return 0;
-    dim3 grid(((max_w + 3) / 4 + 255) / 256, max_rows, npages);
+    dim3 grid(((max_w + 3) / 4 + 255) / 256, (max_rows + kConvRows - 1) / kConvRows, npages);
     k_convert<<<grid, 256, 0, st>>>(d_pages);
     return 1;
 }
