@@ -280,11 +280,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    all_cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+    my_cores = sharding.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if not args.no_pin else []
+    cores = host_cores() if world > 1 and not args.no_pin else cores      # of this rank from here on
 
     # ---- synthetic pages: drawn by spawned worker processes (FreeType rendering holds the GIL; spawn, not fork, so CUDA in this
     #      process is no concern), written straight into pinned host memory
     t_gen = time.perf_counter()
-    fac = PageFactory(max(2, cores // world))
+    fac = PageFactory(max(2, cores if my_cores and world > 1 else cores // world))
     n = PAGES_PER_GPU
     w, h = 1700, 2200
     host = torch.empty((n, h, w, 3), dtype=torch.uint8, pin_memory=True)          # pinned host copies of the pages
@@ -369,7 +372,7 @@ def run_ours(args):
     e2e_sync = world * n * Ke / max_over_ranks(time.perf_counter() - t0e)       # one synchronous prepare_pages call per step
     # the same K steps through prepare_stream: several steps in flight, so one step's pipeline drains (LZ / Huffman / D2H of its
     # last pages with the PCIe link idle) while the next one copies.  Every step still moves its 718 MB in and its bytes out.
-    depth = max(2, min(3, cores // (4 * world)))            # host threads are the scarce resource once several ranks share the box
+    depth = max(2, min(3, cores // 2 if my_cores and world > 1 else cores // (4 * world)))   # host threads are the scarce resource once several ranks share the box
     for _o in V.prepare_stream((host_np for _ in range(4)), depth=depth, device=local):
         assert all(o.error is None for o in _o)
     barrier()
@@ -462,6 +465,9 @@ def run_ours(args):
         c4 = sub_config("C4", run_c4)
 
     if rank == 0:
+        if all_cores and hasattr(os, "sched_setaffinity"):           # the CPU legs below use the whole box again (the other ranks are idle)
+            os.sched_setaffinity(0, all_cores)
+            cores = len(all_cores)
         # correctness of what was timed (not timed): first page decodes to the input and base64 matches
         import io
         from PIL import Image
@@ -589,6 +595,7 @@ def run_ours(args):
             "decode": decode_info,
             "configs": configs,
             "c4": c4,
+            "host": {"cores": len(all_cores) or cores, "cores_per_rank": len(my_cores) or cores, "pinned_ranks": bool(my_cores) and world > 1},
             "page_generation_s": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)
@@ -606,6 +613,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--c3-pages", type=int, default=C3_PAGES, help="pages of the C3 side config (BASELINE: 256)")
     ap.add_argument("--c4-pages", type=int, default=C4_PAGES, help="pages of the C4 document (BASELINE: 2000; 0 = skip the leg)")
+    ap.add_argument("--no-pin", action="store_true", help="N > 1: leave the ranks' threads unpinned (default: each rank gets its slice of the cores)")
     ap.add_argument("--headline-only", action="store_true", help="C2 only (profiling runs): no C1/C3/C5 side configs")
     args = ap.parse_args()
     if args.impl == "reference":

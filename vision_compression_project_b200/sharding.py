@@ -96,3 +96,17 @@ def gather_in_page_order(local: Sequence, lo: int, n_pages: int, group=None) -> 
     for l, items in gathered:
         out[l:l + len(items)] = items
     return out
+
+
+def pin_rank_to_cores(rank: int, world: int) -> list:
+    """One process per GPU on a shared host: give rank r its own slice of the cores this process may use, so that the ranks' pack /
+    scatter threads (and the Python threads that feed them) do not migrate over each other.  Returns the cores of this rank
+    (no-op outside Linux).  The library sizes its host thread pools from LOCAL_WORLD_SIZE; this only decides WHERE they run."""
+    import os
+    if not hasattr(os, "sched_setaffinity") or world <= 1:
+        return sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+    cores = sorted(os.sched_getaffinity(0))
+    lo, hi = page_range(len(cores), rank, world)
+    mine = cores[lo:hi] or cores
+    os.sched_setaffinity(0, mine)
+    return mine
