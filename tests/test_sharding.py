@@ -31,13 +31,17 @@ def test_balanced_ranges_mixed_sizes():
         assert max(loads) <= sum(w) / world + max(w)
 
 
-def _worker(rank, world, port, n_pages, q):
+def _worker(rank, world, port, n_pages, q, same_host=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if same_host:
+        os.environ["LOCAL_WORLD_SIZE"] = str(world)                          # as torchrun sets it: payloads go through shared memory
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = S.page_range(n_pages, rank, world)
     local = [f"page-{i}".encode() * (i + 1) for i in range(lo, hi)]          # variable-length byte strings, like PNGs
     out = S.gather_in_page_order(local, lo, n_pages)
+    pairs = S.gather_in_page_order([(b, None if i % 3 == 0 else b[::-1]) for i, b in zip(range(lo, hi), local)], lo, n_pages)
     if rank == 0:
+        assert pairs == [(b, None if i % 3 == 0 else b[::-1]) for i, b in enumerate(out)]      # (png, b64-or-None) tuples survive too
         q.put(out)
     dist.barrier()
     dist.destroy_process_group()
@@ -49,6 +53,21 @@ def test_gather_in_page_order_world2_gloo():
     q = ctx.Queue()
     n_pages = 11
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_pages, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert out == [f"page-{i}".encode() * (i + 1) for i in range(n_pages)]
+
+
+def test_gather_in_page_order_same_host_shared_memory():
+    """All ranks on one host (LOCAL_WORLD_SIZE == WORLD_SIZE, what torchrun sets on one box): the payload bytes go through POSIX
+    shared memory, only the layout through the process group; the result is the same list."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_pages = 13
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_pages, q, True)) for r in range(2)]
     [p.start() for p in procs]
     out = q.get(timeout=120)
     [p.join(60) for p in procs]
