@@ -121,7 +121,10 @@ def gather_in_page_order(local: Sequence, lo: int, n_pages: int, group=None) -> 
         for l, items in gathered:
             out[l:l + len(items)] = items
         return out
+    import ctypes
     from multiprocessing import shared_memory
+    from . import _native
+    threads = max(2, min(16, (os.cpu_count() or 4) // 2))
     layout, parts = flat
     total = sum(len(p) for p in parts)
     shm = shared_memory.SharedMemory(create=True, size=max(1, total))
@@ -138,19 +141,19 @@ def gather_in_page_order(local: Sequence, lo: int, n_pages: int, group=None) -> 
             for l, name, lay in metas:
                 blk = shm if name == shm.name else shared_memory.SharedMemory(name=name)
                 try:
-                    view, o = blk.buf, 0
+                    # every byte string of the block in one multi-threaded copy (vcp_host_scatter fills fresh bytes objects, GIL released)
+                    ranges, o = [], 0
+                    for ent in lay:
+                        for ln in ((ent,) if isinstance(ent, int) else ent):
+                            if ln >= 0:
+                                ranges.append((o, ln)); o += ln
+                    anchor = ctypes.c_char.from_buffer(blk.buf)
+                    try:
+                        objs = iter(_native.gather_bytes(ctypes.addressof(anchor), ranges, threads))
+                    finally:
+                        del anchor
                     for k, ent in enumerate(lay):
-                        if isinstance(ent, int):
-                            out[l + k] = bytes(view[o:o + ent]); o += ent
-                        else:
-                            item = []
-                            for ln in ent:
-                                if ln < 0:
-                                    item.append(None)
-                                else:
-                                    item.append(bytes(view[o:o + ln])); o += ln
-                            out[l + k] = tuple(item)
-                    del view
+                        out[l + k] = next(objs) if isinstance(ent, int) else tuple(None if ln < 0 else next(objs) for ln in ent)
                 finally:
                     if blk is not shm:
                         blk.close()
