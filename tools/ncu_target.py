@@ -1,5 +1,5 @@
 """Profiling target: one device-resident launch set per page class, so that an ncu capture sees every kernel of the path once with
-realistic sizes.  usage: ncu_target.py [c2|c3|c5|all]   (C2 = 64 letter-200 text pages; C3 = 16 letter-300 pages -> 1568;
+realistic sizes.  usage: ncu_target.py [c2|c3|c5|dec|all]   (C2 = 64 letter-200 text pages; C3 = 16 letter-300 pages -> 1568;
 C5 = 8 pages incl. 600-DPI (reduce) and an RGBA page (convert))."""
 import sys
 import numpy as np, torch
@@ -35,3 +35,17 @@ if __name__ == "__main__":
             ts = [torch.from_numpy(x).cuda() for x in a]
             rgba = torch.from_numpy(np.concatenate([a[0], np.full(a[0].shape[:2] + (1,), 255, np.uint8)], axis=2)).cuda()
             print("c5", {k: round(v, 3) for k, v in run(eng, ts + [rgba], {"max_side": 1568, "reducing_gap": 2.0}).items() if k.startswith("ms_")})
+        if what in ("dec",):
+            import io
+            from PIL import Image
+            import vision_compression_project_b200 as V
+            a = fac.arrays([(i, "letter", 200, "RGB", i % 4 == 3) for i in range(32)])
+            ours = [r.png for r in V.prepare_pages(a, want_base64=False)]
+            pil = []
+            for x in a[:8]:
+                b = io.BytesIO(); Image.fromarray(x, "RGB").save(b, format="PNG"); pil.append(b.getvalue())
+            for _ in range(2):
+                out = eng.decode_pages(ours + pil, to_device=True)
+            torch.cuda.synchronize()
+            assert all(not isinstance(o, Exception) for o in out) and bytes(out[3].cpu().numpy().tobytes()) == a[3].tobytes()
+            print("dec ok", len(out))

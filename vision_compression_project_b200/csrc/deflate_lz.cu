@@ -9,7 +9,7 @@
 // Decomposition: the filtered stream of a page is cut into 32 KiB sub-chunks, one WARP each (persistent warps pull
 // sub-chunks from a work queue in stream order).  A warp owns two small hash tables in shared memory (3-byte and
 // 4-byte keys, 2^10 buckets x 2 ways each, u16 positions relative to sub-chunk start - 32 KiB, so the previous 32 KiB
-// of the page are addressable history and are inserted before the sub-chunk starts; 9.25 KB per warp -> 22 warps/SM).
+// of the page are addressable history and are inserted before the sub-chunk starts; 8.6 KB per warp -> 26 warps/SM).
 // It then walks its sub-chunk in windows of 32 positions, one per lane:
 //   1. the stream is pulled through three 128-byte register chunks per warp (current, next, prefetched), so a
 //      window's bytes come from shuffles and the global-load latency is hidden behind the previous windows;
@@ -60,8 +60,12 @@ template <class Cfg>
 struct __align__(16) WarpMem {
     uint32_t t3[1 << Cfg::HB3];
     uint32_t t6[1 << Cfg::HB6];
-    uint32_t hist[320];
+    uint32_t hist[160];          // 320 token counters, two 16-bit halves per word (a sub-chunk has at most kSubBytes tokens)
 };
+
+static_assert(kSubBytes < 65536, "token counters are 16-bit");
+template <class WM> __device__ __forceinline__ uint32_t hist_get(const WM& M, int i) { return (M.hist[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu; }
+template <class WM> __device__ __forceinline__ void hist_add(WM& M, int i, uint32_t v) { atomicAdd(&M.hist[i >> 1], v << ((i & 1) * 16)); }
 
 __device__ __forceinline__ uint32_t ldu(const uint32_t* __restrict__ S32, int x) {   // unaligned u32 at byte x
     const int w = x >> 2;
@@ -411,12 +415,12 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
                 for (int kk = 0; kk < kCostMaxLen; kk++) {
                     if (kk < bl) {
                         const uint32_t byte = (kk < 4 ? (cur4 >> (8 * kk)) : (nxt4 >> (8 * (kk - 4)))) & 0xFFu;
-                        lit += lgN - ilog2x4(M.hist[byte] + 1);
+                        lit += lgN - ilog2x4(hist_get(M, (int)byte) + 1);
                     }
                 }
                 const int ls = bl - 3, ds = dist_sym(bd);                         // bl <= 8: no length extra bits
                 const int dx = ds < 4 ? 0 : (ds >> 1) - 1;
-                const int mc = (lgN - ilog2x4(M.hist[257 + ls] + 1)) + (lgN - ilog2x4(M.hist[286 + ds] + 1)) + 4 * dx;
+                const int mc = (lgN - ilog2x4(hist_get(M, 257 + ls) + 1)) + (lgN - ilog2x4(hist_get(M, 286 + ds) + 1)) + 4 * dx;
                 if (mc >= lit) { bl = 0; bd = 0; }
             }
         }
@@ -495,11 +499,11 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             const int rank = __popc(sel & ((1u << lane) - 1u));
             if (bl) {
                 tok[ntok + rank] = 0x80000000u | ((uint32_t)(bd - 1) << 8) | (uint32_t)(bl - 3);
-                atomicAdd(&M.hist[257 + len_sym(bl)], 1u);
-                atomicAdd(&M.hist[286 + dist_sym(bd)], 1u);
+                hist_add(M, 257 + len_sym(bl), 1u);
+                hist_add(M, 286 + dist_sym(bd), 1u);
             } else {
                 tok[ntok + rank] = bq;
-                atomicAdd(&M.hist[bq], 1u);
+                hist_add(M, (int)bq, 1u);
             }
         }
         ntok += __popc(sel);
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             const uint32_t extra = (uint32_t)((rend - next) / kMaxMatch);
             for (uint32_t i = lane; i < extra; i += 32) tok[ntok + i] = 0x80000000u | (uint32_t)(kMaxMatch - 3);
             if (extra) {
-                if (lane == 0) { atomicAdd(&M.hist[257 + 28], extra); atomicAdd(&M.hist[286], extra); }
+                if (lane == 0) { hist_add(M, 257 + 28, extra); hist_add(M, 286, extra); }
                 ntok += extra;
                 next += (int)extra * kMaxMatch;
             }
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     // ---- results
     if (lane == 0) B.sub_ntok[sub] = ntok;
     uint32_t* hout = B.sub_hist + (size_t)sub * kHistSize;
-    for (int i = lane; i < kHistSize; i += 32) hout[i] = M.hist[i];
+    for (int i = lane; i < kHistSize; i += 32) hout[i] = hist_get(M, i);
     __syncwarp();
    }
   }
