@@ -13,7 +13,9 @@
  * Plain C: POD structs, raw pointers and sizes only.  Every function returns 0 or a negative VCP_E*;
  * the message of the last error on the calling thread is vcp_last_error().
  * A handle owns four lanes (CUDA stream + device arena + pinned staging each; host batches rotate over them so copies and
- * kernels overlap); calls on one handle are serialised by a mutex, different handles are independent (the reference calls the path from 5 threads: pdf_extract.py:313-333).
+ * kernels overlap); calls on one handle are serialised by a mutex, different handles are independent (the reference calls the path
+ * from 5 threads: pdf_extract.py:313-333).  Between vcp_batch_begin and vcp_batch_end the handle belongs to the streaming worker:
+ * any other call on it returns VCP_EINVAL instead of blocking.
  */
 #ifndef VCPREP_H
 #define VCPREP_H
@@ -125,6 +127,10 @@ typedef struct {
     int32_t width, height, channels;
     uint64_t pix_off, pix_len;         /* byte range inside out_pixels                                   */
 } vcp_decode_result;
+/* Accepts and rejects what Image.open(png).load() does (Pillow 12 / zlib 1.3): chunks in front of the first IDAT need a correct CRC-32
+ * (IDAT CRCs are skipped like Pillow skips them), the zlib header, every block header and code must be valid (incomplete codes are
+ * errors as in inftrees.c), the stream must deliver every row, and the Adler-32 of the inflated stream — computed on the device — must
+ * match the trailer whenever zlib's inflate() would have met it in the call that produced the last row.  status = VCP_EINVAL otherwise. */
 int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs /* host pointers */, const uint64_t* png_lens, int n,
                          void* out_pixels, uint64_t out_cap, int dst_device, vcp_decode_result* results);
 
