@@ -1058,6 +1058,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     //      (probe, window chain, un-filter pipeline) overlap the throughput-bound ones of the other (exec, resolve)
     constexpr unsigned long long kResolveChunk = 32768, kCkpt = 65536, kScanBits = 8192;      // keep in step with png_decode.cu
     constexpr int kMaxCand = 1024;                                                              // scanned block headers per page
+    constexpr unsigned long long kSpecBits = VCP_SPEC_BITS;                                      // one speculative start point per so many bits of stream (png_decode.cu: k_infl_spec)
     struct Group { int i0 = 0, i1 = 0; uint64_t pix_base = 0, pix_bytes = 0; DecPageD* hd = nullptr; Lane* L = nullptr; };
     auto enqueue = [&](Group& G) -> int {
         Lane& L = *G.L;
@@ -1068,7 +1069,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         std::vector<uint32_t> chunk_page, chunk_pos, scan_page, scan_bit;
         uint64_t pix_total = 0;
         int nbands = 0;
-        size_t nslots = 0, iv_total = 0, seg_total = 0, surv_total = 0;
+        size_t nslots = 0, iv_total = 0, seg_total = 0, surv_total = 0, spec_total = 0;
         for (int j = 0; j < m; j++) {
             DecPageD& D = dp[i0 + j];
             D.band0 = nbands; D.iv0 = (int32_t)iv_total; D.seg0 = D.cand0 = (int32_t)seg_total; D.surv0 = (int32_t)surv_total; D.slot0 = (int32_t)nslots;
@@ -1092,7 +1093,9 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
                 o += c.n; q++;
             }
             D.n_idat = n_idat; D.ncand = (uint32_t)n_idat; D.nsurv = 0;
-            D.seg_cap = n_idat + kMaxCand;
+            D.spec0 = (int32_t)spec_total; D.nspec = (int32_t)(zl * 8ull / kSpecBits);
+            spec_total += (size_t)D.nspec;
+            D.seg_cap = n_idat + kMaxCand + D.nspec;
             cand.resize(seg_total + (size_t)D.seg_cap, 0ull);
             seg_total += (size_t)D.seg_cap;
             nslots += (size_t)D.seg_cap * page_iv;
@@ -1139,6 +1142,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
                      chunk_bytes = align_up(chunk_page.size() * sizeof(uint32_t), 256), band_bytes = align_up(band_page.size() * sizeof(uint32_t), 256),
                      scan_bytes = align_up(scan_page.size() * sizeof(uint32_t), 256);
         const size_t meta_bytes = desc_bytes + seg_bytes + 2 * chunk_bytes + 2 * band_bytes + 2 * scan_bytes;
+        const size_t o_chdr = bump.take(seg_bytes + 16);                  // candidate header bits (zeroed on the device)
         const size_t o_desc = bump.take(meta_bytes + 16);
         const size_t flag_bytes = align_up(((size_t)nbands + 64) * sizeof(uint32_t), 256);
         const size_t o_flag = bump.take(flag_bytes);
@@ -1183,10 +1187,12 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         if (zoff_total) CU(cudaMemcpyAsync(A + o_zreg, L.stage, zoff_total, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(A + o_desc, hm, meta_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaMemsetAsync(A + o_flag, 0, flag_bytes, st));
+        CU(cudaMemsetAsync(A + o_chdr, 0, seg_bytes, st));
         DecBatchD B; memset(&B, 0, sizeof B);
         B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = m;
         B.segs = reinterpret_cast<DecSegD*>(A + o_segs); B.seg_total = (int32_t)seg_total;
         B.cand_bits = reinterpret_cast<unsigned long long*>(A + o_desc + desc_bytes);
+        B.cand_hdr = reinterpret_cast<unsigned long long*>(A + o_chdr); B.spec_total = (int32_t)spec_total;
         B.surv = reinterpret_cast<uint32_t*>(A + o_surv); B.surv_total = (int32_t)surv_total;
         B.scan_page = reinterpret_cast<const uint32_t*>(A + o_desc + scan_off);
         B.scan_bit = reinterpret_cast<const uint32_t*>(A + o_desc + scan_off + scan_bytes);

@@ -488,16 +488,81 @@ __global__ void __launch_bounds__(256) k_infl_sort(const DecBatchD b) {
     }
     const int K = (int)min(P.ncand, (uint32_t)P.seg_cap);
     const unsigned long long* C = b.cand_bits + P.cand0;
+    const unsigned long long* H = b.cand_hdr + P.cand0;
     for (int i = threadIdx.x; i < K; i += 256) {
         const unsigned long long v = C[i];
         int rank = 0;
-        for (int j = 0; j < K; j++) rank += C[j] < v ? 1 : 0;
+        for (int j = 0; j < K; j++) rank += (C[j] < v || (C[j] == v && j < i)) ? 1 : 0;     // stable: equal start bits keep distinct slots
         DecSegD S; memset(&S, 0, sizeof S);
-        S.page = blockIdx.x; S.start_bit = v;
+        S.page = blockIdx.x; S.start_bit = v; S.hdr_bit = H[i] ? H[i] : v;
         S.iv0 = (uint32_t)P.slot0 + (uint32_t)rank * (uint32_t)P.page_iv; S.iv_cap = (uint32_t)P.page_iv;
         b.segs[P.seg0 + rank] = S;
     }
     if (threadIdx.x == 0) P.nseg = K;
+}
+
+// ------------------------------------------------------------------------------------------ spec: parse units INSIDE long blocks
+// The first parse is serial per parse unit, and a unit is a deflate block: zlib starts one every 32 Ki symbols, but this library's
+// own PNGs (512 KiB of input per block: 400 K tokens on a photo) and other encoders' large blocks leave one warp parsing alone for
+// tens of milliseconds.  Huffman-coded streams re-synchronise: a parse started at a WRONG bit falls into step with the true token
+// boundaries after a few dozen tokens.  So every kSpecBits of stream one warp builds the tables of the block that (as far as the
+// found headers say) contains that point, starts decoding at the point itself, and after kSpecSync bits reports the token boundary
+// it has reached as a further candidate parse unit "inside block H".  Nothing is assumed about it: k_infl_probe only ends a
+// unit's parse on a candidate when its own token boundary falls exactly on the candidate's start AND it is inside the same block
+// (same header bit) — from there on the two parses are identical by construction.  A candidate that is not a true boundary is
+// walked over and never reached by the chain, like a false positive of the header scan.
+constexpr unsigned long long kSpecBits = VCP_SPEC_BITS;   // (api.cu sizes the candidate ranges with the same constant)
+constexpr unsigned long long kSpecSync = 6144;
+
+__global__ void __launch_bounds__(128) k_infl_spec(const DecBatchD b) {
+    __shared__ InflMem mem[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * 4 + warp;
+    if (g >= b.spec_total) return;
+    int plo = 0, phi = b.npages - 1;                    // page of speculative point g: last page with spec0 <= g
+    while (plo < phi) { const int mid = (plo + phi + 1) >> 1; if (b.pages[mid].spec0 <= g) plo = mid; else phi = mid - 1; }
+    DecPageD& P = b.pages[plo];
+    const int t = g - P.spec0;
+    if (P.status != 0 || t >= P.nspec || P.nseg <= 0) return;
+    const unsigned long long nbits = P.zlen * 8ull;
+    const unsigned long long point = (unsigned long long)(t + 1) * kSpecBits;
+    if (point + kSpecSync + 2048 >= nbits) return;
+    const DecSegD* PS = b.segs + P.seg0;                // the block starts found so far, sorted
+    int lo = 0, hi = P.nseg - 1;
+    if (PS[0].start_bit > point) return;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (PS[mid].start_bit <= point) lo = mid; else hi = mid - 1; }
+    const unsigned long long H = PS[lo].start_bit;
+    if (point - H < kSpecBits / 2) return;                                                  // a unit starts close in front anyway
+    if (lo + 1 < P.nseg && PS[lo + 1].start_bit < point + kSpecSync + 2048) return;         // ... or close behind
+    InflMem& M = mem[warp];
+    BitReader br; br.init(P.z, P.zlen, M.zbuf);
+    uint32_t filled = 0;
+    seek_bit(M, br, filled, H);
+    int last = 0, btype = 0, slen = 0; unsigned long long ssrc = 0;
+    if (block_header(M, br, filled, &last, &btype, &slen, &ssrc) != INF_OK || btype == 0) return;
+    if (__shfl_sync(kFull, br.bits_used(), 0) >= point) return;
+    unsigned long long B = point;
+    filled = 0;
+    int resync = 0;
+    while (B < point + kSpecSync) {
+        topup(M, br, filled, (uint32_t)((B + 8ull * (unsigned)br.mis) >> 5));
+        uint32_t w0, w1, info = 0, tok = 0;
+        ring_window(M, br, B + lane, &w0, &w1);
+        spec_decode<true>(M, w0, w1, &info, &tok);
+        int o = 0; bool stop = false;
+        while (o < 32) {
+            const uint32_t inf = __shfl_sync(kFull, info, o);
+            if (inf & SP_EOB) { stop = true; break; }                                        // a block ends (or seems to): leave it to the header scan
+            if (inf & SP_BAD) { if (++resync > 64) stop = true; o += 1; continue; }          // not a code here: try the next bit
+            o += (int)(inf & 63u);
+        }
+        if (stop) return;
+        B += o;
+    }
+    if (lane == 0) {
+        const uint32_t idx = atomicAdd(&P.ncand, 1u);
+        if (idx < (uint32_t)P.seg_cap) { b.cand_bits[P.cand0 + idx] = B; b.cand_hdr[P.cand0 + idx] = H; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ probe: parse, count, checkpoint
@@ -518,16 +583,19 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
     BitReader br; br.init(P.z, P.zlen, M.zbuf);
     uint32_t filled = 0;
     int status = INF_OK;
-    const unsigned long long start_bit = S.start_bit;
-    seek_bit(M, br, filled, start_bit);
+    const unsigned long long start_bit = S.start_bit, unit_hdr = S.hdr_bit;   // unit_hdr != start_bit: the unit starts inside a block (k_infl_spec)
+    seek_bit(M, br, filled, unit_hdr);
     const unsigned long long cap = P.filt_len, nbits = P.zlen * 8ull;
     unsigned long long pos = 0;                         // output bytes so far
     // interval being built (lane 0)
-    unsigned long long iv_hdr = start_bit, iv_start = start_bit, iv_out = 0, next_ck = kCkpt;
+    unsigned long long iv_hdr = unit_hdr, iv_start = start_bit, iv_out = 0, next_ck = kCkpt;
     uint32_t niv = 0;
     int end_seg = s_loc + 1;                            // the first parse unit whose start the parse has not passed yet
     int last = 0, next = P.nseg;
-    bool done = false;
+    bool done = false, first_block = true;
+    // every lane: the next unit in stream order, for the token-boundary test inside blocks
+    int ns = s_loc + 1;
+    unsigned long long nxt_start = ns < P.nseg ? PS[ns].start_bit : ~0ull;
     auto emit = [&](unsigned long long out_now, unsigned long long hdr_bit, unsigned long long bit_now) {   // lane 0: close the interval at a token boundary
         if (out_now > iv_out) {
             if (niv < S.iv_cap) { DecIvD& I = slots[S.iv0 + niv]; I.hdr_bit = iv_hdr; I.start_bit = iv_start; I.out = (uint32_t)iv_out; I.len = (uint32_t)(out_now - iv_out); I.seg = (uint32_t)sg; I.last = 0; }
@@ -543,24 +611,36 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
         status = block_header(M, br, filled, &last, &btype, &slen, &ssrc);
         if (__shfl_sync(kFull, br.bits_used(), 0) > nbits) status = INF_SHORT;   // the header runs past the end of the data (bits behind it are not the stream's)
         if (status != INF_OK) break;
+        hdr_bit = __shfl_sync(kFull, hdr_bit, 0);
+        const bool mid_start = first_block && unit_hdr != start_bit;
+        first_block = false;
+        if (mid_start && (btype == 0 || __shfl_sync(kFull, br.bits_used(), 0) > start_bit)) { status = INF_SEG; break; }   // never offered by k_infl_spec
         if (btype == 0) {
             pos += slen;
             if (pos > cap) { status = INF_OVERRUN; break; }
         } else {
-            bool eob = false;
-            unsigned long long B = __shfl_sync(kFull, br.bits_used(), 0);      // bit position of the next token
+            bool eob = false, unit_stop = false;
+            unsigned long long B = mid_start ? start_bit : __shfl_sync(kFull, br.bits_used(), 0);      // bit position of the next token
             uint32_t p = (uint32_t)pos;                                       // cap < 2^32, a token adds <= 258: no wrap before the checks
             uint32_t ck = (uint32_t)min(__shfl_sync(kFull, next_ck, 0), 0xffffffffull);
-            while (status == INF_OK && !eob) {
+            while (status == INF_OK && !eob && !unit_stop) {
                 if (B > br.n * 8ull + 64ull) { status = INF_SHORT; break; }
                 topup(M, br, filled, (uint32_t)((B + 8ull * (unsigned)br.mis) >> 5));
-                for (int r = 0; r < 48 && !eob && status == INF_OK; r++) {    // 48 rounds eat at most 48 * 79 bits = 119 words
+                for (int r = 0; r < 48 && !eob && !unit_stop && status == INF_OK; r++) {    // 48 rounds eat at most 48 * 79 bits = 119 words
                     uint32_t w0, w1, info = 0, tok = 0;
                     ring_window(M, br, B + lane, &w0, &w1);
                     spec_decode<false>(M, w0, w1, &info, &tok);
                     int o = 0;
                     const bool near_end = B + 2048ull > nbits;                // a round eats < 2048 bits: only the last ones look at the end
+                    const bool near_unit = nxt_start < B + 2048ull;           // ... or at the next parse unit's start
                     while (o < 32) {
+                        if (near_unit) {
+                            // does a token boundary of this parse fall exactly on the start of another unit of the same block?  Then
+                            // that unit's parse is this one's continuation: stop here.  Units walked over were not on a boundary.
+                            const unsigned long long at = B + o;
+                            while (nxt_start < at || (nxt_start == at && PS[ns].hdr_bit != hdr_bit)) { ns++; nxt_start = ns < P.nseg ? PS[ns].start_bit : ~0ull; }
+                            if (nxt_start == at && at > start_bit) { unit_stop = true; break; }
+                        }
                         uint32_t inf = __shfl_sync(kFull, info, o);
                         if ((inf & (SP_SLOW | SP_BAD | SP_EOB)) || near_end) {    // the common token pays one test for all of these
                             if (inf & SP_SLOW) {
@@ -585,6 +665,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
             }
             if (status == INF_OK && p > cap) status = INF_OVERRUN;
             pos = p;
+            if (status == INF_OK && unit_stop) { next = ns; last = 0; done = true; break; }   // (all lanes) handed over to the unit that starts here
             if (status == INF_OK) seek_bit(M, br, filled, B);                 // the header reader continues behind the end-of-block code
             if (status != INF_OK) break;
         }
@@ -600,6 +681,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
                 while (hi2 < P.nseg && PS[hi2].start_bit < used) { end_seg = hi2 + 1; hi2 += step; step <<= 1; }
                 hi2 = min(hi2, P.nseg);
                 while (end_seg < hi2) { const int mid = (end_seg + hi2) >> 1; if (PS[mid].start_bit < used) end_seg = mid + 1; else hi2 = mid; }
+                while (end_seg < P.nseg && PS[end_seg].start_bit == used && PS[end_seg].hdr_bit != used) end_seg++;   // only a unit that IS a block start
                 if (end_seg < P.nseg && PS[end_seg].start_bit == used) { stop = 1; next = end_seg; }
             }
             if (br.over && status == INF_OK) status = INF_SHORT;
@@ -1033,6 +1115,12 @@ int launch_inflate(const DecBatchD& b, cudaStream_t st) {
         k_infl_scan2<<<(b.surv_total + 127) / 128, 128, 0, st>>>(b);
     }
     k_infl_sort<<<b.npages, 256, 0, st>>>(b);
+    int extra = 0;
+    if (b.spec_total > 0) {                              // further parse units inside long blocks, then the units in order again
+        k_infl_spec<<<(b.spec_total + 3) / 4, 128, 0, st>>>(b);
+        k_infl_sort<<<b.npages, 256, 0, st>>>(b);
+        extra = 2;
+    }
     k_infl_probe<<<(b.seg_total + 3) / 4, 128, 0, st>>>(b.pages, b.segs, b.slots, b.npages, b.seg_total);
     k_infl_plan<<<b.npages, 32, 0, st>>>(b.pages, b.segs, b.slots, b.ivs, b.npages);
     k_infl_exec<<<b.iv_total, 32, 0, st>>>(b.pages, b.segs, b.ivs, b.npages, b.iv_total);
@@ -1042,7 +1130,7 @@ int launch_inflate(const DecBatchD& b, cudaStream_t st) {
         k_dec_adler_part<<<b.nchunks, 256, 0, st>>>(b);
     }
     k_dec_adler_fin<<<b.npages, 32, 0, st>>>(b);
-    return 8 + (b.nchunks ? 2 : 0);
+    return 8 + extra + (b.nchunks ? 2 : 0);
 }
 
 // ------------------------------------------------------------------------------------------ un-filter

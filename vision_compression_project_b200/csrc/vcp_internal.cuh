@@ -16,6 +16,9 @@ namespace vcp {
 // sub-chunk (one warp walking dense glyph rows), and hashing the history in front of a sub-chunk costs as much per byte as a quarter
 // of the parse.  16 KiB sub-chunks primed with 16 KiB: same kernel time as 32/32 on a full batch, half the latency of a small one
 // (single page 2.85 -> 2.0 ms, the reference's 5-thread pattern 1600 -> 2100 pages/s), +1.3 % PNG size on text pages.
+#ifndef VCP_SPEC_BITS
+#define VCP_SPEC_BITS 32768        // decode: one speculative parse start per 4 KiB of compressed stream (png_decode.cu k_infl_spec)
+#endif
 constexpr int kSubBytes   = VCP_SUB_BYTES;   // LZ sub-chunk: one warp; table entries are u16 positions relative to (start - 32 KiB)
 constexpr int kPrimeBytes = VCP_PRIME_BYTES; // bytes in front of a sub-chunk that are hashed into its tables before it starts (<= 32 KiB, multiple of 512)
 constexpr int kBlockBytes = 512 * 1024;   // deflate block = one IDAT chunk = 16 sub-chunks
@@ -124,6 +127,7 @@ struct DecPageD {
     int32_t iv0, iv_cap, niv;                       // its intervals in the DecIvD array (niv written by k_infl_plan)
     int32_t band0;                                  // first 32-row band of this page in the un-filter's band numbering
     int32_t chunk0;                                 // first 32 KiB chunk of this page in the resolve / Adler work list
+    int32_t spec0, nspec;                           // its range of speculative start points (one per kSpecBits of stream, k_infl_spec)
     // ---- what Pillow's decoder (zlib inflate driven row by row, ZipDecode.c) would have seen at the end of the image; the host
     //      turns these into accept / reject exactly as Image.open(png).load() does (api.cu: decode_verdict)
     unsigned long long valid_len;                   // inflated bytes that exist: filt_len, or less when the final block ended early
@@ -145,6 +149,7 @@ struct DecSegD {
     uint32_t niv;            // intervals it wrote
     uint32_t iv0, iv_cap;    // its private range of checkpoint slots
     unsigned long long end_bit;     // fin: bit position behind the final block (the Adler-32 follows at the next byte boundary)
+    unsigned long long hdr_bit;     // header of the deflate block the unit starts in (== start_bit unless the unit starts inside a block, k_infl_spec)
 };
 
 // A stretch of tokens between two checkpoints of a parse: the unit of k_infl_exec.
@@ -160,6 +165,8 @@ struct DecBatchD {
     DecPageD* pages; int32_t npages;
     DecSegD* segs; int32_t seg_total;                                         // parse units, one range of seg_cap per page
     unsigned long long* cand_bits;                                            // candidate start bits, same ranges
+    unsigned long long* cand_hdr;                                             // per candidate: header bit of its block (0: the candidate IS a block start)
+    int32_t spec_total;                                                       // speculative start points over all pages
     uint32_t* surv; int32_t surv_total;                                       // k_infl_scan1 survivors, one range per page
     const uint32_t* scan_page; const uint32_t* scan_bit; int32_t nscan;       // scan work list: 8 Ki bit positions each
     DecIvD* slots;                                                            // checkpoint slots, one private range per parse unit
