@@ -372,7 +372,7 @@ def run_ours(args):
     e2e_sync = world * n * Ke / max_over_ranks(time.perf_counter() - t0e)       # one synchronous prepare_pages call per step
     # the same K steps through prepare_stream: several steps in flight, so one step's pipeline drains (LZ / Huffman / D2H of its
     # last pages with the PCIe link idle) while the next one copies.  Every step still moves its 718 MB in and its bytes out.
-    depth = max(2, min(3, cores // 2 if my_cores and world > 1 else cores // (4 * world)))   # host threads are the scarce resource once several ranks share the box
+    depth = 2                                                # batches in flight: measured 2 >= 3 > 4 on B200 (tools/quick_e2e.py): more only fight for the one PCIe link
     for _o in V.prepare_stream((host_np for _ in range(4)), depth=depth, device=local):
         assert all(o.error is None for o in _o)
     barrier()
