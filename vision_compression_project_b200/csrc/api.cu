@@ -214,6 +214,24 @@ __attribute__((target("ssse3"))) void pack_rgbx_ssse3(uint8_t* d, const uint8_t*
     if (aligned) _mm_sfence();
 }
 
+// memcpy into the pinned bounce buffer with streaming stores.  The copy engine reads that buffer next: lines left dirty in the CPU
+// caches by ordinary stores make its reads snoop them (measured on the B200 box: a one-page launch set took 1.6 ms longer from a
+// pageable numpy array than from a PIL image, whose pack already streamed), and the data would only evict useful cache lines.
+__attribute__((target("sse2"))) void stream_copy(uint8_t* d, const uint8_t* s, size_t n) {
+    if (n < 256) { memcpy(d, s, n); return; }
+    const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(s + i + 32)), e = _mm_loadu_si128((const __m128i*)(s + i + 48));
+        _mm_stream_si128((__m128i*)(d + i), a); _mm_stream_si128((__m128i*)(d + i + 16), b);
+        _mm_stream_si128((__m128i*)(d + i + 32), c); _mm_stream_si128((__m128i*)(d + i + 48), e);
+    }
+    _mm_sfence();
+    if (i < n) memcpy(d + i, s + i, n - i);
+}
+
 void pack_rgbx(uint8_t* d, const uint8_t* s, size_t npix) {
     static const bool has = __builtin_cpu_supports("ssse3");
     if (has) { pack_rgbx_ssse3(d, s, npix); return; }
@@ -239,7 +257,7 @@ void parallel_copy(const std::vector<CopyJob>& jobs, int T) {
                 a = std::min(a, j.len); b = std::min(b, j.len);
                 if (a < b) {
                     if (j.drop4) pack_rgbx(j.dst + a / 4 * 3, j.src + a, (b - a) / 4);
-                    else memcpy(j.dst + a, j.src + a, b - a);
+                    else stream_copy(j.dst + a, j.src + a, b - a);
                 }
             }
             pos += j.len;
