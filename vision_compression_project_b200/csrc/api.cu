@@ -245,10 +245,14 @@ void parallel_copy(const std::vector<CopyJob>& jobs, int T) {
     if (total < ((size_t)1 << 20)) T = 1;
     // part t takes the source bytes [t * total / T, (t + 1) * total / T) of the concatenation, cut on 64-byte (16-pixel) boundaries
     // of each range so that packed pixels never straddle two parts
-    HostPool::get().run(T, T, [&jobs, total, T](int t) {
+    std::vector<size_t> cum(jobs.size() + 1, 0);              // many small ranges (one per row of a strided source): every part finds its first range by bisection
+    for (size_t i = 0; i < jobs.size(); i++) cum[i + 1] = cum[i] + jobs[i].len;
+    HostPool::get().run(T, T, [&jobs, &cum, total, T](int t) {
         const size_t lo = total * t / T, hi = total * (t + 1) / T;
-        size_t pos = 0;
-        for (size_t i = 0; i < jobs.size() && pos < hi; i++) {
+        size_t i0 = (size_t)(std::upper_bound(cum.begin(), cum.end(), lo) - cum.begin());
+        i0 = i0 ? i0 - 1 : 0;
+        size_t pos = cum[i0];
+        for (size_t i = i0; i < jobs.size() && pos < hi; i++) {
             const CopyJob& j = jobs[i];
             size_t a = std::max(lo, pos) - pos, b = std::min(hi, pos + j.len) - pos;
             if (std::max(lo, pos) < std::min(hi, pos + j.len)) {
