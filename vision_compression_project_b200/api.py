@@ -487,6 +487,24 @@ class PagePrep:
             bb = self._pinned("_out_b64", cap_b64) if want_b64 else None
             res = (N.PageResult * m)()
             done = {}
+            if m <= 2:
+                # a page or two is one launch set: the synchronous call, no worker thread to start and join (single-page latency)
+                rc = self.lib.vcp_prepare_batch(self.handle, descs, m, C.byref(opts), bp.data_ptr(), bp.numel(),
+                                                bb.data_ptr() if bb is not None else None, bb.numel() if bb is not None else 0, res)
+                err = N.error_for(rc, N.last_error()) if rc else None
+                if err is None:
+                    t_b = time.perf_counter()
+                    sel = [i for i in range(m) if res[i].status == 0]
+                    pngs = N.gather_bytes(bp.data_ptr(), [(res[i].png_off, res[i].png_len) for i in sel], 1)
+                    b64s = (N.gather_bytes(bb.data_ptr(), [(res[i].b64_off, res[i].b64_len) for i in sel], 1)
+                            if bb is not None else [None] * len(sel))
+                    for i, png, b64 in zip(sel, pngs, b64s):
+                        done[i] = (png, b64)
+                    t_bytes += time.perf_counter() - t_b
+                    break
+                if attempt or not (isinstance(err, ValueError) and "too small" in str(err)):
+                    raise err
+                continue
             # streaming batch: the library's worker thread drives the H2D / kernel / D2H pipeline while this thread turns every
             # finished run of pages into Python bytes (vcp_host_scatter, GIL released) — the copies overlap the GPU work
             N.check(self.lib.vcp_batch_begin(self.handle, descs, m, C.byref(opts), bp.data_ptr(), bp.numel(),

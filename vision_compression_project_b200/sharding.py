@@ -110,6 +110,13 @@ def gather_in_page_order(local: Sequence, lo: int, n_pages: int, group=None) -> 
     rank = dist.get_rank(group)
     same_host = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0) == world or world == 1
     flat = _flatten_bytes(local) if same_host else None
+    if flat is not None:                               # a tmpfs too small for the block would fault on write, not raise: check first
+        try:
+            vfs = os.statvfs("/dev/shm")
+            if vfs.f_bavail * vfs.f_frsize < 2 * sum(len(p) for p in flat[1]) * world + (64 << 20):
+                flat = None
+        except OSError:
+            flat = None
     ok = [None] * world
     dist.all_gather_object(ok, flat is not None, group=group)
     if not all(ok):
