@@ -124,9 +124,12 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
 
     int64_t p = s;
     int score = 0;                     /* EMA of literal tokens per window (x8) */
+    uint32_t hsnap[316]; uint32_t Nsnap = 0; int64_t epoch = 0;
+    memset(hsnap, 0, sizeof hsnap);
     while (p < e) {
         const int noisy = P->noisy_thresh < 0 || (P->noisy_thresh > 0 && score >= P->noisy_thresh);   /* < 0: always */
-        uint32_t hsnap[316]; memcpy(hsnap, hist, sizeof hsnap);   /* costs use the counts as of the window start */
+        /* costs use the counts as of the window start, or (cost_epoch) as of the first window after every cost_epoch tokens */
+        if (!P->cost_epoch || ntok / P->cost_epoch != epoch) { memcpy(hsnap, hist, sizeof hsnap); Nsnap = (uint32_t)ntok; if (P->cost_epoch) epoch = ntok / P->cost_epoch; }
         uint32_t Ntok = (uint32_t)ntok;
         int nlit = 0;
         int len[WIN], dist[WIN], capped[WIN];
@@ -194,7 +197,7 @@ int64_t dm_lz_subchunk_ex(const uint8_t* S, int64_t F, int64_t s, int64_t e, con
             if (bl < 3 || (bl == 3 && bd > P->too_far)) continue;
             if (noisy && bl < P->noisy_minlen && bd > P->noisy_neard) continue;
             if (P->cost_maxlen && bl <= P->cost_maxlen && Ntok >= (uint32_t)P->cost_warm) {
-                int lgN = ilog2x4(Ntok + 1);
+                int lgN = ilog2x4(Nsnap + 1);
                 int lit = 0;
                 for (int k = 0; k < bl; k++) lit += lgN - ilog2x4(hsnap[S[q + k]] + 1);
                 int ls = dm_len_sym(bl), ds = dm_dist_sym(bd);

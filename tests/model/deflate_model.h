@@ -35,6 +35,7 @@ typedef struct {
     int32_t exact_sel;    /* 1: a selected token whose lane has capped candidates compares all of them to the limit */
     int32_t group_subs;   /* consecutive sub-chunks of a page that share one pair of tables (first primed, rest continue) */
     int32_t prime_win;    /* positions per priming step (32 or 128): within a step only the highest position of a bucket is inserted */
+    int32_t cost_epoch;   /* 0: costs from the counts as of the window start; N: from a table refreshed at the first window after every N tokens */
     int64_t block_bytes;  /* deflate block (multiple of sub_bytes) */
 } dm_params;
 typedef struct { int64_t tokens, blocks, stored_blocks; } dm_stats;

@@ -14,7 +14,7 @@ class Params(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("bpp", "hash_bits", "ways", "lane_cap", "too_far", "lazy", "cont_min",
                                          "prime_bytes", "capped_wins", "inwin", "cont_maxd", "sub_bytes", "hash2_bytes",
                                          "hash2_bits", "noisy_thresh", "noisy_minlen", "noisy_neard", "cost_maxlen",
-                                         "cost_margin", "cost_warm", "hash2_ways", "ins_limit", "noisy_ways1", "lane_cap_win", "rowlen", "row_gate", "exact_sel", "group_subs", "prime_win")] + [("block_bytes", C.c_int64)]
+                                         "cost_margin", "cost_warm", "hash2_ways", "ins_limit", "noisy_ways1", "lane_cap_win", "rowlen", "row_gate", "exact_sel", "group_subs", "prime_win", "cost_epoch")] + [("block_bytes", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -24,7 +24,7 @@ class Stats(C.Structure):
 # the configuration csrc/deflate_lz.cu + deflate_huff.cu implement (group_subs mirrors kGroupSubs in vcp_internal.cuh)
 KERNEL_PARAMS = dict(bpp=3, hash_bits=10, ways=2, lane_cap=16, too_far=32768, lazy=16, cont_min=258, prime_bytes=16384,
                      capped_wins=1, inwin=0, cont_maxd=1, noisy_thresh=160, noisy_minlen=0, noisy_neard=0, cost_maxlen=8,
-                     cost_margin=0, cost_warm=64, hash2_ways=2, ins_limit=0, noisy_ways1=1, lane_cap_win=0, rowlen=-1, row_gate=1, exact_sel=1, group_subs=1, prime_win=512, hash2_bytes=4, hash2_bits=10, sub_bytes=16384,
+                     cost_margin=0, cost_warm=64, hash2_ways=2, ins_limit=0, noisy_ways1=1, lane_cap_win=0, rowlen=-1, row_gate=1, exact_sel=1, group_subs=1, prime_win=512, cost_epoch=64, hash2_bytes=4, hash2_bits=10, sub_bytes=16384,
                      block_bytes=512 * 1024)
 
 

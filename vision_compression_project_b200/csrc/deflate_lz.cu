@@ -54,6 +54,7 @@ constexpr int kLzWarps = 2;           // warps (= sub-chunks) per CTA
 constexpr int kLaneCap = 16;          // compare depth of a hash candidate inside a lane (deeper only for tokens the parse selects)
 constexpr int kCostMaxLen = 8;
 constexpr int kCostWarm = 64;
+constexpr int kCostEpochLog2 = 6;     // the cost table is refreshed at the first window after every 64 tokens (deflate_model.c cost_epoch)
 constexpr unsigned kFull = 0xffffffffu;
 
 template <class Cfg>
@@ -61,6 +62,7 @@ struct __align__(16) WarpMem {
     uint32_t t3[1 << Cfg::HB3];
     uint32_t t6[1 << Cfg::HB6];
     uint32_t hist[160];          // 320 token counters, two 16-bit halves per word (a sub-chunk has at most kSubBytes tokens)
+    uint8_t clg[320];            // quarter-bit log2 of (count + 1) per token symbol, as of the last cost epoch (pricing of short matches)
 };
 
 static_assert(kSubBytes < 65536, "token counters are 16-bit");
@@ -276,9 +278,17 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
     int p = s;
     uint32_t ntok = 0;
     int score = 0;                                                               // EMA of literal tokens per window, x8
+    uint32_t cost_ep = 0; int lgN = 0;                                           // cost epoch of M.clg, and log2 of the token count it was taken at
     int A0 = ((p - 4) >> 7) << 7;                                                // may be -128: the pad in front of the stream is addressable
     uint32_t w0r = __ldg(S32 + (A0 >> 2) + lane), w1r = __ldg(S32 + (A0 >> 2) + 32 + lane), w2r = __ldg(S32 + (A0 >> 2) + 64 + lane);
     while (p < e) {
+        if ((ntok >> kCostEpochLog2) != cost_ep) {
+            // short matches are priced against literals with the token statistics of this sub-chunk: log2 tables, refreshed every 64
+            // tokens (exact counts per window cost 8 % of the kernel's instructions for 0.1 % of PNG size)
+            cost_ep = ntok >> kCostEpochLog2; lgN = ilog2x4(ntok + 1);
+            for (int i = lane; i < kHistSize; i += 32) M.clg[i] = (uint8_t)ilog2x4(hist_get(M, i) + 1);
+            __syncwarp();
+        }
         int ofs = p - 4 - A0;
         if (ofs >= 384) {                                                        // long jump: refill
             A0 = ((p - 4) >> 7) << 7; ofs = p - 4 - A0;
@@ -409,18 +419,17 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             else if (xbest) { bl = (int)(xbest >> 16); bd = 32768 - (int)(xbest & 0xFFFFu); }
             // price short matches against literals with the histogram as of the window start
             if (bl >= 3 && bl <= kCostMaxLen && ntok >= kCostWarm) {
-                const int lgN = ilog2x4(ntok + 1);
                 int lit = 0;
 #pragma unroll
                 for (int kk = 0; kk < kCostMaxLen; kk++) {
                     if (kk < bl) {
                         const uint32_t byte = (kk < 4 ? (cur4 >> (8 * kk)) : (nxt4 >> (8 * (kk - 4)))) & 0xFFu;
-                        lit += lgN - ilog2x4(hist_get(M, (int)byte) + 1);
+                        lit += lgN - (int)M.clg[byte];
                     }
                 }
                 const int ls = bl - 3, ds = dist_sym(bd);                         // bl <= 8: no length extra bits
                 const int dx = ds < 4 ? 0 : (ds >> 1) - 1;
-                const int mc = (lgN - ilog2x4(hist_get(M, 257 + ls) + 1)) + (lgN - ilog2x4(hist_get(M, 286 + ds) + 1)) + 4 * dx;
+                const int mc = (lgN - (int)M.clg[257 + ls]) + (lgN - (int)M.clg[286 + ds]) + 4 * dx;
                 if (mc >= lit) { bl = 0; bd = 0; }
             }
         }
