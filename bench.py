@@ -13,7 +13,8 @@ Contract (task statement §④):  python bench.py --gpus N --steps K --warmup W 
   * cpu_baseline / --impl reference = the reference's own CPU path (Pillow save + base64, oracle/pillow_path.py)
     on all host cores of this box, on the same 64 pages.
   * configs = the other BASELINE.json configs, each pixel-checked against the Pillow path outside the timed region:
-      C1 the reference's recorded output/page_1.png, one call;  C3 256 letter-300 pages -> LANCZOS 1568;  C5 the 48-type mix  (N = 1)
+      C1 the reference's recorded output/page_1.png, one call;  C3 256 letter-300 pages -> LANCZOS 1568;  C5 the 48-type mix;
+      S150 the service's default 150-DPI pages  (N = 1)
       c4  = the 2,000-page document (25 % photo pages) sharded by page range over the N ranks through sharding.py: STRONG scaling.
 """
 from __future__ import annotations
@@ -304,6 +305,7 @@ def run_ours(args):
         c4_arrs = fac.arrays(c4_specs(c4_lo, c4_hi), out=[c4_block[i].numpy() for i in range(m4)])
     side = {}
     if world == 1 and not args.headline_only:
+        side["S150"] = fac.arrays([(s_, "letter", 150, "RGB", s_ % 4 == 3) for s_ in range(64)])
         side["C3"] = fac.arrays(c3_specs(args.c3_pages))
         side["C5"] = fac.arrays(c5_specs())
     fac.close()
@@ -561,6 +563,9 @@ def run_ours(args):
                         "png_size_vs_pillow": ratio_, "pixel_checked_pages": len(idx),
                         "pillow_cpu_pages_per_s": cpu_rate, "cpu_sample": f"{len(idx)} of the pages on {cores} threads"}
             configs["C1"] = sub_config("C1", run_c1)
+            configs["S150"] = sub_config("S150", lambda: run_side(
+                "S150", side["S150"], {},
+                "S150: the service's default rasterisation (backend/app/config.py:57 DEFAULT_DPI = 150): 64 letter pages @150 DPI (1275x1650 RGB, every 4th photo-heavy), convert('RGB') + PNG + base64", 16))
             configs["C3"] = sub_config("C3", lambda: run_side(
                 "C3", side["C3"], {"max_side": MAX_SIDE},
                 f"C3: {len(side['C3'])} synthetic letter pages @300 DPI (2550x3300 RGB, every 4th photo-heavy) -> LANCZOS to {MAX_SIDE} px long edge (1212x1568) + PNG + base64", 16))

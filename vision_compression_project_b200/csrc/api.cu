@@ -9,6 +9,7 @@
 // Host work is planning only: geometry, Pillow's coefficient tables (double math, cached), arena carving.
 #include "../../include/vcprep.h"
 #include "vcp_internal.cuh"
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cctype>
@@ -100,6 +101,14 @@ struct HandleGuard {
 };
 #define LOCK_HANDLE(h) HandleGuard guard_(h); \
     if (!guard_.ok) return fail(VCP_EINVAL, "a streaming batch is in flight on this handle (finish it with vcp_batch_end first)")
+
+// NVTX ranges around the host-side phases of a batch (issue of a launch set, wait + hand-over, PNG decode), for nsys / Nsight timelines.
+// Header-only NVTX3: without a profiler attached a range is a call through a null function table.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+};
 
 int ensure_arena(Lane& L, size_t need) {
     if (need <= L.arena_cap) return 0;
@@ -381,6 +390,7 @@ enum RunMode { RUN_FULL = 0, RUN_STREAM = 1, RUN_FILTER_ONLY = 2, RUN_LZ_ONLY = 
 
 // Enqueues the whole launch set of a group on lane L (nothing here waits for the GPU).
 int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_opts& o, RunMode mode, GroupOut& out) {
+    NvtxRange nvtx_("vcp issue launch set");
     const int n = (int)plans.size();
     cudaStream_t st = L.stream;
     const bool stream_in = (mode == RUN_STREAM || mode == RUN_LZ_ONLY);
@@ -654,6 +664,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
 
 // Waits for a group's launch set and exposes its results block.
 int finish_group(vcp_handle* h, GroupOut& out) {
+    NvtxRange nvtx_("vcp wait launch set");
     Lane& L = *out.lane;
     const int n = out.n;
     CU(cudaStreamSynchronize(L.stream));
@@ -1013,6 +1024,7 @@ int vcp_batch_end(vcp_handle* h) {
 int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t* png_lens, int n,
                          void* out_pixels, uint64_t out_cap, int dst_device, vcp_decode_result* results) {
     if (!h || n < 0 || (n > 0 && (!pngs || !png_lens || !results || !out_pixels))) return fail(VCP_EINVAL, "bad arguments");
+    NvtxRange nvtx_("vcp_png_decode_batch");
     LOCK_HANDLE(h);
     CU(cudaSetDevice(h->device));
     std::vector<std::vector<Idat>> idats(n);
