@@ -447,7 +447,7 @@ int issue_group(vcp_handle* h, Lane& L, std::vector<PagePlan>& plans, const vcp_
     const size_t o_sub_hist = bump.take((size_t)nsub * kHistSize * 4 + 4);
     const size_t o_row_adler = bump.take((size_t)nrows * 4 + 4);
     const size_t o_row_busy = bump.take((size_t)nrows + 4);
-    const size_t o_lz_order = bump.take((size_t)nsub * 5 + 8);        // u32 order + u8 keys
+    const size_t o_lz_order = bump.take((size_t)nsub * 5 + 32 + ((size_t)nsub / 256 + 2) * 64 * 4);   // u32 order + u8 keys + per-CTA key counts of the stable sort
     const size_t o_page_adler = bump.take((size_t)n * 4);
     const size_t o_blk_code = bump.take((size_t)nblocks * kCodeStride * 2 + 4);
     const size_t o_blk_clen = bump.take((size_t)nblocks * kCodeStride + 4);

@@ -216,36 +216,44 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
 
     // ---- prime with the kPrimeBytes in front of the sub-chunk.  The history streams through 512-byte register blocks (one uint4
     //      per lane, two blocks ahead in flight).  A block is ONE insert step: a lane hashes its own 16 positions (its 16 bytes and
-    //      the first 3 of its neighbour's), reads their buckets, and after one barrier the highest position of every bucket wins
-    //      (atomicMax) and shifts the bucket once: newest = highest position of the block, older = newest in front of the block.
-    //      (Steps of 32 positions, like the main loop's, cost 16 barriers and twice the instructions per block for the same PNG
-    //      size within 0.1 %: tests/model/deflate_model.c prime_win.)  A block that is one repeated byte (white paper after
-    //      filtering: most of a text page) hashes every position to the same two buckets: one store per table.
+    //      the first 3 of its neighbour's) and reads their buckets; after one barrier the highest position of the block wins each
+    //      bucket (atomicMax).  The state to reach is: newest way = highest position of the last block that touches the bucket,
+    //      older way = highest position of the block that touched it before that (tests/model/deflate_model.c prime_win walks the
+    //      blocks forwards and shifts the bucket once per block).  The blocks are walked BACKWARDS here, nearest first: the first
+    //      block that touches a bucket fills the newest way, the second the older way, and every later one finds the bucket full
+    //      and issues nothing — a shared-memory atomic holds the load/store pipe 2 cycles per lane, and walking forwards spent
+    //      them on entries that the next blocks overwrote.  A block that is one repeated byte (white paper after filtering: most
+    //      of a text page) hashes every position to the same two buckets: one store per table.
     if (si == 0) {
         const int h0 = max(0, s - kPrimeBytes);                                  // multiple of 512 (s and kPrimeBytes are)
         const uint4* __restrict__ S128 = reinterpret_cast<const uint4*>(S);
-        uint4 bc = make_uint4(0, 0, 0, 0), bn = bc;
-        if (h0 < s) { bc = __ldg(S128 + (h0 >> 4) + lane); bn = __ldg(S128 + ((h0 + 512) >> 4) + lane); }
-        for (int b0 = h0; b0 < s; b0 += 512) {
-            const uint4 bf = __ldg(S128 + ((b0 + 1024) >> 4) + lane);            // <= 1.5 KiB past s: inside the stream or its pad
-            const uint32_t c00 = __shfl_sync(kFull, bc.x, 0), n00 = __shfl_sync(kFull, bn.x, 0);
+        const uint4 none = make_uint4(0, 0, 0, 0);
+        uint4 bc = none, bn = none;
+        uint32_t after0 = __ldg(S32 + (s >> 2));                                 // first word behind the block in hand
+        if (s - 512 >= h0) bc = __ldg(S128 + ((s - 512) >> 4) + lane);
+        if (s - 1024 >= h0) bn = __ldg(S128 + ((s - 1024) >> 4) + lane);
+        for (int b0 = s - 512; b0 >= h0; b0 -= 512) {
+            const uint4 bf = b0 - 1024 >= h0 ? __ldg(S128 + ((b0 - 1024) >> 4) + lane) : none;
+            const uint32_t c00 = __shfl_sync(kFull, bc.x, 0);
             if (__all_sync(kFull, bc.x == c00 && bc.y == c00 && bc.z == c00 && bc.w == c00) && c00 == __funnelshift_l(c00, c00, 8) &&
-                n00 == c00 && b0 + 516 <= F) {
+                after0 == c00 && b0 + 516 <= F) {
                 if (lane == 0) {
                     const uint32_t h3 = ((c00 & 0xFFFFFFu) * 0x9E3779B1u) >> (32 - HB3);
                     const uint32_t h6 = (c00 * 0x9E3779B1u) >> (32 - HB6);
-                    const uint32_t pos = (uint32_t)(b0 + 511 - base) << 16;
-                    M.t3[h3] = pos | (M.t3[h3] >> 16); M.t6[h6] = pos | (M.t6[h6] >> 16);
+                    const uint32_t pos = (uint32_t)(b0 + 511 - base);
+                    const uint32_t w3 = M.t3[h3], w6 = M.t6[h6];
+                    if (!(w3 >> 16)) M.t3[h3] = pos << 16; else if (!(w3 & 0xFFFFu)) M.t3[h3] = w3 | pos;
+                    if (!(w6 >> 16)) M.t6[h6] = pos << 16; else if (!(w6 & 0xFFFFu)) M.t6[h6] = w6 | pos;
                 }
                 __syncwarp();
-                bc = bn; bn = bf;
+                after0 = c00; bc = bn; bn = bf;
                 continue;
             }
-            // this lane's 16 bytes and the 4 behind them (the last lane's neighbour is lane 0 of the next block)
+            // this lane's 16 bytes and the 4 behind them (the last lane's neighbour is lane 0 of the block behind)
             uint32_t wd[5] = {bc.x, bc.y, bc.z, bc.w, 0u};
             {
-                const uint32_t nx = __shfl_down_sync(kFull, bc.x, 1), nb0 = __shfl_sync(kFull, bn.x, 0);
-                wd[4] = lane == 31 ? nb0 : nx;
+                const uint32_t nx = __shfl_down_sync(kFull, bc.x, 1);
+                wd[4] = lane == 31 ? after0 : nx;
             }
             const int q0 = b0 + 16 * lane;
             uint32_t hh[16], bb[16];
@@ -257,8 +265,11 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                if (q0 + k + 2 < F) atomicMax(&M.t3[hh[k]], ((uint32_t)(q0 + k - base) << 16) | (bb[k] >> 16));
+            for (int k = 0; k < 16; k++) {
+                const uint32_t pos = (uint32_t)(q0 + k - base);
+                if (q0 + k + 2 < F && !(bb[k] & 0xFFFFu))
+                    atomicMax(&M.t3[hh[k]], (bb[k] >> 16) ? (bb[k] | pos) : (pos << 16));
+            }
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const uint32_t cur4 = __funnelshift_r(wd[k >> 2], wd[(k >> 2) + 1], (k & 3) * 8);
@@ -267,10 +278,13 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
             }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                if (q0 + k + kH2Bytes <= F) atomicMax(&M.t6[hh[k]], ((uint32_t)(q0 + k - base) << 16) | (bb[k] >> 16));
+            for (int k = 0; k < 16; k++) {
+                const uint32_t pos = (uint32_t)(q0 + k - base);
+                if (q0 + k + kH2Bytes <= F && !(bb[k] & 0xFFFFu))
+                    atomicMax(&M.t6[hh[k]], (bb[k] >> 16) ? (bb[k] | pos) : (pos << 16));
+            }
             __syncwarp();
-            bc = bn; bn = bf;
+            after0 = c00; bc = bn; bn = bf;
         }
     }
 
@@ -559,9 +573,14 @@ __global__ void __launch_bounds__(kLzWarps * 32) k_lz(BatchD B) {
 
 // Work items sorted by a cost hint, heaviest first (longest-processing-time-first scheduling): a sub-chunk costs roughly in
 // proportion to the ink of the rows it covers (the PNG filter's winning |residual| sum; blank rows are one long run).
-// Counting sort with 64 keys: k_lz_keys bins the items (global histogram in B.counters[64..128)), k_lz_scatter places them
-// (cursors in B.counters[128..192)).  The order inside a key is arbitrary — it only changes scheduling, never the output.
+// Stable counting sort with 64 keys: k_lz_keys bins the items (global histogram in B.counters[64..128), one histogram per CTA
+// behind the keys), k_lz_scatter places them.  The order only changes scheduling, never the output.
 constexpr int kOrderKeys = 64;
+#ifndef VCP_ORDER_GROUP
+#define VCP_ORDER_GROUP 8
+#endif
+constexpr int kOrderGroup = VCP_ORDER_GROUP;              // consecutive sub-chunks that share one key (the heaviest of the group): a sub-chunk primes
+                                                          // its tables from the 16 KiB in front of it, which its neighbour reads at the same moment
 
 __device__ __forceinline__ int lz_item_key(const BatchD& B, int item) {
     const int sub = (int)B.item2sub[item];
@@ -577,30 +596,55 @@ __device__ __forceinline__ int lz_item_key(const BatchD& B, int item) {
     return seen ? min(kOrderKeys - 1, (busy * 8 / seen + 31) >> 5) : 0;       // scaled to 8 rows
 }
 
-__global__ void __launch_bounds__(256) k_lz_keys(BatchD B, uint8_t* __restrict__ keys) {
+__global__ void __launch_bounds__(256) k_lz_keys(BatchD B, uint8_t* __restrict__ keys, uint32_t* __restrict__ blkcnt) {
     __shared__ uint32_t cnt[kOrderKeys];
     if (threadIdx.x < kOrderKeys) cnt[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B.nitems) { const int k = lz_item_key(B, i); keys[i] = (uint8_t)k; atomicAdd(&cnt[k], 1u); }
+    int k = i < B.nitems ? lz_item_key(B, i) : 0;
+    for (int d = 1; d < kOrderGroup; d <<= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, d));     // neighbours travel together
+    if (i < B.nitems) { keys[i] = (uint8_t)k; atomicAdd(&cnt[k], 1u); }
     __syncthreads();
-    if (threadIdx.x < kOrderKeys && cnt[threadIdx.x]) atomicAdd(&B.counters[64 + threadIdx.x], cnt[threadIdx.x]);
+    if (threadIdx.x < kOrderKeys) {
+        blkcnt[(size_t)blockIdx.x * kOrderKeys + threadIdx.x] = cnt[threadIdx.x];
+        if (cnt[threadIdx.x]) atomicAdd(&B.counters[64 + threadIdx.x], cnt[threadIdx.x]);
+    }
 }
 
-__global__ void __launch_bounds__(256) k_lz_scatter(BatchD B, const uint8_t* __restrict__ keys) {
-    __shared__ uint32_t first[kOrderKeys];                  // first slot of every key, heaviest key first
-    if (threadIdx.x == 0) { uint32_t o = 0; for (int k = kOrderKeys - 1; k >= 0; k--) { first[k] = o; o += B.counters[64 + k]; } }
+// Stable placement: inside a key the items keep stream order, so the sub-chunks a warp primes its tables from (the 16 KiB in front of
+// its own) were parsed moments before by a neighbouring warp and are still in L2, and so are the rows above for the row probe.
+__global__ void __launch_bounds__(256) k_lz_scatter(BatchD B, const uint8_t* __restrict__ keys, const uint32_t* __restrict__ blkcnt) {
+    __shared__ uint32_t base[kOrderKeys];                   // first slot of this CTA's items of every key (heaviest key first)
+    __shared__ uint32_t wcnt[8][kOrderKeys];                // per warp: items of the key in the warps in front of it
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < 8 * kOrderKeys; j += 256) (&wcnt[0][0])[j] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B.nitems) { const int k = keys[i]; B.lz_order[first[k] + atomicAdd(&B.counters[128 + k], 1u)] = (uint32_t)i; }
+    const int k = i < B.nitems ? (int)keys[i] : 255;
+    const uint32_t same = __match_any_sync(0xffffffffu, k);
+    const int lower = __popc(same & ((1u << lane) - 1u));
+    if (k != 255 && lower == 0) wcnt[warp][k] = (uint32_t)__popc(same);
+    __syncthreads();
+    if (threadIdx.x < kOrderKeys) {
+        const int kk = threadIdx.x;
+        uint32_t o = 0;
+        for (int q = kOrderKeys - 1; q > kk; q--) o += B.counters[64 + q];          // heavier keys come first
+        for (int b2 = 0; b2 < (int)blockIdx.x; b2++) o += blkcnt[(size_t)b2 * kOrderKeys + kk];
+        base[kk] = o;
+        uint32_t run = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t t = wcnt[w][kk]; wcnt[w][kk] = run; run += t; }
+    }
+    __syncthreads();
+    if (k != 255) B.lz_order[base[k] + wcnt[warp][k] + lower] = (uint32_t)i;
 }
 
 int launch_lz_order(const BatchD& b, cudaStream_t st) {
     if (b.nitems == 0 || !b.lz_order || !b.row_busy) return 0;
-    uint8_t* keys = reinterpret_cast<uint8_t*>(b.lz_order + b.nitems);         // the order buffer has room for the keys behind it
+    uint8_t* keys = reinterpret_cast<uint8_t*>(b.lz_order + b.nitems);         // the order buffer has room for the keys and the per-CTA counts behind it
+    uint32_t* blkcnt = reinterpret_cast<uint32_t*>(keys + ((b.nitems + 15) & ~15));
     const int ctas = (b.nitems + 255) / 256;
-    k_lz_keys<<<ctas, 256, 0, st>>>(b, keys);
-    k_lz_scatter<<<ctas, 256, 0, st>>>(b, keys);
+    k_lz_keys<<<ctas, 256, 0, st>>>(b, keys, blkcnt);
+    k_lz_scatter<<<ctas, 256, 0, st>>>(b, keys, blkcnt);
     return 2;
 }
 
