@@ -1,5 +1,5 @@
 """Profiling target: one device-resident launch set per page class, so that an ncu capture sees every kernel of the path once with
-realistic sizes.  usage: ncu_target.py [c2|c3|c5|dec|all]   (C2 = 64 letter-200 text pages; C3 = 16 letter-300 pages -> 1568;
+realistic sizes.  usage: ncu_target.py [c2|c3|c5|dec|dec8p|dec64t|all]   (C2 = 64 letter-200 text pages; C3 = 16 letter-300 pages -> 1568;
 C5 = 8 pages incl. 600-DPI (reduce) and an RGBA page (convert))."""
 import sys
 import numpy as np, torch
@@ -35,6 +35,18 @@ if __name__ == "__main__":
             ts = [torch.from_numpy(x).cuda() for x in a]
             rgba = torch.from_numpy(np.concatenate([a[0], np.full(a[0].shape[:2] + (1,), 255, np.uint8)], axis=2)).cuda()
             print("c5", {k: round(v, 3) for k, v in run(eng, ts + [rgba], {"max_side": 1568, "reducing_gap": 2.0}).items() if k.startswith("ms_")})
+        if what in ("dec8p", "dec64t"):                       # decode only: 8 photo-heavy / 64 text pages, this library's PNGs
+            import vision_compression_project_b200 as V
+            n, photo = (8, True) if what == "dec8p" else (64, False)
+            a = fac.arrays([(i, "letter", 200, "RGB", photo) for i in range(n)])
+            ours = [r.png for r in V.prepare_pages(a, want_base64=False)]
+            import time
+            for _ in range(3):
+                torch.cuda.synchronize(); t = time.perf_counter()
+                out = eng.decode_pages(ours, to_device=True)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t
+            assert bytes(out[3].cpu().numpy().tobytes()) == a[3].tobytes()
+            print(what, "ok", f"{n / dt:.0f} pages/s ({dt * 1e3:.2f} ms)")
         if what in ("dec",):
             import io
             from PIL import Image

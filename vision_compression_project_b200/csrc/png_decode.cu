@@ -36,6 +36,7 @@
 //                  range from a ticket, so a band only ever waits on bands that are already running.
 // Every loop is bounded by the stream / output length: malformed input ends in a status, never in a hang.
 #include "vcp_internal.cuh"
+#include <type_traits>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -1136,12 +1137,12 @@ int launch_inflate(const DecBatchD& b, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------ un-filter
 namespace {
 
-constexpr int kUfPitch = 136;             // bytes per staged row: up to 3 + 32 pixels x 4 channels, as 34 words (bank = 2 * lane + const)
+constexpr int kUfW = 33;                  // words per staged row: up to 3 + 32 pixels x 4 channels bytes; odd pitch: lane r on word k of row r hits bank r + k
 
 struct UfMem {                            // views of one warp's staging buffers (separate __shared__ arrays: loads of `in` may pass stores to `out`)
-    uint32_t (*in)[kUfPitch / 4];         // row r: the aligned words that cover its 32 pixels of this chunk
-    uint8_t (*out)[kUfPitch];
-    uint32_t* up;                         // the same for the last row of the band above
+    uint32_t (*in)[kUfW];                 // row r: the aligned words that cover its 32 pixels of this chunk
+    uint32_t (*out)[kUfW];                // row r: word 0 = the last word of the previous chunk, words 1 .. 8 * BPP = this chunk's pixels
+    uint32_t* up;                         // like `in`, for the last row of the band above
 };
 
 // aligned word `k` of the run that starts at byte address a (a itself may be misaligned); 0 outside [lo, hi)
@@ -1149,6 +1150,57 @@ __device__ __forceinline__ uint32_t word_at(const uint8_t* a, int k, const uint8
     const uint8_t* w = a - ((uintptr_t)a & 3) + 4 * k;
     if (w < lo || w + 4 > hi) return 0u;
     return l2 ? __ldcg(reinterpret_cast<const uint32_t*>(w)) : __ldg(reinterpret_cast<const uint32_t*>(w));
+}
+
+// ---- pixels as packed bytes (one register, channel k in byte k) and as 16-bit pairs (channels 0,1 / 2,3 in the halves of two registers):
+//      sm_100a has VIADD.16x2, VIMNMX.16x2 and VABSDIFF4 but no packed byte compare, and 8-bit channels need 10 bits for Paeth's a + b - 2c.
+template <int BPP> struct UfPx { uint32_t v[(BPP + 1) / 2]; };
+
+template <int BPP> __device__ __forceinline__ UfPx<BPP> uf_unpack(uint32_t p) {
+    UfPx<BPP> u;
+    u.v[0] = __byte_perm(p, 0u, BPP == 1 ? 0x4440u : 0x4140u);
+    if (BPP >= 3) u.v[(BPP + 1) / 2 - 1] = __byte_perm(p, 0u, BPP == 3 ? 0x4442u : 0x4342u);
+    return u;
+}
+template <int BPP> __device__ __forceinline__ uint32_t uf_pack(const UfPx<BPP>& u) {
+    return BPP >= 3 ? __byte_perm(u.v[0], u.v[(BPP + 1) / 2 - 1], 0x6420u) : __byte_perm(u.v[0], 0u, 0x4420u);
+}
+// pixel m (0..3) of the 4 * BPP dense bytes in d[]; bytes above the pixel's channels are whatever follows
+template <int BPP> __device__ __forceinline__ uint32_t uf_px_get(const uint32_t* d, int m) {
+    if (BPP == 1) return d[0] >> (8 * m);
+    if (BPP == 2) return (m & 1) ? d[m >> 1] >> 16 : d[m >> 1];
+    if (BPP == 4) return d[m];
+    return m == 0 ? d[0] : m == 1 ? __funnelshift_r(d[0], d[1], 24) : m == 2 ? __funnelshift_r(d[1], d[2], 16) : d[2] >> 8;
+}
+// the 4 * BPP dense bytes of four packed pixels
+template <int BPP> __device__ __forceinline__ void uf_px_put(const uint32_t* o, uint32_t* w) {
+    if (BPP == 1) w[0] = __byte_perm(__byte_perm(o[0], o[1], 0x0040u), __byte_perm(o[2], o[3], 0x0040u), 0x5410u);
+    if (BPP == 2) { w[0] = __byte_perm(o[0], o[1], 0x5410u); w[1] = __byte_perm(o[2], o[3], 0x5410u); }
+    if (BPP == 3) { w[0] = __byte_perm(o[0], o[1], 0x4210u); w[1] = __byte_perm(o[1], o[2], 0x5421u); w[2] = __byte_perm(o[2], o[3], 0x6542u); }
+    if (BPP == 4) { w[0] = o[0]; w[1] = o[1]; w[2] = o[2]; w[3] = o[3]; }
+}
+// all-ones in a half where x >= y (halves 0 .. 32767): the borrow-free difference x + 0x8000 - y has its top bit set there
+__device__ __forceinline__ uint32_t uf_ge16(uint32_t x, uint32_t y) {
+    uint32_t m;                                   // prmt with selector bit 3 replicates the byte's sign (__byte_perm masks that bit away)
+    asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(m) : "r"(x + 0x80008000u - y));
+    return m;
+}
+
+// one un-filter step on two channels: a = left, b = above, c = above-left, r = filtered bytes (halves 0..255).  None / Sub / Up are Paeth
+// with the unused neighbours masked to 0 (Paeth(a,0,0) = a, Paeth(0,b,0) = b); Avg is selected over it by mask.  ZipDecode.c / libpng's
+// rule: pa = |b-c|, pb = |a-c|, pc = |a+b-2c|; a unless pb < pa (then b), c if pc is below the smaller of the two.
+template <bool HAS_AVG>
+__device__ __forceinline__ uint32_t uf_step16(uint32_t a, uint32_t b, uint32_t c, uint32_t r, uint32_t ma, uint32_t mb, uint32_t mc, uint32_t mavg) {
+    const uint32_t ae = a & ma, be = b & mb, ce = c & mc;
+    const uint32_t pa = __vabsdiffu4(be, ce), pb = __vabsdiffu4(ae, ce);
+    const uint32_t s = ae + be, c2 = ce + ce;
+    const uint32_t pc = __vmaxu2(s, c2) - __vminu2(s, c2);
+    const uint32_t keep_a = uf_ge16(pb, pa);
+    const uint32_t ab = (ae & keep_a) | (be & ~keep_a);
+    const uint32_t keep_ab = uf_ge16(pc, __vminu2(pa, pb));
+    uint32_t pred = (ab & keep_ab) | (ce & ~keep_ab);
+    if (HAS_AVG) pred = (pred & ~mavg) | (((a + b) >> 1) & mavg);
+    return (r + pred) & 0x00FF00FFu;
 }
 
 template <int BPP>
@@ -1165,6 +1217,7 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
     if (ft > 4) { *bad = 1; ft = 0; }
     const int nchunks = (W + 31 + 31) / 32;
     constexpr int NW = (3 + 32 * BPP + 3) / 4;                                    // words per staged row (<= 33)
+    constexpr int NR = (BPP + 1) / 2;
     const long long rstep = (long long)nb + 1 - BPP;                              // row r starts r pixels behind row r - 1
     uint32_t pre[32], pre_x = 0, pre_u = 0, pre_ux = 0;                           // the next chunk, in flight while this one computes
     uint32_t seen = 0;                                                            // lane 0: last value read from the flag of the band above
@@ -1195,7 +1248,7 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
     };
     auto stage = [&]() {
         M.up[lane] = pre_u;
-        if (BPP == 4 && lane == 0) M.up[32] = pre_ux;
+        if (lane == 0) M.up[32] = BPP == 4 ? pre_ux : 0u;
 #pragma unroll
         for (int r = 0; r < 32; r++) M.in[r][lane] = pre[r];
         if (BPP == 4) M.in[lane][32] = pre_x;
@@ -1204,82 +1257,105 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
 
     fetch(0);
     stage();
-    uint32_t cur = 0, bprev = 0;              // packed channels: my pixel x-1, the pixel above x-1
-    const int ka = ft == 1 ? -1 : 0, kb = ft == 2 ? -1 : 0, kavg = ft == 3 ? -1 : 0, kp = ft == 4 ? -1 : 0;
+    // filter type as masks: which neighbours the Paeth core sees (none: None; a: Sub; b: Up; all: Paeth), and Avg
+    const uint32_t ma = (ft == 1 || ft == 4) ? ~0u : 0u, mb = (ft == 2 || ft == 4) ? ~0u : 0u, mc = ft == 4 ? ~0u : 0u, mavg = ft == 3 ? ~0u : 0u;
     const bool simple = __all_sync(kFull, ft <= 2);
+    const bool has_avg = __any_sync(kFull, ft == 3);
+    const int in_sh = 8 * (int)((uintptr_t)(F + (unsigned long long)y * (nb + 1) + 1 + (long long)(0 - lane) * BPP) & 3);   // the same in every chunk
+    uint32_t curp = 0;                        // packed: my pixel x - 1
+    UfPx<BPP> au, cu;                         // 16-bit pairs: my pixel x - 1, the pixel above x - 1
+#pragma unroll
+    for (int q = 0; q < NR; q++) au.v[q] = cu.v[q] = 0;
+    M.out[lane][0] = 0;
     for (int j = 0; j < nchunks; j++) {
         if (j + 1 < nchunks) fetch(j + 1);
-        const uint8_t* inb = reinterpret_cast<const uint8_t*>(M.in[lane]) +
-                             ((uintptr_t)(F + (unsigned long long)y * (nb + 1) + 1 + (long long)(32 * j - lane) * BPP) & 3);
         // lane s holds pixel s of the row above (packed), handed to lane 0 by a broadcast at step s
         uint32_t upv = 0;
         if (band > 0) {
-            const uint8_t* upb = reinterpret_cast<const uint8_t*>(M.up) + ((uintptr_t)(X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP) & 3);
-#pragma unroll
-            for (int ch = 0; ch < BPP; ch++) upv |= (uint32_t)upb[lane * BPP + ch] << (8 * ch);
+            const int ub = (int)((uintptr_t)(X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP) & 3) + lane * BPP;
+            upv = __funnelshift_r(M.up[ub >> 2], M.up[(ub >> 2) + 1], 8 * (ub & 3));
         }
-        uint8_t* outb = M.out[lane];
-        if (simple) {
-            // no Avg / Paeth row in the band (blank paper is all Up): the predictor is a or b, four channels at a time
-            const uint32_t ma = (uint32_t)ka, mb = (uint32_t)kb;
-#pragma unroll 8
-            for (int s = 0; s < 32; s++) {
-                const int x = 32 * j + s - lane;
-                const uint32_t bs = __shfl_up_sync(kFull, cur, 1), b0 = __shfl_sync(kFull, upv, s);
-                const uint32_t b = lane == 0 ? b0 : bs;
-                uint32_t r = 0;
+        const uint32_t* inw = M.in[lane];
+        uint32_t* outw = M.out[lane] + 1;
+        const bool ramp = j == 0;             // only in the first chunk a lane may not have started (x < 0): left and upper-left of pixel 0 are 0
+        uint32_t wprev = inw[0];
+        auto body = [&](auto simple_c, auto avg_c) {
+#pragma unroll 1
+            for (int i = 0; i < 8; i++) {
+                uint32_t d[BPP], o[4];
 #pragma unroll
-                for (int ch = 0; ch < BPP; ch++) r |= (uint32_t)inb[s * BPP + ch] << (8 * ch);
-                const uint32_t o = __vadd4(r, (cur & ma) | (b & mb));
+                for (int k = 0; k < BPP; k++) { const uint32_t w = inw[BPP * i + k + 1]; d[k] = __funnelshift_r(wprev, w, in_sh); wprev = w; }
 #pragma unroll
-                for (int ch = 0; ch < BPP; ch++) outb[s * BPP + ch] = (uint8_t)(o >> (8 * ch));
-                cur = x < 0 ? 0u : o;
-                bprev = x < 0 ? 0u : b;
+                for (int m = 0; m < 4; m++) {
+                    const int sidx = 4 * i + m;
+                    const uint32_t bs = __shfl_up_sync(kFull, curp, 1), b0 = __shfl_sync(kFull, upv, sidx);
+                    const uint32_t bp = lane == 0 ? b0 : bs;
+                    const uint32_t rp = uf_px_get<BPP>(d, m);
+                    if (decltype(simple_c)::value) {
+                        // no Avg / Paeth row in the band (blank paper is all Up): the predictor is a or b, four channels at a time
+                        o[m] = __vadd4(rp, (curp & ma) | (bp & mb));
+                    } else {
+                        const UfPx<BPP> bu = uf_unpack<BPP>(bp), ru = uf_unpack<BPP>(rp);
+                        UfPx<BPP> ou;
+#pragma unroll
+                        for (int q = 0; q < NR; q++) ou.v[q] = uf_step16<decltype(avg_c)::value>(au.v[q], bu.v[q], cu.v[q], ru.v[q], ma, mb, mc, mavg);
+                        o[m] = uf_pack<BPP>(ou);
+                        au = ou; cu = bu;
+                    }
+                    curp = o[m];
+                    if (ramp && 32 * j + sidx - lane < 0) {
+                        curp = 0;
+#pragma unroll
+                        for (int q = 0; q < NR; q++) au.v[q] = cu.v[q] = 0;
+                    }
+                }
+                uint32_t w[BPP];
+                uf_px_put<BPP>(o, w);
+#pragma unroll
+                for (int k = 0; k < BPP; k++) outw[BPP * i + k] = w[k];
             }
-        } else
-#pragma unroll 8
-        for (int s = 0; s < 32; s++) {
-            const int x = 32 * j + s - lane;
-            const uint32_t bs = __shfl_up_sync(kFull, cur, 1), b0 = __shfl_sync(kFull, upv, s);
-            const uint32_t b = lane == 0 ? b0 : bs;
-            uint32_t o = 0;
-#pragma unroll
-            for (int ch = 0; ch < BPP; ch++) {                // branch-free: the filter type differs from lane to lane
-                const int a = (cur >> (8 * ch)) & 255, bb = (b >> (8 * ch)) & 255, c = (bprev >> (8 * ch)) & 255;
-                const int pa = abs(bb - c), pb = abs(a - c), pc = abs(a + bb - 2 * c);
-                const int t = pb <= pc ? bb : c;
-                const int paeth = (pa <= pb) & (pa <= pc) ? a : t;
-                const int pred = (a & ka) | (bb & kb) | (((a + bb) >> 1) & kavg) | (paeth & kp);
-                const int v = ((int)inb[s * BPP + ch] + pred) & 255;
-                outb[s * BPP + ch] = (uint8_t)v;
-                o |= (uint32_t)v << (8 * ch);
-            }
-            cur = x < 0 ? 0u : o;                             // not started: left and upper-left of pixel 0 are 0
-            bprev = x < 0 ? 0u : b;
-        }
+        };
+        if (simple) body(std::true_type{}, std::false_type{});
+        else if (has_avg) body(std::false_type{}, std::true_type{});
+        else body(std::false_type{}, std::false_type{});
         __syncwarp();
+        // ---- copy out, a row at a time.  Inside a row whole aligned words go out: the word that straddles the start of this chunk is
+        //      completed from the previous chunk's last word (out[r][0]), the one that straddles its end waits for the next chunk.
+        //      Chunks that touch either end of the row, and the band's last row (the band below reads it as soon as the flag
+        //      says so), are written byte by byte, including the three bytes in front that an earlier chunk may have left.
         for (int r = 0; r < 32; r++) {
             if (y0 + r >= H) break;
             uint8_t* dst = X + (unsigned long long)(y0 + r) * nb;
-            const int g0 = (32 * j - r) * BPP;
+            const int x0 = 32 * j - r;
+            const int g0 = x0 * BPP;
+            if (x0 >= 3 && x0 + 32 <= W && r != 31) {
+                const int mis = (int)((uintptr_t)(dst + g0) & 3);
+                if (lane < 8 * BPP) {
+                    const uint32_t v = __funnelshift_rc(M.out[r][lane], M.out[r][lane + 1], 8 * (4 - mis));
+                    *reinterpret_cast<uint32_t*>(dst + g0 - mis + 4 * lane) = v;
+                }
+            } else {
+                const uint8_t* ob = reinterpret_cast<const uint8_t*>(M.out[r]) + 1;      // byte 3 of the carry word = byte -3 of the chunk
 #pragma unroll
-            for (int i = 0; i < BPP; i++) {
-                const int bi = lane + 32 * i, gb = g0 + bi;
-                if (gb >= 0 && gb < nb) dst[gb] = M.out[r][bi];
+                for (int i = 0; i < BPP + 1; i++) {
+                    const int bi = lane + 32 * i, gb = g0 - 3 + bi;
+                    if (bi < 32 * BPP + 3 && gb >= 0 && gb < nb) dst[gb] = ob[bi];
+                }
             }
         }
         __syncwarp();
         if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + band), "r"((uint32_t)(j + 1)) : "memory");
-        if (j + 1 < nchunks) stage();
+        M.out[lane][0] = M.out[lane][8 * BPP];
+        if (j + 1 < nchunks) stage(); else __syncwarp();
     }
 }
 
 }  // namespace
 
 __global__ void __launch_bounds__(32) k_unfilter(const DecBatchD b) {
-    __shared__ uint32_t s_in[32][kUfPitch / 4];
-    __shared__ uint8_t s_out[32][kUfPitch];
-    __shared__ uint32_t s_up[kUfPitch / 4];
+    __shared__ uint32_t s_in[32][kUfW];
+    __shared__ uint32_t s_out[32][kUfW];
+    __shared__ uint32_t s_up[kUfW + 1];
     // One band per CTA (a finished band frees its slot at once).  Bands are handed out by ticket, band-major over the pages of
     // the batch (band 0 of every page, then band 1, ...): a band only waits on one that holds an earlier ticket, and the resident
     // CTAs are the pipeline fronts of all pages rather than all bands of a few.
