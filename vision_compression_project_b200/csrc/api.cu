@@ -1112,7 +1112,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             if (zl >= (1ull << 28) || idats[i0 + j].size() > (1u << 20)) { results[i0 + j].status = D.status = fail(VCP_EINVAL, "PNG %d: too large", i0 + j); continue; }
             D.zlen = zl;
             s_z[j] = zoff_total; zoff_total += align_up(zl + 64, 256);
-            o_f[j] = bump.take((size_t)D.filt_len + 16);
+            o_f[j] = bump.take((size_t)D.filt_len + 16 + 512);          // k_unfilter's TMA rows read up to 62 pixels + a granule past the last row
             o_s[j] = bump.take(((size_t)D.filt_len + 16) * 2);
             nbands += (D.h + 31) / 32;
             // parse units: every IDAT start, plus up to kMaxCand block headers the scan finds on the device.  A parse can produce at

@@ -1137,13 +1137,22 @@ int launch_inflate(const DecBatchD& b, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------ un-filter
 namespace {
 
-constexpr int kUfW = 33;                  // words per staged row: up to 3 + 32 pixels x 4 channels bytes; odd pitch: lane r on word k of row r hits bank r + k
+constexpr int kUfInW = 36;                // words per staged input row: a TMA copy of whole 16-byte granules around the row's 32 pixels (<= 15 + 128 bytes)
+constexpr int kUfOutW = 33;               // words per staged output row; odd pitch: lane r on word k of row r hits bank r + k
+constexpr int kUfSin = 3, kUfSout = 2;    // stages of the input / output rings
 
-struct UfMem {                            // views of one warp's staging buffers (separate __shared__ arrays: loads of `in` may pass stores to `out`)
-    uint32_t (*in)[kUfW];                 // row r: the aligned words that cover its 32 pixels of this chunk
-    uint32_t (*out)[kUfW];                // row r: word 0 = the last word of the previous chunk, words 1 .. 8 * BPP = this chunk's pixels
-    uint32_t* up;                         // like `in`, for the last row of the band above
+struct __align__(16) UfSmem {
+    uint32_t in[kUfSin][32][kUfInW];      // row r of a stage: the 16-byte granules that cover its 32 pixels of the chunk
+    uint32_t up[kUfSin][36];              // the aligned words that cover the same 32 pixels of the last row of the band above
+    uint32_t out[kUfSout][32][kUfOutW];   // row r: the chunk's pixels, byte 0 = first pixel
+    uint32_t carry[32];                   // row r: the last word of the previous chunk (its tail may still be owed to global memory)
+    uint64_t in_full[kUfSin], in_empty[kUfSin], out_full[kUfSout], out_empty[kUfSout];
+    uint32_t ticket;
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 
 // aligned word `k` of the run that starts at byte address a (a itself may be misaligned); 0 outside [lo, hi)
 __device__ __forceinline__ uint32_t word_at(const uint8_t* a, int k, const uint8_t* lo, const uint8_t* hi, bool l2) {
@@ -1203,83 +1212,131 @@ __device__ __forceinline__ uint32_t uf_step16(uint32_t a, uint32_t b, uint32_t c
     return (r + pred) & 0x00FF00FFu;
 }
 
+// One band of 32 rows, three warps.  Warp 0 computes: lane = row, lane l runs l pixels behind lane l - 1, so the pixel above arrives by
+// shuffle and the band advances 32 pixels (a chunk) at a time.  Warp 1 loads: per chunk one 1-D TMA copy per row into a three-stage
+// ring (mbarrier complete_tx), and the row above the band from L2 once the band above has published it (acquire / release flag).
+// Warp 2 stores finished chunks from a two-stage ring to global memory as aligned words and publishes the band's progress.  The warps
+// meet only at mbarriers, so loading chunk j + 2, computing chunk j + 1 and storing chunk j overlap.
 template <int BPP>
-__device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32_t* __restrict__ flags /* of this page */, int* bad, bool nowait) {
-    const int lane = threadIdx.x & 31;
+__device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* __restrict__ flags /* of this page */, int* bad, bool nowait) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = P.w, nb = W * BPP, H = P.h;
     const int y0 = band * 32, y = y0 + lane;
     const bool row_ok = y < H;
     const uint8_t* __restrict__ F = P.filt;
     uint8_t* __restrict__ X = P.pix;
-    const uint8_t* Fend = F + ((P.filt_len + 3ull) & ~3ull);                      // both buffers are 256-byte aligned with slack behind
-    const uint8_t* Xend = X + (((unsigned long long)nb * H + 3ull) & ~3ull);
-    int ft = row_ok ? F[(unsigned long long)y * (nb + 1)] : 0;
-    if (ft > 4) { *bad = 1; ft = 0; }
     const int nchunks = (W + 31 + 31) / 32;
-    constexpr int NW = (3 + 32 * BPP + 3) / 4;                                    // words per staged row (<= 33)
     constexpr int NR = (BPP + 1) / 2;
-    const long long rstep = (long long)nb + 1 - BPP;                              // row r starts r pixels behind row r - 1
-    uint32_t pre[32], pre_x = 0, pre_u = 0, pre_ux = 0;                           // the next chunk, in flight while this one computes
-    uint32_t seen = 0;                                                            // lane 0: last value read from the flag of the band above
+    // row `lane`, chunk j: its 32 pixels start at a0 + 32 * BPP * j (x = 32 j - lane: lane l runs l pixels behind lane l - 1)
+    const uint8_t* a0 = F + (unsigned long long)y * (nb + 1) + 1 - (long long)lane * BPP;
+    const int ioff = (int)((uintptr_t)a0 & 15);                                   // the same in every chunk: a chunk is 32 * BPP bytes
+    const uint32_t tma_bytes = row_ok ? (uint32_t)((ioff + 32 * BPP + 15) & ~15) : 0u;
 
-    auto fetch = [&](int j) {
-        if (band > 0) {                       // the band above must have finished the pixels lane 0 will read in chunk j
-            const uint32_t need = (uint32_t)min(j + 2, nchunks);
-            if (lane == 0 && seen < need) {       // acquire load: what the band above stored before its release is visible after it
-                const uint32_t* f = flags + band - 1;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-                    if (seen >= need || nowait) break;
-                    __nanosleep(100);
-                } while (true);
+    if (warp == 2) {
+        // ------------------------------------------------------------------ stores
+        // A chunk goes out a row at a time.  Inside a row whole aligned words are written: the word that straddles the start of the chunk
+        // is completed from the previous chunk's last word (carry), the one that straddles its end waits for the next chunk.  Chunks
+        // that touch either end of the row, and the band's last row, are written byte by byte, including the three bytes in front that
+        // an earlier chunk may have left.  The last row goes first and the band's progress is published right behind it: it is all the
+        // band below reads, and the release only has to wait for those few stores (lane 31 issues it: it has no word in the word path).
+        S.carry[lane] = 0;
+        __syncwarp();
+        auto store_row = [&](int so, int j, int r) {
+            uint8_t* dst = X + (unsigned long long)(y0 + r) * nb;
+            const int x0 = 32 * j - r;
+            const int g0 = x0 * BPP;
+            if (x0 >= 3 && x0 + 32 <= W && r != 31) {
+                const int mis = (int)((uintptr_t)(dst + g0) & 3);
+                if (lane < 8 * BPP) {
+                    const uint32_t lo = lane ? S.out[so][r][lane - 1] : S.carry[r];
+                    const uint32_t v = __funnelshift_rc(lo, S.out[so][r][lane], 8 * (4 - mis));
+                    *reinterpret_cast<uint32_t*>(dst + g0 - mis + 4 * lane) = v;
+                }
+            } else {
+                const uint8_t* cb = reinterpret_cast<const uint8_t*>(&S.carry[r]) + 1;   // bytes -3 .. -1 of the chunk
+                const uint8_t* ob = reinterpret_cast<const uint8_t*>(S.out[so][r]);
+#pragma unroll
+                for (int i = 0; i < BPP + 1; i++) {
+                    const int bi = lane + 32 * i, gb = g0 - 3 + bi;
+                    if (bi < 32 * BPP + 3 && gb >= 0 && gb < nb) dst[gb] = bi < 3 ? cb[bi] : ob[bi - 3];
+                }
+            }
+        };
+        const int nrows = min(32, H - y0);
+        for (int j = 0; j < nchunks; j++) {
+            const int so = j % kUfSout;
+            mbar_wait(&S.out_full[so], (uint32_t)(j / kUfSout) & 1u);
+            if (nrows == 32) store_row(so, j, 31);
+            __syncwarp();
+            if (lane == 31) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + band), "r"((uint32_t)(j + 1)) : "memory");
+#pragma unroll 4
+            for (int r = 0; r < min(nrows, 31); r++) store_row(so, j, r);
+            __syncwarp();
+            S.carry[lane] = S.out[so][lane][8 * BPP - 1];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.out_empty[so]);
+        }
+        return;
+    }
+    if (warp == 1) {
+        // ------------------------------------------------------------------ loads (up to kUfSin chunks ahead of the compute warp)
+        uint32_t total_tx = tma_bytes;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) total_tx += __shfl_xor_sync(kFull, total_tx, d);
+        const uint8_t* Xend = X + (((unsigned long long)nb * H + 3ull) & ~3ull);   // the buffer is 256-byte aligned with slack behind
+        uint32_t seen = 0;                                                        // lane 0: last value read from the flag of the band above
+        for (int j = 0; j < nchunks; j++) {
+            const int s = j % kUfSin;
+            mbar_wait(&S.in_empty[s], ((uint32_t)(j / kUfSin) & 1u) ^ 1u);
+            if (row_ok) bulk_g2s(&S.in[s][lane][0], a0 + (long long)32 * BPP * j - ioff, tma_bytes, &S.in_full[s]);
+            if (band > 0) {                   // the band above must have stored the pixels lane 0 will need in chunk j
+                const uint32_t need = (uint32_t)min(j + 2, nchunks);
+                if (lane == 0 && seen < need) {   // acquire load: what the band above stored before its release is visible after it
+                    const uint32_t* f = flags + band - 1;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                        if (seen >= need || nowait) break;
+                        __nanosleep(32);
+                    } while (true);
+                }
+                __syncwarp();
+                const uint8_t* u = X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP;
+                S.up[s][lane] = word_at(u, lane, X, Xend, true);
+                if (lane == 0) S.up[s][32] = BPP == 4 ? word_at(u, 32, X, Xend, true) : 0u;
             }
             __syncwarp();
-            const uint8_t* u = X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP;
-            pre_u = word_at(u, lane, X, Xend, true);
-            if (BPP == 4 && lane == 0) pre_ux = word_at(u, 32, X, Xend, true);
+            if (lane == 0) mbar_expect_tx(&S.in_full[s], total_tx);                 // the one arrival of this phase + the bytes in flight
         }
-        const uint8_t* a = F + (unsigned long long)y0 * (nb + 1) + 1 + (long long)32 * j * BPP;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            pre[r] = (y0 + r < H && lane < NW) ? word_at(a, lane, F, Fend, false) : 0u;
-            if (BPP == 4 && lane == r) pre_x = (y0 + r < H) ? word_at(a, 32, F, Fend, false) : 0u;   // word 32 of row r goes through lane r
-            a += rstep;
-        }
-    };
-    auto stage = [&]() {
-        M.up[lane] = pre_u;
-        if (lane == 0) M.up[32] = BPP == 4 ? pre_ux : 0u;
-#pragma unroll
-        for (int r = 0; r < 32; r++) M.in[r][lane] = pre[r];
-        if (BPP == 4) M.in[lane][32] = pre_x;
-        __syncwarp();
-    };
+        return;
+    }
 
-    fetch(0);
-    stage();
+    // ---------------------------------------------------------------------- compute
+    int ft = row_ok ? F[(unsigned long long)y * (nb + 1)] : 0;
+    if (ft > 4) { *bad = 1; ft = 0; }
     // filter type as masks: which neighbours the Paeth core sees (none: None; a: Sub; b: Up; all: Paeth), and Avg
     const uint32_t ma = (ft == 1 || ft == 4) ? ~0u : 0u, mb = (ft == 2 || ft == 4) ? ~0u : 0u, mc = ft == 4 ? ~0u : 0u, mavg = ft == 3 ? ~0u : 0u;
     const bool simple = __all_sync(kFull, ft <= 2);
     const bool has_avg = __any_sync(kFull, ft == 3);
-    const int in_sh = 8 * (int)((uintptr_t)(F + (unsigned long long)y * (nb + 1) + 1 + (long long)(0 - lane) * BPP) & 3);   // the same in every chunk
+    const int in_w = ioff >> 2, in_sh = 8 * (ioff & 3);
     uint32_t curp = 0;                        // packed: my pixel x - 1
     UfPx<BPP> au, cu;                         // 16-bit pairs: my pixel x - 1, the pixel above x - 1
 #pragma unroll
     for (int q = 0; q < NR; q++) au.v[q] = cu.v[q] = 0;
-    M.out[lane][0] = 0;
     for (int j = 0; j < nchunks; j++) {
-        if (j + 1 < nchunks) fetch(j + 1);
+        const int s = j % kUfSin, so = j % kUfSout;
+        mbar_wait(&S.in_full[s], (uint32_t)(j / kUfSin) & 1u);
+        mbar_wait(&S.out_empty[so], ((uint32_t)(j / kUfSout) & 1u) ^ 1u);
         // lane s holds pixel s of the row above (packed), handed to lane 0 by a broadcast at step s
         uint32_t upv = 0;
         if (band > 0) {
             const int ub = (int)((uintptr_t)(X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP) & 3) + lane * BPP;
-            upv = __funnelshift_r(M.up[ub >> 2], M.up[(ub >> 2) + 1], 8 * (ub & 3));
+            upv = __funnelshift_r(S.up[s][ub >> 2], S.up[s][(ub >> 2) + 1], 8 * (ub & 3));
         }
-        const uint32_t* inw = M.in[lane];
-        uint32_t* outw = M.out[lane] + 1;
+        const uint32_t* inw = S.in[s][lane] + in_w;
+        uint32_t* outw = S.out[so][lane];
         const bool ramp = j == 0;             // only in the first chunk a lane may not have started (x < 0): left and upper-left of pixel 0 are 0
         uint32_t wprev = inw[0];
-        auto body = [&](auto simple_c, auto avg_c) {
+        auto body = [&](auto simple_c, auto avg_c, auto ramp_c) {
 #pragma unroll 1
             for (int i = 0; i < 8; i++) {
                 uint32_t d[BPP], o[4];
@@ -1303,7 +1360,7 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
                         au = ou; cu = bu;
                     }
                     curp = o[m];
-                    if (ramp && 32 * j + sidx - lane < 0) {
+                    if (decltype(ramp_c)::value && sidx - lane < 0) {
                         curp = 0;
 #pragma unroll
                         for (int q = 0; q < NR; q++) au.v[q] = cu.v[q] = 0;
@@ -1315,75 +1372,50 @@ __device__ void unfilter_band(const UfMem M, const DecPageD& P, int band, uint32
                 for (int k = 0; k < BPP; k++) outw[BPP * i + k] = w[k];
             }
         };
-        if (simple) body(std::true_type{}, std::false_type{});
-        else if (has_avg) body(std::false_type{}, std::true_type{});
-        else body(std::false_type{}, std::false_type{});
+        if (ramp) { if (simple) body(std::true_type{}, std::false_type{}, std::true_type{}); else body(std::false_type{}, std::true_type{}, std::true_type{}); }
+        else if (simple) body(std::true_type{}, std::false_type{}, std::false_type{});
+        else if (has_avg) body(std::false_type{}, std::true_type{}, std::false_type{});
+        else body(std::false_type{}, std::false_type{}, std::false_type{});
         __syncwarp();
-        // ---- copy out, a row at a time.  Inside a row whole aligned words go out: the word that straddles the start of this chunk is
-        //      completed from the previous chunk's last word (out[r][0]), the one that straddles its end waits for the next chunk.
-        //      Chunks that touch either end of the row, and the band's last row (the band below reads it as soon as the flag
-        //      says so), are written byte by byte, including the three bytes in front that an earlier chunk may have left.
-        for (int r = 0; r < 32; r++) {
-            if (y0 + r >= H) break;
-            uint8_t* dst = X + (unsigned long long)(y0 + r) * nb;
-            const int x0 = 32 * j - r;
-            const int g0 = x0 * BPP;
-            if (x0 >= 3 && x0 + 32 <= W && r != 31) {
-                const int mis = (int)((uintptr_t)(dst + g0) & 3);
-                if (lane < 8 * BPP) {
-                    const uint32_t v = __funnelshift_rc(M.out[r][lane], M.out[r][lane + 1], 8 * (4 - mis));
-                    *reinterpret_cast<uint32_t*>(dst + g0 - mis + 4 * lane) = v;
-                }
-            } else {
-                const uint8_t* ob = reinterpret_cast<const uint8_t*>(M.out[r]) + 1;      // byte 3 of the carry word = byte -3 of the chunk
-#pragma unroll
-                for (int i = 0; i < BPP + 1; i++) {
-                    const int bi = lane + 32 * i, gb = g0 - 3 + bi;
-                    if (bi < 32 * BPP + 3 && gb >= 0 && gb < nb) dst[gb] = ob[bi];
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + band), "r"((uint32_t)(j + 1)) : "memory");
-        M.out[lane][0] = M.out[lane][8 * BPP];
-        if (j + 1 < nchunks) stage(); else __syncwarp();
+        if (lane == 0) { mbar_arrive(&S.in_empty[s]); mbar_arrive(&S.out_full[so]); }
     }
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(32) k_unfilter(const DecBatchD b) {
-    __shared__ uint32_t s_in[32][kUfW];
-    __shared__ uint32_t s_out[32][kUfW];
-    __shared__ uint32_t s_up[kUfW + 1];
+__global__ void __launch_bounds__(96) k_unfilter(const DecBatchD b) {
+    __shared__ UfSmem S;
     // One band per CTA (a finished band frees its slot at once).  Bands are handed out by ticket, band-major over the pages of
     // the batch (band 0 of every page, then band 1, ...): a band only waits on one that holds an earlier ticket, and the resident
     // CTAs are the pipeline fronts of all pages rather than all bands of a few.
-    uint32_t t = 0;
-    if (threadIdx.x == 0) t = atomicAdd(b.counters, 1u);
-    t = __shfl_sync(kFull, t, 0);
+    if (threadIdx.x == 0) {
+        S.ticket = atomicAdd(b.counters, 1u);
+        for (int i = 0; i < kUfSin; i++) { mbar_init(&S.in_full[i], 1); mbar_init(&S.in_empty[i], 1); }
+        for (int i = 0; i < kUfSout; i++) { mbar_init(&S.out_full[i], 1); mbar_init(&S.out_empty[i], 1); }
+    }
+    __syncthreads();
+    const uint32_t t = S.ticket;
     if ((int)t >= b.nbands) return;
-    const UfMem mem_w{s_in, s_out, s_up};
     DecPageD& P = b.pages[b.band_page[t]];
     const int band = (int)b.band_idx[t];
     uint32_t* flags = b.band_flag + P.band0;
     int bad = 0;
     if (P.status != 0) {                                  // a skipped band still releases the bands waiting on it
         if (threadIdx.x == 0) *(volatile uint32_t*)(flags + band) = 0xffffffffu;
-    } else {
-        switch (P.c) {
-            case 1: unfilter_band<1>(mem_w, P, band, flags, &bad, b.dbg_nowait != 0); break;
-            case 2: unfilter_band<2>(mem_w, P, band, flags, &bad, b.dbg_nowait != 0); break;
-            case 3: unfilter_band<3>(mem_w, P, band, flags, &bad, b.dbg_nowait != 0); break;
-            default: unfilter_band<4>(mem_w, P, band, flags, &bad, b.dbg_nowait != 0); break;
-        }
+        return;
     }
-    if (__any_sync(kFull, bad) && threadIdx.x == 0) atomicMin(&P.status, (int)INF_BAD_FILTER);
+    switch (P.c) {
+        case 1: unfilter_band<1>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        case 2: unfilter_band<2>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        case 3: unfilter_band<3>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        default: unfilter_band<4>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
+    }
+    if (threadIdx.x < 32 && __any_sync(kFull, bad) && threadIdx.x == 0) atomicMin(&P.status, (int)INF_BAD_FILTER);
 }
 
 int launch_unfilter(const DecBatchD& b, cudaStream_t st) {
     if (b.nbands == 0) return 0;
-    k_unfilter<<<b.nbands, 32, 0, st>>>(b);
+    k_unfilter<<<b.nbands, 96, 0, st>>>(b);
     return 1;
 }
 
