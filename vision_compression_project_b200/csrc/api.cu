@@ -1163,13 +1163,13 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
             pix_total = (o_p[j] - o_preg) + pl;
         }
         G.pix_bytes = align_up(pix_total, 256);
-        // un-filter work list: band b of every page that has one, for b = 0, 1, ...
+        // un-filter work list: bands g .. g + VCP_UF_GROUP - 1 of every page that has them, for g = 0, VCP_UF_GROUP, ...
         std::vector<uint32_t> band_page, band_idx;
         band_page.reserve(nbands); band_idx.reserve(nbands);
         {
             int maxb = 0;
             for (int j = 0; j < m; j++) if (!dp[i0 + j].status) maxb = std::max(maxb, (dp[i0 + j].h + 31) / 32);
-            for (int bnd = 0; bnd < maxb; bnd++)
+            for (int bnd = 0; bnd < maxb; bnd += VCP_UF_GROUP)
                 for (int j = 0; j < m; j++) if (!dp[i0 + j].status && bnd < (dp[i0 + j].h + 31) / 32) { band_page.push_back((uint32_t)j); band_idx.push_back((uint32_t)bnd); }
         }
         const size_t desc_bytes = align_up((size_t)m * sizeof(DecPageD), 256), seg_bytes = align_up(cand.size() * sizeof(unsigned long long), 256),
@@ -1239,7 +1239,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         B.nchunks = (int32_t)chunk_page.size();
         B.chunk_adler = reinterpret_cast<uint32_t*>(A + o_cadl);
         B.counters = reinterpret_cast<uint32_t*>(A + o_flag);
-        B.band_flag = B.counters + 64; B.nbands = nbands;
+        B.band_flag = B.counters + 64; B.nbands = nbands; B.ngroups = (int32_t)band_page.size();
         B.band_page = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes);
         B.band_idx = reinterpret_cast<const uint32_t*>(A + o_desc + desc_bytes + seg_bytes + 2 * chunk_bytes + band_bytes);
         if (const char* g = getenv("VCP_DBG_UF_NOWAIT")) B.dbg_nowait = atoi(g);

@@ -37,6 +37,7 @@
 // Every loop is bounded by the stream / output length: malformed input ends in a status, never in a hang.
 #include "vcp_internal.cuh"
 #include <type_traits>
+#include <atomic>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -1140,6 +1141,7 @@ namespace {
 constexpr int kUfInW = 36;                // words per staged input row: a TMA copy of whole 16-byte granules around the row's 32 pixels (<= 15 + 128 bytes)
 constexpr int kUfOutW = 33;               // words per staged output row; odd pitch: lane r on word k of row r hits bank r + k
 constexpr int kUfSin = 3, kUfSout = 2;    // stages of the input / output rings
+constexpr int kUfGroup = VCP_UF_GROUP;    // consecutive bands of a page per CTA (vcp_internal.cuh)
 
 struct __align__(16) UfSmem {
     uint32_t in[kUfSin][32][kUfInW];      // row r of a stage: the 16-byte granules that cover its 32 pixels of the chunk
@@ -1218,8 +1220,9 @@ __device__ __forceinline__ uint32_t uf_step16(uint32_t a, uint32_t b, uint32_t c
 // Warp 2 stores finished chunks from a two-stage ring to global memory as aligned words and publishes the band's progress.  The warps
 // meet only at mbarriers, so loading chunk j + 2, computing chunk j + 1 and storing chunk j overlap.
 template <int BPP>
-__device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* __restrict__ flags /* of this page */, int* bad, bool nowait) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ void unfilter_band(UfSmem& S, UfSmem* above /* the band above, if this CTA runs it */, bool below /* the band below is in this CTA */,
+                              const DecPageD& P, int band, uint32_t* __restrict__ flags /* of this page */, int* bad, bool nowait) {
+    const int warp = (threadIdx.x >> 5) % 3, lane = threadIdx.x & 31;
     const int W = P.w, nb = W * BPP, H = P.h;
     const int y0 = band * 32, y = y0 + lane;
     const bool row_ok = y < H;
@@ -1245,7 +1248,7 @@ __device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* 
             uint8_t* dst = X + (unsigned long long)(y0 + r) * nb;
             const int x0 = 32 * j - r;
             const int g0 = x0 * BPP;
-            if (x0 >= 3 && x0 + 32 <= W && r != 31) {
+            if (x0 >= 3 && x0 + 32 <= W && (below || r != 31)) {
                 const int mis = (int)((uintptr_t)(dst + g0) & 3);
                 if (lane < 8 * BPP) {
                     const uint32_t lo = lane ? S.out[so][r][lane - 1] : S.carry[r];
@@ -1266,11 +1269,13 @@ __device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* 
         for (int j = 0; j < nchunks; j++) {
             const int so = j % kUfSout;
             mbar_wait(&S.out_full[so], (uint32_t)(j / kUfSout) & 1u);
-            if (nrows == 32) store_row(so, j, 31);
-            __syncwarp();
-            if (lane == 31) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + band), "r"((uint32_t)(j + 1)) : "memory");
+            if (!below) {
+                if (nrows == 32) store_row(so, j, 31);
+                __syncwarp();
+                if (lane == 31) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(flags + band), "r"((uint32_t)(j + 1)) : "memory");
+            }
 #pragma unroll 4
-            for (int r = 0; r < min(nrows, 31); r++) store_row(so, j, r);
+            for (int r = 0; r < min(nrows, below ? 32 : 31); r++) store_row(so, j, r);
             __syncwarp();
             S.carry[lane] = S.out[so][lane][8 * BPP - 1];
             __syncwarp();
@@ -1285,11 +1290,44 @@ __device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* 
         for (int d = 16; d; d >>= 1) total_tx += __shfl_xor_sync(kFull, total_tx, d);
         const uint8_t* Xend = X + (((unsigned long long)nb * H + 3ull) & ~3ull);   // the buffer is 256-byte aligned with slack behind
         uint32_t seen = 0;                                                        // lane 0: last value read from the flag of the band above
+        uint32_t tail = 0;                                                        // packed: the pixel of the row above at x = 32 j
         for (int j = 0; j < nchunks; j++) {
             const int s = j % kUfSin;
             mbar_wait(&S.in_empty[s], ((uint32_t)(j / kUfSin) & 1u) ^ 1u);
             if (row_ok) bulk_g2s(&S.in[s][lane][0], a0 + (long long)32 * BPP * j - ioff, tma_bytes, &S.in_full[s]);
-            if (band > 0) {                   // the band above must have stored the pixels lane 0 will need in chunk j
+            if (above) {
+                // the band above runs in this CTA: its last row comes out of its output ring.  Row 31 of its chunk c holds x = 32 c - 31 ..
+                // 32 c; this chunk needs x = 32 j .. 32 j + 31: the last pixel of its chunk j (kept in `tail`) and the first 31 of chunk
+                // j + 1.  Every chunk of the ring is read once, then handed back (out_empty counts the neighbour's storer and this warp).
+                constexpr int TW = (31 * BPP) >> 2, TS = 8 * ((31 * BPP) & 3);
+                if (j == 0) {
+                    mbar_wait(&above->out_full[0], 0u);
+                    tail = __funnelshift_r(above->out[0][31][TW], above->out[0][31][TW + 1], TS);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&above->out_empty[0]);
+                }
+                uint32_t v = 0, ntail = 0;
+                if (j + 1 < nchunks) {
+                    const int c = j + 1, so = c % kUfSout;
+                    mbar_wait(&above->out_full[so], (uint32_t)(c / kUfSout) & 1u);
+                    const uint32_t* ar = above->out[so][31];
+                    if (lane < 8 * BPP) {
+                        // up bytes 4 lane .. 4 lane + 3 = chunk bytes 4 lane - BPP ..
+                        if (BPP == 4) v = lane ? ar[lane - 1] : 0u;
+                        else {
+                            const int o = 4 * lane - BPP;                        // >= 0 from lane 1 on
+                            v = lane ? __funnelshift_r(ar[o >> 2], ar[(o >> 2) + 1], 8 * (o & 3)) : ar[0] << (8 * BPP);
+                        }
+                    }
+                    ntail = __funnelshift_r(ar[TW], ar[TW + 1], TS);
+                }
+                if (lane == 0) v = BPP == 4 ? tail : (v | (tail & ((1u << (8 * (BPP & 3))) - 1u)));
+                S.up[s][lane] = v;
+                if (lane == 0) S.up[s][32] = 0u;
+                tail = ntail;
+                __syncwarp();
+                if (lane == 0 && j + 1 < nchunks) mbar_arrive(&above->out_empty[(j + 1) % kUfSout]);
+            } else if (band > 0) {            // the band above must have stored the pixels lane 0 will need in chunk j
                 const uint32_t need = (uint32_t)min(j + 2, nchunks);
                 if (lane == 0 && seen < need) {   // acquire load: what the band above stored before its release is visible after it
                     const uint32_t* f = flags + band - 1;
@@ -1329,7 +1367,7 @@ __device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* 
         // lane s holds pixel s of the row above (packed), handed to lane 0 by a broadcast at step s
         uint32_t upv = 0;
         if (band > 0) {
-            const int ub = (int)((uintptr_t)(X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP) & 3) + lane * BPP;
+            const int ub = (above ? 0 : (int)((uintptr_t)(X + (unsigned long long)(y0 - 1) * nb + (long long)32 * j * BPP) & 3)) + lane * BPP;
             upv = __funnelshift_r(S.up[s][ub >> 2], S.up[s][(ub >> 2) + 1], 8 * (ub & 3));
         }
         const uint32_t* inw = S.in[s][lane] + in_w;
@@ -1383,39 +1421,56 @@ __device__ void unfilter_band(UfSmem& S, const DecPageD& P, int band, uint32_t* 
 
 }  // namespace
 
-__global__ void __launch_bounds__(96) k_unfilter(const DecBatchD b) {
-    __shared__ UfSmem S;
-    // One band per CTA (a finished band frees its slot at once).  Bands are handed out by ticket, band-major over the pages of
-    // the batch (band 0 of every page, then band 1, ...): a band only waits on one that holds an earlier ticket, and the resident
-    // CTAs are the pipeline fronts of all pages rather than all bands of a few.
-    if (threadIdx.x == 0) {
-        S.ticket = atomicAdd(b.counters, 1u);
-        for (int i = 0; i < kUfSin; i++) { mbar_init(&S.in_full[i], 1); mbar_init(&S.in_empty[i], 1); }
-        for (int i = 0; i < kUfSout; i++) { mbar_init(&S.out_full[i], 1); mbar_init(&S.out_empty[i], 1); }
+__global__ void __launch_bounds__(96 * kUfGroup) k_unfilter(const DecBatchD b) {
+    extern __shared__ __align__(16) unsigned char uf_smem[];
+    UfSmem* S = reinterpret_cast<UfSmem*>(uf_smem);
+    // A CTA runs kUfGroup consecutive bands of one page (a finished group frees its slot at once): inside the group the last row of a
+    // band reaches the band below through shared memory, between groups through global memory and a flag.  Groups are handed out by
+    // ticket, group-major over the pages of the batch (group 0 of every page, then group 1, ...): a band only waits on one that holds an
+    // earlier ticket, and the resident CTAs are the pipeline fronts of all pages rather than all bands of a few.
+    const int slot = threadIdx.x / 96;
+    if (threadIdx.x == 0) S[0].ticket = atomicAdd(b.counters, 1u);
+    if (threadIdx.x % 96 == 0) {
+        for (int i = 0; i < kUfSin; i++) { mbar_init(&S[slot].in_full[i], 1); mbar_init(&S[slot].in_empty[i], 1); }
+        for (int i = 0; i < kUfSout; i++) mbar_init(&S[slot].out_full[i], 1);
     }
     __syncthreads();
-    const uint32_t t = S.ticket;
-    if ((int)t >= b.nbands) return;
+    const uint32_t t = S[0].ticket;
+    if ((int)t >= b.ngroups) return;
     DecPageD& P = b.pages[b.band_page[t]];
-    const int band = (int)b.band_idx[t];
+    const int band = (int)b.band_idx[t] + slot, pbands = (P.h + 31) / 32;
     uint32_t* flags = b.band_flag + P.band0;
+    const bool live = band < pbands, below = slot + 1 < kUfGroup && band + 1 < pbands;
+    if (threadIdx.x % 96 == 0)                            // a ring stage is free again when the storer and, if there is one, the neighbour below have read it
+        for (int i = 0; i < kUfSout; i++) mbar_init(&S[slot].out_empty[i], below ? 2 : 1);
+    __syncthreads();
+    if (!live) return;
     int bad = 0;
     if (P.status != 0) {                                  // a skipped band still releases the bands waiting on it
-        if (threadIdx.x == 0) *(volatile uint32_t*)(flags + band) = 0xffffffffu;
+        if (threadIdx.x % 96 == 0) *(volatile uint32_t*)(flags + band) = 0xffffffffu;
         return;
     }
+    UfSmem* above = slot > 0 ? &S[slot - 1] : nullptr;
     switch (P.c) {
-        case 1: unfilter_band<1>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
-        case 2: unfilter_band<2>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
-        case 3: unfilter_band<3>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
-        default: unfilter_band<4>(S, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        case 1: unfilter_band<1>(S[slot], above, below, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        case 2: unfilter_band<2>(S[slot], above, below, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        case 3: unfilter_band<3>(S[slot], above, below, P, band, flags, &bad, b.dbg_nowait != 0); break;
+        default: unfilter_band<4>(S[slot], above, below, P, band, flags, &bad, b.dbg_nowait != 0); break;
     }
-    if (threadIdx.x < 32 && __any_sync(kFull, bad) && threadIdx.x == 0) atomicMin(&P.status, (int)INF_BAD_FILTER);
+    if (threadIdx.x % 96 < 32 && __any_sync(kFull, bad) && threadIdx.x % 96 == 0) atomicMin(&P.status, (int)INF_BAD_FILTER);
 }
 
 int launch_unfilter(const DecBatchD& b, cudaStream_t st) {
-    if (b.nbands == 0) return 0;
-    k_unfilter<<<b.nbands, 96, 0, st>>>(b);
+    if (b.ngroups == 0) return 0;
+    static std::atomic<int> attr_by_dev[kMaxDevices];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int smem = (int)sizeof(UfSmem) * kUfGroup;
+    if (dev >= 0 && dev < kMaxDevices && !attr_by_dev[dev].load(std::memory_order_acquire)) {
+        cudaFuncSetAttribute(k_unfilter, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_by_dev[dev].store(1, std::memory_order_release);
+    }
+    k_unfilter<<<b.ngroups, 96 * kUfGroup, smem, st>>>(b);
     return 1;
 }
 

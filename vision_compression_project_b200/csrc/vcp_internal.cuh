@@ -6,6 +6,9 @@
 
 namespace vcp {
 
+#ifndef VCP_UF_GROUP
+#define VCP_UF_GROUP 4
+#endif
 #ifndef VCP_SUB_BYTES
 #define VCP_SUB_BYTES 16384
 #endif
@@ -173,8 +176,8 @@ struct DecBatchD {
     DecIvD* ivs; int32_t iv_total;                                            // intervals in stream order, one range per page
     const uint32_t* chunk_page; const uint32_t* chunk_pos; int32_t nchunks;   // resolve / Adler work list: 32 Ki positions each
     uint32_t* chunk_adler;                                                    // per chunk: (sum of bytes, position-weighted sum) mod 65521
-    uint32_t* band_flag; int32_t nbands;                                      // un-filter progress per band (zeroed per launch)
-    const uint32_t* band_page; const uint32_t* band_idx;                      // un-filter work list in ticket order (band-major over pages)
+    uint32_t* band_flag; int32_t nbands; int32_t ngroups;                     // un-filter progress per band (zeroed per launch); CTAs = groups of VCP_UF_GROUP bands
+    const uint32_t* band_page; const uint32_t* band_idx;                      // un-filter work list in ticket order (group-major over pages): page, first band
     uint32_t* counters;                                                       // [0] un-filter CTA ticket (zeroed per launch)
     int32_t dbg_nowait;                                                       // timing experiments only: bands do not wait (wrong pixels)
     int32_t no_scan;                                                          // VCP_DECODE_NO_SCAN: parse units are the IDAT starts only
