@@ -329,3 +329,58 @@ def test_decode_png_cut_into_thousands_of_idats(V):
     png = _png_from_idats(400, 300, 3, [z[i:i + step] for i in range(0, len(z), step)])
     d = V.decode_pages([png])[0]
     assert not isinstance(d, Exception) and np.array_equal(d, px)
+
+
+def _filtered_png(px, types):
+    """A PNG of `px` (H, W, C) whose row y uses filter types[y % len(types)] (hand-filtered, then zlib)."""
+    import struct
+    h, w, c = px.shape
+    rows = []
+    prev = np.zeros(w * c, np.int32)
+    for y in range(h):
+        cur = px[y].reshape(-1).astype(np.int32)
+        a = np.concatenate([np.zeros(c, np.int32), cur[:-c]])
+        cc = np.concatenate([np.zeros(c, np.int32), prev[:-c]])
+        t = types[y % len(types)]
+        if t == 0: pred = 0
+        elif t == 1: pred = a
+        elif t == 2: pred = prev
+        elif t == 3: pred = (a + prev) >> 1
+        else:
+            p = a + prev - cc
+            pa, pb, pc = np.abs(p - a), np.abs(p - prev), np.abs(p - cc)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, cc))
+        rows.append(bytes([t]) + ((cur - pred) & 255).astype(np.uint8).tobytes())
+        prev = cur
+    def chunk(t, d): return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    ct = {1: 0, 2: 4, 3: 2, 4: 6}[c]
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, ct, 0, 0, 0)) +
+            chunk(b"IDAT", zlib.compress(b"".join(rows), 6)) + chunk(b"IEND", b""))
+
+
+def test_unfilter_geometries_and_filter_mixes(V):
+    """The un-filter kernel's edges: widths around its 32-pixel chunks and 3-pixel word rule, heights around its 32-row bands and
+    4-band groups, all four channel counts, every filter type alone and mixed row by row — against Pillow's decode of the same bytes."""
+    rng = np.random.default_rng(11)
+    widths = [1, 2, 3, 4, 5, 7, 29, 31, 32, 33, 34, 35, 36, 61, 63, 64, 65, 67, 95, 97, 129, 257, 400, 641]
+    heights = [1, 2, 31, 32, 33, 63, 64, 65, 96, 127, 128, 129, 160, 200, 257]
+    mixes = [[0], [1], [2], [3], [4], [4, 3], [2, 2, 2, 4], [0, 1, 2, 3, 4], [1, 2], [3, 3, 1, 4, 2, 0, 4]]
+    pngs, names = [], []
+    k = 0
+    for w in widths:
+        for c in (1, 2, 3, 4):
+            h = heights[k % len(heights)]; mix = mixes[k % len(mixes)]; k += 1
+            if k % 3 == 0:
+                px = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+            else:
+                base = (np.add.outer(np.arange(h) * 5, np.arange(w) * 3)[:, :, None] + np.arange(c) * 29)
+                px = (base + rng.integers(0, 4, (h, w, c))).astype(np.uint8)
+            pngs.append(_filtered_png(px, mix)); names.append(f"{w}x{h}x{c} filters {mix}")
+    assert _assert_like_pillow(V, pngs, names) == 0
+    # one tall page per channel count: many groups of bands, row-by-row filter mix, width not a multiple of anything
+    pngs, names = [], []
+    for c in (1, 2, 3, 4):
+        px = rng.integers(0, 256, (700, 1003, c), dtype=np.uint8)
+        px[100:300] = 255                                                  # blank rows: bands without Avg / Paeth rows use the packed step
+        pngs.append(_filtered_png(px, [2] * 40 + [4, 1, 3, 0, 2, 4, 4, 3])); names.append(f"tall {c}")
+    assert _assert_like_pillow(V, pngs, names) == 0
