@@ -35,11 +35,18 @@ if __name__ == "__main__":
             ts = [torch.from_numpy(x).cuda() for x in a]
             rgba = torch.from_numpy(np.concatenate([a[0], np.full(a[0].shape[:2] + (1,), 255, np.uint8)], axis=2)).cuda()
             print("c5", {k: round(v, 3) for k, v in run(eng, ts + [rgba], {"max_side": 1568, "reducing_gap": 2.0}).items() if k.startswith("ms_")})
-        if what in ("dec8p", "dec64t"):                       # decode only: 8 photo-heavy / 64 text pages, this library's PNGs
+        if what in ("dec8p", "dec64t", "dec8pp", "dec8pt"):   # decode only: 8 photo-heavy / 64 text pages, this library's PNGs; ..pp / ..pt: Pillow-written photo / text
             import vision_compression_project_b200 as V
-            n, photo = (8, True) if what == "dec8p" else (64, False)
+            n, photo = (64, False) if what == "dec64t" else (8, what != "dec8pt")
             a = fac.arrays([(i, "letter", 200, "RGB", photo) for i in range(n)])
-            ours = [r.png for r in V.prepare_pages(a, want_base64=False)]
+            if what in ("dec8pp", "dec8pt"):
+                import io
+                from PIL import Image
+                ours = []
+                for x in a:
+                    bio = io.BytesIO(); Image.fromarray(x, "RGB").save(bio, format="PNG"); ours.append(bio.getvalue())
+            else:
+                ours = [r.png for r in V.prepare_pages(a, want_base64=False)]
             import time
             for _ in range(3):
                 torch.cuda.synchronize(); t = time.perf_counter()

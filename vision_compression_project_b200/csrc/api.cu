@@ -1092,8 +1092,8 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
     //      (probe, window chain, un-filter pipeline) overlap the throughput-bound ones of the other (exec, resolve)
     constexpr unsigned long long kResolveChunk = 32768, kCkpt = 65536, kScanBits = 8192;      // keep in step with png_decode.cu
     constexpr int kMaxCand = 1024;                                                              // scanned block headers per page
-    constexpr unsigned long long kSpecBits = VCP_SPEC_BITS;                                      // one speculative start point per so many bits of stream (png_decode.cu: k_infl_spec)
-    struct Group { int i0 = 0, i1 = 0; uint64_t pix_base = 0, pix_bytes = 0; DecPageD* hd = nullptr; Lane* L = nullptr; };
+    constexpr unsigned long long kSpecBitsMax = VCP_SPEC_BITS, kSpecBitsMin = 8192, kSpecUnits = 3000;   // speculative start points (png_decode.cu: k_infl_spec)
+    struct Group { int i0 = 0, i1 = 0; uint64_t pix_base = 0, pix_bytes = 0; DecPageD* hd = nullptr; Lane* L = nullptr; const DecSegD* d_segs = nullptr; int seg_total = 0; };
     auto enqueue = [&](Group& G) -> int {
         Lane& L = *G.L;
         const int i0 = G.i0, m = G.i1 - G.i0;
@@ -1104,6 +1104,12 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         uint64_t pix_total = 0;
         int nbands = 0;
         size_t nslots = 0, iv_total = 0, seg_total = 0, surv_total = 0, spec_total = 0;
+        // One speculative parse start per spec_bits of a page's stream: 4 KiB when the batch is large (its first parse then has thousands of
+        // units, more than the GPU holds at once), down to 1 KiB when a few pages with short streams would otherwise leave it a few
+        // hundred serial units on 148 SMs.  Literal-heavy pages (long streams) keep the coarse spacing: every start costs a 6 Kbit walk.
+        int m_ok = 0;
+        for (int j = 0; j < m; j++) m_ok += !dp[i0 + j].status;
+        const unsigned long long units_per_page = std::max<unsigned long long>(64, kSpecUnits / (unsigned long long)std::max(1, m_ok));
         for (int j = 0; j < m; j++) {
             DecPageD& D = dp[i0 + j];
             D.band0 = nbands; D.iv0 = (int32_t)iv_total; D.seg0 = D.cand0 = (int32_t)seg_total; D.surv0 = (int32_t)surv_total; D.slot0 = (int32_t)nslots;
@@ -1127,7 +1133,10 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
                 o += c.n; q++;
             }
             D.n_idat = n_idat; D.ncand = (uint32_t)n_idat; D.nsurv = 0;
-            D.spec0 = (int32_t)spec_total; D.nspec = (int32_t)(zl * 8ull / kSpecBits);
+            unsigned long long spec_bits = kSpecBitsMax;
+            while (spec_bits > kSpecBitsMin && zl * 8ull / spec_bits < units_per_page) spec_bits >>= 1;
+            D.spec_bits = (uint32_t)spec_bits;
+            D.spec0 = (int32_t)spec_total; D.nspec = (int32_t)(zl * 8ull / spec_bits);
             spec_total += (size_t)D.nspec;
             D.seg_cap = n_idat + kMaxCand + D.nspec;
             cand.resize(seg_total + (size_t)D.seg_cap, 0ull);
@@ -1225,6 +1234,7 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         DecBatchD B; memset(&B, 0, sizeof B);
         B.pages = reinterpret_cast<DecPageD*>(A + o_desc); B.npages = m;
         B.segs = reinterpret_cast<DecSegD*>(A + o_segs); B.seg_total = (int32_t)seg_total;
+        G.d_segs = B.segs; G.seg_total = (int)seg_total;
         B.cand_bits = reinterpret_cast<unsigned long long*>(A + o_desc + desc_bytes);
         B.cand_hdr = reinterpret_cast<unsigned long long*>(A + o_chdr); B.spec_total = (int32_t)spec_total;
         B.surv = reinterpret_cast<uint32_t*>(A + o_surv); B.surv_total = (int32_t)surv_total;
@@ -1275,10 +1285,23 @@ int vcp_png_decode_batch(vcp_handle* h, const void* const* pngs, const uint64_t*
         if (e != cudaSuccess && rc == 0) rc = fail(VCP_ECUDA, "CUDA: %s", cudaGetErrorString(e));
     }
     if (rc) return rc;
+    if (getenv("VCP_DECODE_DEBUG"))
+        for (int g = 0; g < 2; g++) if (G[g].seg_total > 0) {
+            std::vector<DecSegD> hs((size_t)G[g].seg_total);
+            cudaMemcpy(hs.data(), G[g].d_segs, hs.size() * sizeof(DecSegD), cudaMemcpyDeviceToHost);
+            const DecPageD& R = G[g].hd[0];
+            fprintf(stderr, "[vcp] parse units of page %d (start bit, header bit, bytes out, ok, kilo-cycles):", G[g].i0);
+            for (int k = 0; k < R.nseg && k < 90; k++) { const DecSegD& S = hs[(size_t)R.seg0 + k];
+                fprintf(stderr, " (%llu,%llu,%u,%d,%u)", (unsigned long long)S.start_bit, (unsigned long long)S.hdr_bit, S.olen, S.ok, S.pad); }
+            fprintf(stderr, "\n");
+        }
     for (int g = 0; g < 2; g++)
         for (int i = G[g].i0; i < G[g].i1; i++) {
             if (!G[g].hd) continue;
             const DecPageD& R = G[g].hd[i - G[g].i0];
+            if (getenv("VCP_DECODE_DEBUG"))
+                fprintf(stderr, "[vcp] decode page %d: zlen %llu n_idat %d nspec %d candidates %u parse units %d intervals %d status %d\n", i,
+                        (unsigned long long)R.zlen, R.n_idat, R.nspec, R.ncand, R.nseg, R.niv, R.status);
             if (results[i].status) continue;
             if (R.status) { results[i].status = VCP_EINVAL; fail(VCP_EINVAL, "PNG %d: corrupt zlib stream or filter byte (code %d)", i, R.status); continue; }
             const char* why = decode_verdict(R, idats[i]);

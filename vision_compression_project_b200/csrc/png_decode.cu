@@ -513,7 +513,6 @@ __global__ void __launch_bounds__(256) k_infl_sort(const DecBatchD b) {
 // unit's parse on a candidate when its own token boundary falls exactly on the candidate's start AND it is inside the same block
 // (same header bit) — from there on the two parses are identical by construction.  A candidate that is not a true boundary is
 // walked over and never reached by the chain, like a false positive of the header scan.
-constexpr unsigned long long kSpecBits = VCP_SPEC_BITS;   // (api.cu sizes the candidate ranges with the same constant)
 constexpr unsigned long long kSpecSync = 6144;
 
 __global__ void __launch_bounds__(128) k_infl_spec(const DecBatchD b) {
@@ -526,22 +525,33 @@ __global__ void __launch_bounds__(128) k_infl_spec(const DecBatchD b) {
     DecPageD& P = b.pages[plo];
     const int t = g - P.spec0;
     if (P.status != 0 || t >= P.nspec || P.nseg <= 0) return;
-    const unsigned long long nbits = P.zlen * 8ull;
+    const unsigned long long nbits = P.zlen * 8ull, kSpecBits = P.spec_bits;                // api.cu sizes the candidate ranges with the same number
     const unsigned long long point = (unsigned long long)(t + 1) * kSpecBits;
     if (point + kSpecSync + 2048 >= nbits) return;
     const DecSegD* PS = b.segs + P.seg0;                // the block starts found so far, sorted
     int lo = 0, hi = P.nseg - 1;
     if (PS[0].start_bit > point) return;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (PS[mid].start_bit <= point) lo = mid; else hi = mid - 1; }
-    const unsigned long long H = PS[lo].start_bit;
-    if (point - H < kSpecBits / 2) return;                                                  // a unit starts close in front anyway
+    if (point - PS[lo].start_bit < kSpecBits / 2) return;                                   // a unit starts close in front anyway
     if (lo + 1 < P.nseg && PS[lo + 1].start_bit < point + kSpecSync + 2048) return;         // ... or close behind
     InflMem& M = mem[warp];
     BitReader br; br.init(P.z, P.zlen, M.zbuf);
     uint32_t filled = 0;
-    seek_bit(M, br, filled, H);
-    int last = 0, btype = 0, slen = 0; unsigned long long ssrc = 0;
-    if (block_header(M, br, filled, &last, &btype, &slen, &ssrc) != INF_OK || btype == 0) return;
+    // The block that contains the point starts at the last found start in front of it that really is a block header.  IDAT starts
+    // are in the list too, and a foreign encoder cuts IDATs in the middle of blocks (Pillow: every 64 KiB): a start that does not
+    // read as a dynamic-Huffman header is stepped over.  (A wrong pick costs nothing but this point: k_infl_probe only ends a unit
+    // on a candidate whose header is the block it is parsing.)
+    unsigned long long H = 0;
+    bool found = false;
+    for (int back = 0; back < 6 && lo - back >= 0; back++) {
+        H = PS[lo - back].start_bit;
+        filled = 0;
+        seek_bit(M, br, filled, H);
+        int last = 0, btype = 0, slen = 0; unsigned long long ssrc = 0;
+        if (block_header(M, br, filled, &last, &btype, &slen, &ssrc) == INF_OK && btype == 2) { found = true; break; }
+        if (back == 0 && P.n_idat > 0 && lo == 0) break;                                    // the stream start is a block start: nothing in front of it
+    }
+    if (!found) return;
     if (__shfl_sync(kFull, br.bits_used(), 0) >= point) return;
     unsigned long long B = point;
     filled = 0;
@@ -580,6 +590,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
     const int s_loc = sg - P.seg0;
     if (P.status != 0 || s_loc >= P.nseg) return;
     DecSegD& S = segs[sg];
+    const long long t_dbg0 = clock64();
     InflMem& M = mem[warp];
     const DecSegD* PS = segs + P.seg0;                  // this page's parse units, sorted by start bit
     BitReader br; br.init(P.z, P.zlen, M.zbuf);
@@ -700,6 +711,7 @@ __global__ void __launch_bounds__(128) k_infl_probe(const DecPageD* __restrict__
         S.olen = (uint32_t)min(pos, cap); S.next = next; S.fin = status == INF_OK ? last : 0; S.niv = niv;
         S.end_bit = (status == INF_OK && last) ? used : 0ull;
         S.ok = status == INF_OK ? 1 : status;
+        S.pad = (uint32_t)((clock64() - t_dbg0) >> 10);         // debug: kilo-cycles this unit's parse took (VCP_DECODE_DEBUG)
     }
 }
 

@@ -20,7 +20,7 @@ namespace vcp {
 // of the parse.  16 KiB sub-chunks primed with 16 KiB: same kernel time as 32/32 on a full batch, half the latency of a small one
 // (single page 2.85 -> 2.0 ms, the reference's 5-thread pattern 1600 -> 2100 pages/s), +1.3 % PNG size on text pages.
 #ifndef VCP_SPEC_BITS
-#define VCP_SPEC_BITS 32768        // decode: one speculative parse start per 4 KiB of compressed stream (png_decode.cu k_infl_spec)
+#define VCP_SPEC_BITS 32768        // decode: at most one speculative parse start per 4 KiB of compressed stream (png_decode.cu k_infl_spec)
 #endif
 constexpr int kSubBytes   = VCP_SUB_BYTES;   // LZ sub-chunk: one warp; table entries are u16 positions relative to (start - 32 KiB)
 constexpr int kPrimeBytes = VCP_PRIME_BYTES; // bytes in front of a sub-chunk that are hashed into its tables before it starts (<= 32 KiB, multiple of 512)
@@ -130,7 +130,8 @@ struct DecPageD {
     int32_t iv0, iv_cap, niv;                       // its intervals in the DecIvD array (niv written by k_infl_plan)
     int32_t band0;                                  // first 32-row band of this page in the un-filter's band numbering
     int32_t chunk0;                                 // first 32 KiB chunk of this page in the resolve / Adler work list
-    int32_t spec0, nspec;                           // its range of speculative start points (one per kSpecBits of stream, k_infl_spec)
+    int32_t spec0, nspec;                           // its range of speculative start points (one per spec_bits of stream, k_infl_spec)
+    uint32_t spec_bits, pad_spec;                   // distance of those points in the stream, bits (host: 8192 .. VCP_SPEC_BITS by batch size and stream length)
     // ---- what Pillow's decoder (zlib inflate driven row by row, ZipDecode.c) would have seen at the end of the image; the host
     //      turns these into accept / reject exactly as Image.open(png).load() does (api.cu: decode_verdict)
     unsigned long long valid_len;                   // inflated bytes that exist: filt_len, or less when the final block ended early
