@@ -64,7 +64,10 @@ struct Lane {
     uint8_t* stage = nullptr; size_t stage_cap = 0;        // pinned bounce buffer for pageable page sources (filled by host threads)
     cudaEvent_t ev[EV_COUNT] = {};
 };
-constexpr int kLanes = 4;
+#ifndef VCP_LANES
+#define VCP_LANES 4
+#endif
+constexpr int kLanes = VCP_LANES;
 constexpr int kMaxGroupPages = 65535;                    // the page index is grid.y / grid.z of the row kernels
 
 struct BatchJob {                  // a streaming batch (vcp_batch_begin .. vcp_batch_end)
@@ -907,6 +910,13 @@ int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* 
     };
     int rc = 0;
     const bool trace = getenv("VCP_TRACE") != nullptr;
+    // Host inputs, several groups: one call at a time feeds the host -> device link.  Two handles that copy at once (prepare_stream keeps
+    // two batches in flight) each get half of it and BOTH finish late; taking turns, the second call's copies start when the first has
+    // issued its last one, so the first call's drain (last group's kernels, payload copy, bytes) hides behind them (VCP_H2D_TURN=0: off).
+    static std::mutex h2d_turn[kMaxDevices];
+    static const bool use_turn = !(getenv("VCP_H2D_TURN") && atoi(getenv("VCP_H2D_TURN")) == 0);
+    std::unique_lock<std::mutex> turn;
+    if (use_turn && !opts->src_device && G > 1 && h->device >= 0 && h->device < kMaxDevices) turn = std::unique_lock<std::mutex>(h2d_turn[h->device]);
     const auto T0 = std::chrono::steady_clock::now();
     auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
     for (int g = 0; g < G && !rc; g++) {
@@ -924,6 +934,7 @@ int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* 
         if (!rc && g >= kLanes - 1) rc = collect(g - (kLanes - 1));
         if (trace) fprintf(stderr, "[vcp] g%d (%d pages) issue %.2f..%.2f collect(g%d) ..%.2f\n", g, (int)groups[g].size(), tb, tc, g - (kLanes - 1), now_ms());
     }
+    if (turn.owns_lock()) turn.unlock();
     for (int g = std::max(0, G - (kLanes - 1)); g < G && !rc; g++) { rc = collect(g); if (trace) fprintf(stderr, "[vcp] tail collect(g%d) ..%.2f\n", g, now_ms()); }
     for (int l = 0; l < kLanes; l++) {             // drain both lanes even on error
         Lane& L = h->lane[l];
