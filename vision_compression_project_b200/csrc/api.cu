@@ -87,6 +87,7 @@ struct vcp_handle {
     std::map<CoeffKey, std::shared_ptr<const Coeffs>> coeff_cache;   // plans hold shared_ptrs: eviction never frees tables a group still uses
     vcp_stats stats = {};
     size_t group_bytes = (size_t)2 << 30;                  // max filtered bytes per launch set
+    cudaEvent_t trace_t0 = nullptr;                        // VCP_TRACE: recorded at the start of a call
     size_t pipe_bytes = (size_t)96 << 20;                  // host inputs: source bytes per pipelined group
     int copy_threads = 8;                                  // host threads that fill the bounce buffer
 };
@@ -684,6 +685,12 @@ int finish_group(vcp_handle* h, GroupOut& out) {
     h->stats.ms_h2d += el(EV_START, EV_H2D); h->stats.ms_convert += el(EV_H2D, EV_CONV); h->stats.ms_resample += el(EV_CONV, EV_PIXEL); h->stats.ms_filter += el(EV_PIXEL, EV_FILTER);
     h->stats.ms_lz += el(EV_FILTER, EV_LZ); h->stats.ms_huff += el(EV_LZ, EV_HUFF); h->stats.ms_assemble += el(EV_HUFF, EV_ASSEMBLE);
     h->stats.ms_b64 += el(EV_ASSEMBLE, EV_B64);
+    if (h->trace_t0) {                                    // VCP_TRACE: where this group's stages sit on the device clock of the call
+        float t[EV_B64 + 1];
+        for (int k = EV_START; k <= EV_B64; k++) { t[k] = 0; cudaEventElapsedTime(&t[k], h->trace_t0, L.ev[k]); }
+        fprintf(stderr, "[vcp]   device: copy %.2f..%.2f pixel ..%.2f filter ..%.2f lz ..%.2f huff ..%.2f out ..%.2f\n",
+                t[EV_START], t[EV_H2D], t[EV_PIXEL], t[EV_FILTER], t[EV_LZ], t[EV_HUFF], t[EV_B64]);
+    }
     return 0;
 }
 
@@ -917,6 +924,10 @@ int run_batch(vcp_handle* h, const vcp_page_desc* pages, int n, const vcp_opts* 
     static const bool use_turn = !(getenv("VCP_H2D_TURN") && atoi(getenv("VCP_H2D_TURN")) == 0);
     std::unique_lock<std::mutex> turn;
     if (use_turn && !opts->src_device && G > 1 && h->device >= 0 && h->device < kMaxDevices) turn = std::unique_lock<std::mutex>(h2d_turn[h->device]);
+    if (trace) {
+        if (!h->trace_t0) cudaEventCreate(&h->trace_t0);
+        cudaEventRecord(h->trace_t0, h->lane[0].stream);
+    } else if (h->trace_t0) { cudaEventDestroy(h->trace_t0); h->trace_t0 = nullptr; }
     const auto T0 = std::chrono::steady_clock::now();
     auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count(); };
     for (int g = 0; g < G && !rc; g++) {
