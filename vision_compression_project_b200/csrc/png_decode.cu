@@ -912,17 +912,55 @@ __global__ void __launch_bounds__(32, 32) k_infl_exec(DecPageD* __restrict__ pag
             const int total = __shfl_sync(kFull, incl, 31);
             const uint32_t my = pos + (uint32_t)(incl - size);
             if (lit) out[my] = (uint16_t)(t & 255u);
-            uint32_t mm = __ballot_sync(kFull, lane < ntok && !lit);
+            const bool is_match = lane < ntok && !lit;
+            if (__any_sync(kFull, is_match && (unsigned long long)(t >> 9) > abs0 + my)) { status = INF_BAD_DIST; break; }
+            // A match whose source lies wholly in front of this batch's output depends on nothing in the batch (on a page: the row above).
+            // Those go first, four 32-symbol pieces at a time with all their loads in flight together; one at a time each piece waited
+            // an L2 round trip for its own load (20 % of the kernel's stall samples).  The others follow in token order.
+            const bool far = is_match && (t >> 9) >= (t & 511u) + (my - pos);
+            uint32_t mf = __ballot_sync(kFull, far);
+            uint32_t mm = __ballot_sync(kFull, is_match && !far);
             __syncwarp();
+            {
+                constexpr int U = 4;
+                uint32_t fat = 0; int flen = 0, fdist = 0, fk = 0;
+                while (mf || fk < flen) {
+                    uint32_t ua[U]; int ul[U], ud[U], uk[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        if (fk >= flen && mf) {
+                            const int f = __ffs(mf) - 1; mf &= mf - 1;
+                            const uint32_t tf = __shfl_sync(kFull, t, f);
+                            fat = __shfl_sync(kFull, my, f); flen = (int)(tf & 511u); fdist = (int)(tf >> 9); fk = 0;
+                        }
+                        ua[u] = fat; ud[u] = fdist; uk[u] = fk; ul[u] = fk < flen ? flen : 0;
+                        fk += 32;
+                    }
+                    uint16_t r[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int k = uk[u] + lane;
+                        r[u] = 0;
+                        if (k < ul[u]) { const int q = (int)ua[u] - ud[u] + k; r[u] = q < 0 ? (uint16_t)(256 + kWin + q) : out[q]; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int k = uk[u] + lane;
+                        if (k < ul[u]) out[ua[u] + k] = r[u];
+                    }
+                }
+                __syncwarp();
+            }
             while (mm) {
                 const int f = __ffs(mm) - 1; mm &= mm - 1;
                 const uint32_t tf = __shfl_sync(kFull, t, f);
                 const uint32_t at = __shfl_sync(kFull, my, f);
                 const int len = (int)(tf & 511u), dist = (int)(tf >> 9);
-                if ((unsigned long long)dist > abs0 + at) { status = INF_BAD_DIST; break; }
                 if (dist == 1) {
-                    // a run (most bytes of a page sit in 258-long ones): one symbol, stored four at a time
-                    const uint32_t v = at == 0 ? (uint32_t)(256 + kWin - 1) : (uint32_t)out[at - 1];
+                    // a run (most bytes of a page sit in 258-long ones): one symbol, stored four at a time.  The symbol in front of it is
+                    // the previous token's if that was a literal (no load behind a store of a moment ago)
+                    const uint32_t tp = __shfl_sync(kFull, t, max(f - 1, 0));
+                    const uint32_t v = (f > 0 && (tp >> 31)) ? (tp & 255u) : at == 0 ? (uint32_t)(256 + kWin - 1) : (uint32_t)out[at - 1];
                     uint16_t* d = out + at;
                     const int head = min(len, (int)((4u - (uint32_t)(((uintptr_t)d >> 1) & 3u)) & 3u));
                     const int body = (len - head) >> 2, tail0 = head + 4 * body;
