@@ -47,7 +47,13 @@ namespace vcp {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kFastLL = 10, kFastD = 9;   // index bits of the lit/len and distance lookup tables
+#ifndef VCP_FAST_LL
+#define VCP_FAST_LL 10
+#endif
+#ifndef VCP_FAST_D
+#define VCP_FAST_D 9
+#endif
+constexpr int kFastLL = VCP_FAST_LL, kFastD = VCP_FAST_D;   // index bits of the lit/len and distance lookup tables
 constexpr int kWin = 32768;
 constexpr int kZWords = 256;              // compressed-input ring (words) the warp keeps filled ahead of lane 0's parser
 constexpr int kResolveChunk = 32768;      // positions per CTA of k_infl_resolve (keep in step with api.cu)
