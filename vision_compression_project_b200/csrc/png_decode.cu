@@ -519,7 +519,10 @@ __global__ void __launch_bounds__(256) k_infl_sort(const DecBatchD b) {
 // unit's parse on a candidate when its own token boundary falls exactly on the candidate's start AND it is inside the same block
 // (same header bit) — from there on the two parses are identical by construction.  A candidate that is not a true boundary is
 // walked over and never reached by the chain, like a false positive of the header scan.
-constexpr unsigned long long kSpecSync = 6144;
+#ifndef VCP_SPEC_SYNC
+#define VCP_SPEC_SYNC 6144
+#endif
+constexpr unsigned long long kSpecSync = VCP_SPEC_SYNC;
 
 __global__ void __launch_bounds__(128) k_infl_spec(const DecBatchD b) {
     __shared__ InflMem mem[4];
