@@ -750,6 +750,7 @@ void vcp_destroy(vcp_handle* h) {
         for (int i = 0; i < EV_COUNT; i++) if (L.ev[i]) cudaEventDestroy(L.ev[i]);
         if (L.stream) cudaStreamDestroy(L.stream);
     }
+    if (h->trace_t0) cudaEventDestroy(h->trace_t0);
     delete h;
 }
 
