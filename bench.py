@@ -283,6 +283,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     all_cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
     my_cores = sharding.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if not args.no_pin else []
+    kept_heap = sharding.keep_result_memory()              # results (Python bytes) reuse heap pages instead of faulting in fresh ones
     cores = host_cores() if world > 1 and not args.no_pin else cores      # of this rank from here on
 
     # ---- synthetic pages: drawn by spawned worker processes (FreeType rendering holds the GIL; spawn, not fork, so CUDA in this
@@ -600,7 +601,7 @@ def run_ours(args):
             "decode": decode_info,
             "configs": configs,
             "c4": c4,
-            "host": {"cores": len(all_cores) or cores, "cores_per_rank": len(my_cores) or cores, "pinned_ranks": bool(my_cores) and world > 1},
+            "host": {"cores": len(all_cores) or cores, "cores_per_rank": len(my_cores) or cores, "pinned_ranks": bool(my_cores) and world > 1, "allocator": "glibc mallopt: freed result blocks stay in the heap (sharding.keep_result_memory)" if kept_heap else "default"},
             "page_generation_s": round(t_gen, 1),
         }
         print(json.dumps(line), flush=True)

@@ -73,3 +73,13 @@ def test_gather_in_page_order_same_host_shared_memory():
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert out == [f"page-{i}".encode() * (i + 1) for i in range(n_pages)]
+
+
+def test_keep_result_memory_is_harmless():
+    """mallopt settings for result bytes: a bool comes back, and large allocations still come and go."""
+    from vision_compression_project_b200 import sharding
+    assert sharding.keep_result_memory() in (True, False)
+    blocks = [bytes(3 << 20) for _ in range(8)]
+    assert sum(len(b) for b in blocks) == 8 * (3 << 20)
+    del blocks
+    assert len(bytearray(5 << 20)) == 5 << 20
