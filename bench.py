@@ -16,6 +16,8 @@ Contract (task statement §④):  python bench.py --gpus N --steps K --warmup W 
       C1 the reference's recorded output/page_1.png, one call;  C3 256 letter-300 pages -> LANCZOS 1568;  C5 the 48-type mix;
       S150 the service's default 150-DPI pages  (N = 1)
       c4  = the 2,000-page document (25 % photo pages) sharded by page range over the N ranks through sharding.py: STRONG scaling.
+            A rank consumes its results batch by batch (the reference's workers write a page and drop it); every rank pins itself to
+            its share of the host cores and keeps freed result memory in its heap (sharding.pin_rank_to_cores / keep_result_memory).
 """
 from __future__ import annotations
 
